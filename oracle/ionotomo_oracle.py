@@ -1,0 +1,595 @@
+"""CPU oracle for the IonoTomo ray-integral forward model and its adjoint.
+
+THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it; nothing under ``ionotomo_b200/`` does.
+
+It is a plain NumPy (fp64) restatement of the reference's algorithm for the hot
+path.  Every function cites the reference file:line it follows (paths relative
+to ``/root/reference/src/ionotomo/``).  The arithmetic the reference delegates
+to SciPy (un-pinned: ``/root/reference/pip-requirements.txt:2``) is restated
+from SciPy's published algorithms:
+
+* ``scipy.interpolate.RegularGridInterpolator(method='linear')`` -> `rgi_linear`
+* ``scipy.integrate.simps(y, x, even='avg')`` (removed from SciPy >= 1.14; the
+  reference's own port is ``tomography/integrate.py:50-153``) -> `simps_avg`
+* ``scipy.integrate.odeint`` on the straight-ray RHS (``inversion/fermat.py:48-84``)
+  -> closed form in `integrate_ray_straight`
+
+Parity pinning (see ``tests/golden/make_golden.py`` and ``tests/test_oracle.py``):
+the oracle is checked against outputs of the *reference's own modules* executed
+in the build container (with stub modules for the absent astropy/h5py/dask and a
+NumPy shim of the TF1 ops used by ``tomography/integrate.py``), committed as
+``tests/golden/*.npz``, and against the installed SciPy where the algorithm is
+still shipped (RGI; ``simpson`` for odd N).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TECU = 1e13  # "TEC unit / km": inversion/forward_equation.py:12, gradient.py:14
+SPEED_OF_LIGHT = 299792458.0  # inversion/iterative_newton.py:15
+
+
+# --------------------------------------------------------------------------
+# quadrature: scipy.integrate.simps(y, x, even='avg'), last axis
+# --------------------------------------------------------------------------
+def _basic_simps(y, start, stop, x):
+    """Composite Simpson over triples starting at start, start+2, ... < stop.
+
+    Non-uniform-x form; follows tomography/integrate.py:50-74 (the reference's
+    port of SciPy's ``_basic_simps``), same operation order.
+    """
+    h = np.diff(x, axis=-1)
+    h0 = h[..., start:stop:2]
+    h1 = h[..., start + 1:stop + 1:2]
+    hsum = h0 + h1
+    hprod = h0 * h1
+    h0divh1 = h0 / h1
+    tmp = hsum / 6.0 * (y[..., start:stop:2] * (2 - 1.0 / h0divh1)
+                        + y[..., start + 1:stop + 1:2] * hsum * hsum / hprod
+                        + y[..., start + 2:stop + 2:2] * (2 - h0divh1))
+    return np.sum(tmp, axis=-1)
+
+
+def simps_avg(y, x):
+    """``simps(y, x, axis=-1, even='avg')`` as the reference ran it.
+
+    tomography/integrate.py:76-153; call sites inversion/forward_equation.py:28,
+    inversion/iterative_newton.py:119,179.  ``x`` has the shape of ``y`` or (N,).
+    """
+    y = np.asarray(y, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1 and y.ndim > 1:
+        x = np.broadcast_to(x, y.shape)
+    N = y.shape[-1]
+    if N % 2 == 0:
+        val = 0.0
+        result = 0.0
+        # 'first': Simpson on the first N-2 intervals, trapezoid on the last
+        last_dx = x[..., -1] - x[..., -2]
+        val = val + 0.5 * last_dx * (y[..., -1] + y[..., -2])
+        result = _basic_simps(y, 0, N - 3, x)
+        # 'last': trapezoid on the first interval, Simpson on the last N-2
+        first_dx = x[..., 1] - x[..., 0]
+        val = val + 0.5 * first_dx * (y[..., 1] + y[..., 0])
+        result = result + _basic_simps(y, 1, N - 2, x)
+        val = val / 2.0
+        result = result / 2.0
+        return result + val
+    return _basic_simps(y, 0, N - 2, x)
+
+
+def simps_weights(x):
+    """Weight vector w with ``simps_avg(y, x) == sum(w*y)`` (rule is linear in y).
+
+    Used by the exact-transpose adjoint.
+    Built by applying `simps_avg` to unit vectors so it is the same rule by
+    construction.
+    """
+    x = np.asarray(x, dtype=np.float64)
+    N = x.shape[-1]
+    eye = np.eye(N)
+    w = np.empty(x.shape, dtype=np.float64)
+    flat_x = x.reshape(-1, N)
+    flat_w = w.reshape(-1, N)
+    for r in range(flat_x.shape[0]):
+        flat_w[r] = simps_avg(eye, flat_x[r])
+    return w
+
+
+def simps_weights_fast(x):
+    """Closed-form Simpson-avg weights, vectorised over leading axes.
+
+    Same rule as `simps_weights` (asserted equal in tests/test_oracle.py) but
+    O(N) per ray, for the adjoint oracle at larger sizes.
+    """
+    x = np.asarray(x, dtype=np.float64)
+    N = x.shape[-1]
+    h = np.diff(x, axis=-1)
+    w = np.zeros_like(x)
+
+    def add_triples(start, stop, scale):
+        h0 = h[..., start:stop:2]
+        h1 = h[..., start + 1:stop + 1:2]
+        hsum = h0 + h1
+        c = hsum / 6.0
+        w[..., start:stop:2] += scale * c * (2 - h1 / h0)
+        w[..., start + 1:stop + 1:2] += scale * c * hsum * hsum / (h0 * h1)
+        w[..., start + 2:stop + 2:2] += scale * c * (2 - h0 / h1)
+
+    if N % 2 == 0:
+        add_triples(0, N - 3, 0.5)
+        add_triples(1, N - 2, 0.5)
+        w[..., -1] += 0.25 * h[..., -1]
+        w[..., -2] += 0.25 * h[..., -1]
+        w[..., 0] += 0.25 * h[..., 0]
+        w[..., 1] += 0.25 * h[..., 0]
+    else:
+        add_triples(0, N - 2, 1.0)
+    return w
+
+
+# --------------------------------------------------------------------------
+# grid interpolation: TriCubic.interp == scipy RGI(method='linear')
+# --------------------------------------------------------------------------
+def find_indices(grid, x):
+    """Per-axis (i, t) of SciPy's RGI: SURVEY Appendix A.1.
+
+    ``i = clip(searchsorted(grid, x, 'right') - 1, 0, n-2)``,
+    ``t = (x - g[i]) / (g[i+1] - g[i])``.  Reference restatement:
+    tomography/interpolation.py:145-195.
+    """
+    grid = np.asarray(grid, dtype=np.float64)
+    i = np.searchsorted(grid, x, side='right') - 1
+    i = np.clip(i, 0, grid.size - 2)
+    t = (x - grid[i]) / (grid[i + 1] - grid[i])
+    return i, t
+
+
+def rgi_linear(xvec, yvec, zvec, M, x, y, z, bounds_error=True):
+    """Trilinear sample of ``M`` at points (x, y, z).
+
+    geometry/tri_cubic.py:22,59,69-70 (``interp``, bounds_error=True raises
+    ValueError) and :71-75 (``extrapolate``: bounds_error=False,
+    fill_value=None keeps the clipped cell and lets t leave [0,1]).
+    Corner order and weight product order follow SciPy's ``_evaluate_linear``:
+    corners 000,001,...,111 (z fastest), weight ((wx*wy)*wz).
+    """
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    z = np.asarray(z, dtype=np.float64)
+    M = np.asarray(M, dtype=np.float64)
+    if bounds_error:
+        for d, (g, p) in enumerate(((xvec, x), (yvec, y), (zvec, z))):
+            if not np.logical_and(np.all(g[0] <= p), np.all(p <= g[-1])):
+                raise ValueError(
+                    "One of the requested xi is out of bounds in dimension %d" % d)
+    ix, tx = find_indices(xvec, x)
+    iy, ty = find_indices(yvec, y)
+    iz, tz = find_indices(zvec, z)
+    out = np.zeros(x.shape, dtype=np.float64)
+    for cx in (0, 1):
+        wx = tx if cx else 1 - tx
+        for cy in (0, 1):
+            wy = ty if cy else 1 - ty
+            for cz in (0, 1):
+                wz = tz if cz else 1 - tz
+                out = out + M[ix + cx, iy + cy, iz + cz] * ((wx * wy) * wz)
+    return out
+
+
+def bisection(array, value):
+    """Scalar binary search of geometry/tri_cubic.py:105-132 (same branches)."""
+    n = len(array)
+    if value < array[0]:
+        return -1
+    elif value > array[n - 1]:
+        return n
+    jl = 0
+    ju = n - 1
+    while ju - jl > 1:
+        jm = (ju + jl) >> 1
+        if value >= array[jm]:
+            jl = jm
+        else:
+            ju = jm
+    if value == array[0]:
+        return 0
+    elif value == array[n - 1]:
+        return n - 1
+    return jl
+
+
+def tci_inner(xvec, yvec, zvec, A, B):
+    """``TriCubic.inner``: triple simps of A*B (geometry/tri_cubic.py:61-67)."""
+    P = A * B
+    return simps_avg(simps_avg(simps_avg(P, zvec), yvec), xvec)
+
+
+# --------------------------------------------------------------------------
+# ray generation: Fermat.integrate_ray (straight, type 'z') + cast_ray
+# --------------------------------------------------------------------------
+def integrate_ray_straight(origin, direction, tmax, N):
+    """Closed form of ``Fermat.integrate_ray`` for the shipped straight case.
+
+    inversion/fermat.py:150-174 with ``euler_ode`` :48-84 at n=1, grad n=0
+    (type 'z'): xdot=px/pz, ydot=py/pz, zdot=1, sdot=1/pz; independent variable
+    z on ``linspace(z0, tmax, N)``.
+    """
+    x0, y0, z0 = origin
+    xd, yd, zd = direction
+    sdot = np.sqrt(xd ** 2 + yd ** 2 + zd ** 2)
+    px, py, pz = xd / sdot, yd / sdot, zd / sdot
+    z = np.linspace(z0, tmax, N)
+    dzs = z - z0
+    x = x0 + (px / pz) * dzs
+    y = y0 + (py / pz) * dzs
+    s = dzs / pz
+    return x, y, z, s
+
+
+def cast_ray(origins, directions, tmax, N):
+    """Vectorised ``cast_ray`` (geometry/calc_rays.py:61-96): (Na,Nt,Nd,3) ->
+    rays (Na,Nt,Nd,4,N), rows x,y,z,s.  Same formulas as `integrate_ray_straight`."""
+    origins = np.asarray(origins, dtype=np.float64)
+    directions = np.asarray(directions, dtype=np.float64)
+    sdot = np.sqrt(directions[..., 0] ** 2 + directions[..., 1] ** 2
+                   + directions[..., 2] ** 2)
+    px = directions[..., 0] / sdot
+    py = directions[..., 1] / sdot
+    pz = directions[..., 2] / sdot
+    z0 = origins[..., 2]
+    # np.linspace(z0, tmax, N) broadcast over rays: i*step + z0, last := tmax
+    step = (tmax - z0) / (N - 1)
+    idx = np.arange(N, dtype=np.float64)
+    z = idx * step[..., None] + z0[..., None]
+    z[..., -1] = tmax
+    dzs = z - z0[..., None]
+    rays = np.empty(origins.shape[:-1] + (4, N), dtype=np.float64)
+    rays[..., 0, :] = origins[..., 0, None] + (px / pz)[..., None] * dzs
+    rays[..., 1, :] = origins[..., 1, None] + (py / pz)[..., None] * dzs
+    rays[..., 2, :] = z
+    rays[..., 3, :] = dzs / pz[..., None]
+    return rays
+
+
+# --------------------------------------------------------------------------
+# TEC forward (generation A): inversion/forward_equation.py
+# --------------------------------------------------------------------------
+def ne_from_m(m, K_ne):
+    """``ne = exp(m) * (K_ne/TECU)`` per voxel: inversion/forward_equation.py:41-43."""
+    ne = np.exp(np.asarray(m, dtype=np.float64))
+    ne *= K_ne / TECU
+    return ne
+
+
+def tec(rays, xvec, yvec, zvec, ne, bounds_error=True):
+    """Per-ray ``simps(interp(ne; x,y,z), s)``: do_forward_equation,
+    inversion/forward_equation.py:13-33 (batched like iterative_newton.py:108,119)."""
+    nevec = rgi_linear(xvec, yvec, zvec, ne, rays[..., 0, :], rays[..., 1, :],
+                       rays[..., 2, :], bounds_error=bounds_error)
+    return simps_avg(nevec, rays[..., 3, :])
+
+
+def forward_equation(rays, K_ne, xvec, yvec, zvec, m, i0):
+    """dTEC (Na,Nt,Nd): inversion/forward_equation.py:36-51."""
+    t = tec(rays, xvec, yvec, zvec, ne_from_m(m, K_ne))
+    return t - t[i0, :, :]
+
+
+# --------------------------------------------------------------------------
+# phase forward (generation B): inversion/iterative_newton.py:86-127
+# --------------------------------------------------------------------------
+def _interp_batched(xvec, yvec, zvec, M, rays, reference_axis_scramble):
+    """``tci.interp(rays[...,0,:], rays[...,1,:], rays[...,2,:])`` on 4-D inputs.
+
+    geometry/tri_cubic.py:69-70 evaluates ``rgi(np.array([x,y,z]).T)`` and then
+    ``np.reshape(..., np.shape(x))``.  For 1-D inputs (generation A, one ray at a
+    time) that is the identity; for the (Na,Nt,Nd,Ns) inputs of generation B
+    (iterative_newton.py:108,157,160) ``.T`` reverses ALL axes and the reshape
+    does not undo it, so the reference returns the samples in a scrambled order
+    (element [a,t,d,s] is taken from the C-order flattening of the
+    (Ns,Nd,Nt,Na) array).  ``reference_axis_scramble=True`` reproduces that
+    bit-for-bit (used only to pin the oracle against the golden vectors); the
+    default is the evidently intended per-ray ordering.
+    """
+    v = rgi_linear(xvec, yvec, zvec, M, rays[..., 0, :], rays[..., 1, :], rays[..., 2, :])
+    if reference_axis_scramble:
+        v = np.reshape(np.transpose(v), v.shape)
+    return v
+
+
+def phase_forward_equation(mu, clock, const, xvec, yvec, zvec, rays, freqs,
+                           K=1e11, i0=0, reference_axis_scramble=False):
+    """Phase (Na,Nt,Nd,Nf): inversion/iterative_newton.py:86-127, same order."""
+    Na, Nt, Nd, _, Ns = rays.shape
+    freqs = np.asarray(freqs, dtype=np.float64)
+    Nf = freqs.shape[0]
+    ne = np.exp(mu).reshape(len(xvec), len(yvec), len(zvec)) * K
+    g = np.einsum("i,j,k,l,i->ijkl", np.ones(Na), np.ones(Nt), np.ones(Nd),
+                  np.ones(Nf), const)
+    ne_rays = _interp_batched(xvec, yvec, zvec, ne, rays, reference_axis_scramble)
+    for l in range(Nf):
+        a_ = 2 * np.pi * freqs[l]
+        dg = a_ * np.einsum("ij,k->ijk", clock, np.ones(Nd))
+        n_p = 1.2404e-2 * freqs[l] ** 2
+        n_rays = ne_rays / (-n_p)
+        n_rays += 1
+        np.sqrt(n_rays, out=n_rays)
+        n_rays *= -1
+        n_rays += 1
+        phi_ion = simps_avg(n_rays, rays[:, :, :, 3, :])
+        phi_ion -= phi_ion[i0, ...]
+        phi_ion *= (a_ / SPEED_OF_LIGHT)
+        dg -= phi_ion
+        g[:, :, :, l] += dg
+    return g
+
+
+def prior_penalty_mu(mu, mu_prior, xvec, yvec, zvec, rays, freqs, K=1e11, i0=0,
+                     reference_axis_scramble=False):
+    """inversion/iterative_newton.py:138-184."""
+    Na, Nt, Nd, _, Ns = rays.shape
+    freqs = np.asarray(freqs, dtype=np.float64)
+    Nf = freqs.shape[0]
+    shape = (len(xvec), len(yvec), len(zvec))
+    ne = np.exp(mu).reshape(shape) * K
+    r = np.zeros([Na, Nt, Nd, Nf], dtype=float)
+    ne_rays = _interp_batched(xvec, yvec, zvec, ne, rays, reference_axis_scramble)
+    dmu_rays = _interp_batched(xvec, yvec, zvec, (mu_prior - mu).reshape(shape), rays,
+                               reference_axis_scramble)
+    for l in range(Nf):
+        n_p = 1.2404e-2 * freqs[l] ** 2
+        a_ = 2 * np.pi * freqs[l]
+        b_ = a_ / (2 * n_p * SPEED_OF_LIGHT)
+        n_rays = ne_rays / (-n_p)
+        n_rays += 1
+        np.sqrt(n_rays, out=n_rays)
+        integrand = ne_rays / n_rays
+        integrand *= dmu_rays
+        ion = simps_avg(integrand, rays[:, :, :, 3, :])
+        ion -= ion[i0, ...]
+        ion *= b_
+        r[:, :, :, l] -= ion
+    return r
+
+
+# --------------------------------------------------------------------------
+# misfit and weighted residual
+# --------------------------------------------------------------------------
+def misfit(g, dobs, CdCt):
+    """``S = sum((g-dobs)^2/(CdCt+1e-15))/2``: inversion/line_search.py:48-49,
+    tests/test_inversion.py:34."""
+    return np.sum((g - dobs) ** 2 / (CdCt + 1e-15)) / 2.0
+
+
+def weighted_residual(g, dobs, CdCt):
+    """``dd = (g-dobs)/(CdCt+1e-15)``: inversion/gradient.py:33-37."""
+    return (g - dobs) / (CdCt + 1e-15)
+
+
+# --------------------------------------------------------------------------
+# adjoint A10: exact transpose of the dTEC forward
+# --------------------------------------------------------------------------
+def adjoint_ray_coefficients(dd, i0):
+    """c[ray] = dd[ray] - [ray is (i0,t,d)] * sum_i dd[i,t,d]  (transpose of the
+    ``tec - tec[i0]`` step, inversion/forward_equation.py:50)."""
+    c = np.array(dd, dtype=np.float64, copy=True)
+    c[i0, :, :] -= dd.sum(axis=0)
+    return c
+
+
+def backproject(rays, xvec, yvec, zvec, coef):
+    """acc[v] = sum_ray coef[ray] * sum_s w_s(ray) * phi_v(x_s): transpose of
+    `tec` w.r.t. the grid values (trilinear hats, Simpson-avg weights)."""
+    nx, ny, nz = len(xvec), len(yvec), len(zvec)
+    ix, tx = find_indices(xvec, rays[..., 0, :])
+    iy, ty = find_indices(yvec, rays[..., 1, :])
+    iz, tz = find_indices(zvec, rays[..., 2, :])
+    w = simps_weights_fast(rays[..., 3, :]) * np.asarray(coef)[..., None]
+    acc = np.zeros(nx * ny * nz, dtype=np.float64)
+    for cx in (0, 1):
+        wx = tx if cx else 1 - tx
+        for cy in (0, 1):
+            wy = ty if cy else 1 - ty
+            for cz in (0, 1):
+                wz = tz if cz else 1 - tz
+                flat = ((ix + cx) * ny + (iy + cy)) * nz + (iz + cz)
+                acc += np.bincount(flat.ravel(), weights=(w * ((wx * wy) * wz)).ravel(),
+                                   minlength=acc.size)
+    return acc.reshape(nx, ny, nz)
+
+
+def gradient_exact(rays, g, dobs, i0, K_ne, xvec, yvec, zvec, m, CdCt):
+    """dS/dm for S = misfit(forward_equation(m)): the gradient the reference's
+    finite-difference protocol (tests/test_inversion.py:71-87) checks.
+    ``ne[v] * backproject(adjoint coefficients of dd)`` (chain rule through
+    ``ne = K exp(m)/TECU``)."""
+    dd = weighted_residual(g, dobs, CdCt)
+    c = adjoint_ray_coefficients(dd, i0)
+    return ne_from_m(m, K_ne) * backproject(rays, xvec, yvec, zvec, c)
+
+
+# --------------------------------------------------------------------------
+# adjoint A8: chord-length "ray dirac" gradient (geometry/ray_dirac.py,
+# geometry/slab_method.py, inversion/gradient.py:15-20), sparse restatement
+# --------------------------------------------------------------------------
+def slab_method_ray_box(r0, n, inv_n, x_min, y_min, z_min, x_max, y_max, z_max):
+    """geometry/slab_method.py:19-58 (returns only the chord length)."""
+    def axis(lo, hi, o, inv):
+        with np.errstate(invalid='ignore'):
+            t1 = (lo - o) * inv
+            t2 = (hi - o) * inv
+        if np.isnan(t1):
+            t1 = 0.
+        if np.isnan(t2):
+            t2 = 0.
+        return min(t1, t2), max(t1, t2)
+    tmin_x, tmax_x = axis(x_min, x_max, r0[0], inv_n[0])
+    tmin_y, tmax_y = axis(y_min, y_max, r0[1], inv_n[1])
+    tmin_z, tmax_z = axis(z_min, z_max, r0[2], inv_n[2])
+    tmax = max(tmin_x, tmin_y, tmin_z)   # entry (reference names are swapped)
+    tmin = min(tmax_x, tmax_y, tmax_z)   # exit
+    if tmax < tmin and tmax > 0:
+        return float(np.linalg.norm(n * (tmax - tmin)))
+    return 0.0
+
+
+def ray_dirac_sparse(ray, xvec, yvec, zvec):
+    """One ray's ``dirac_ray`` of geometry/ray_dirac.py:16-33 as {(xi,yi,zi): ds}.
+
+    ``ray`` is (4, Ns).  The line is first->last point (ray_dirac.py:21); for
+    every sample the +-1 cell neighbourhood of its bisection cell is tested
+    against the cell-centred box (ray_dirac.py:24-31); the value is ASSIGNED
+    (idempotent), so a dict reproduces the dense array exactly.
+    """
+    x, y, z = xvec, yvec, zvec
+    dx, dy, dz = x[1] - x[0], y[1] - y[0], z[1] - z[0]
+    r0 = np.array(ray[0:3, 0], dtype=np.float64)
+    n = np.array(ray[0:3, -1] - ray[0:3, 0], dtype=np.float64)
+    n /= np.linalg.norm(n)
+    with np.errstate(divide='ignore'):
+        inv_n = 1. / n
+    out = {}
+    Ns = ray.shape[1]
+    for s in range(Ns):
+        xi_c = bisection(x, ray[0, s])
+        yi_c = bisection(y, ray[1, s])
+        zi_c = bisection(z, ray[2, s])
+        for xi in range(max(0, xi_c - 1), min(len(x), xi_c + 2)):
+            for yi in range(max(0, yi_c - 1), min(len(y), yi_c + 2)):
+                for zi in range(max(0, zi_c - 1), min(len(z), zi_c + 2)):
+                    if (xi, yi, zi) in out:
+                        continue  # assignment of the same value
+                    out[(xi, yi, zi)] = slab_method_ray_box(
+                        r0, n, inv_n, x[xi] - dx / 2., y[yi] - dy / 2., z[zi] - dz / 2.,
+                        x[xi] + dx / 2., y[yi] + dy / 2., z[zi] + dz / 2.)
+    return out
+
+
+def gradient_chord(rays, g, dobs, i0, K_ne, xvec, yvec, zvec, m, CdCt,
+                   bug_compat=False):
+    """Adjoint A8: ``G[v] = sum_ray l(ray,v) * ne[v] * dd[ray]``
+    (inversion/gradient.py:15-20 einsum "ijklm,klm,ij->klm" over
+    geometry/ray_dirac.py), dd as gradient.py:33-37.  ``bug_compat`` applies the
+    reference's ``gradient -= gradient[i0,...]`` (gradient.py:55), which indexes
+    grid-x rather than the antenna axis."""
+    dd = weighted_residual(g, dobs, CdCt)
+    ne = ne_from_m(m, K_ne)
+    acc = np.zeros_like(ne)
+    Na, Nt, Nd = rays.shape[:3]
+    for i in range(Na):
+        for j in range(Nt):
+            for k in range(Nd):
+                for (xi, yi, zi), ds in ray_dirac_sparse(rays[i, j, k], xvec, yvec, zvec).items():
+                    acc[xi, yi, zi] += ds * dd[i, j, k]
+    grad = acc * ne
+    if bug_compat:
+        grad = grad - grad[i0, ...]
+    return grad
+
+
+# --------------------------------------------------------------------------
+# line search: inversion/line_search.py
+# --------------------------------------------------------------------------
+def vertex(x1, x2, x3, y1, y2, y3):
+    """Vertex of the parabola through three points (inversion/line_search.py:13-43),
+    restated in Lagrange form (algebraically identical; checked against the
+    reference's expression in tests/test_oracle.py via the golden file)."""
+    denom = (x1 - x2) * (x1 - x3) * (x2 - x3)
+    A = (x3 * (y2 - y1) + x2 * (y1 - y3) + x1 * (y3 - y2)) / denom
+    B = (x3 * x3 * (y1 - y2) + x2 * x2 * (y3 - y1) + x1 * x1 * (y2 - y3)) / denom
+    C = (x2 * x3 * (x2 - x3) * y1 + x3 * x1 * (x3 - x1) * y2 + x1 * x2 * (x1 - x2) * y3) / denom
+    xv = -B / (2 * A)
+    return xv, C - B * B / (4 * A)
+
+
+def line_search(rays, K_ne, xvec, yvec, zvec, m, i0, gradient, g, dobs, CdCt):
+    """inversion/line_search.py:45-100 (without the plotting)."""
+    S0 = misfit(g, dobs, CdCt)
+    ep_a, S_a = [], []
+    S = S0
+    dd = (g - dobs) / (CdCt + 1e-15)
+    ep = 1e-3
+    g_ = forward_equation(rays, K_ne, xvec, yvec, zvec, m - ep * gradient, i0)
+    Gm = (g - g_) / ep
+    numerator = 2. * np.sum(dd * Gm)
+    denominator = np.sum(Gm * Gm / (CdCt + 1e-15))
+    epsilon_n = np.abs(numerator / denominator)
+    it = 0
+    while S >= S0 or it < 3:
+        epsilon_n /= 2.
+        g2 = forward_equation(rays, K_ne, xvec, yvec, zvec, m - epsilon_n * gradient, i0)
+        S = misfit(g2, dobs, CdCt)
+        ep_a.append(epsilon_n)
+        S_a.append(S)
+        if not np.isnan(S):
+            it += 1
+        if len(ep_a) > 200:
+            break
+    epsilon_n, S_p = vertex(*ep_a[-3:], *S_a[-3:])
+    g3 = forward_equation(rays, K_ne, xvec, yvec, zvec, m - epsilon_n * gradient, i0)
+    S = misfit(g3, dobs, CdCt)
+    return epsilon_n, S, (S / S0 - 1.)
+
+
+# --------------------------------------------------------------------------
+# synthetic ionosphere (benchmark inputs): ionosphere/iri.py:20-68,
+# ionosphere/simulation.py:45-112, inversion/initial_model.py:38-41,75-84
+# --------------------------------------------------------------------------
+def a_priori_model_(h, zenith, thin_f=False):
+    """Four Chapman layers D/E/F1/F2 vs solar zenith angle: ionosphere/iri.py:20-68."""
+    def peak_density(n0, dn, tau, b, zenith):
+        y = zenith / tau
+        return n0 + dn * np.exp(-y ** 2) / (1. + y ** (2 * b))
+
+    def peak_height(z0, dz, rho, chi0, zenith):
+        return z0 + dz / (1. + np.exp(-(zenith - chi0) / rho))
+
+    def layer_density(nm, zm, H, z):
+        y = (z - zm) / H
+        return nm * np.exp(1. / 2. * (1. - y - np.exp(-y)))
+    y = zenith / 58.
+    nm_d = 4e8 + 5.9e8 * np.exp(-y ** 2) if y < 1 else 4e8
+    n_d = layer_density(nm_d, peak_height(81., 7., 7.46, 100., zenith), 8., h)
+    n_e = layer_density(peak_density(1.6e9, 1.6e11, 87., 8.7, zenith), 110., 11., h)
+    H_f1 = 20. if thin_f else 40.
+    n_f1 = layer_density(peak_density(2.0e11, 9.1e10, 54., 13.6, zenith), 185., H_f1, h)
+    H_f2 = 27.5 if thin_f else 55.
+    n_f2 = layer_density(peak_density(7.7e10, 4.4e11, 111., 4.8, zenith),
+                         peak_height(242., 75., 7.46, 96., zenith), H_f2, h)
+    return np.atleast_1d(n_d + n_e + n_f1 + n_f2)
+
+
+def turbulent_realization(xvec, yvec, zvec, sigma, corr, seed):
+    """Matern-5/2 Gaussian random field: IonosphereSimulation.__init__ and
+    .realization, ionosphere/simulation.py:45-112 (same spectrum, same FFT
+    de-shift by sign flips, same rescale to sigma)."""
+    from math import gamma
+    nx, ny, nz = np.size(xvec), np.size(yvec), np.size(zvec)
+    dx, dy, dz = xvec[1] - xvec[0], yvec[1] - yvec[0], zvec[1] - zvec[0]
+    sx, sy, sz = 1. / (dx * nx), 1. / (dy * ny), 1. / (dz * nz)
+    lvec = np.linspace(0, sx * nx / 2., nx)
+    mvec = np.linspace(0, sy * ny / 2., ny)
+    nvec = np.linspace(0, sz * nz / 2., nz)
+    L, Mm, Nn = np.meshgrid(lvec, mvec, nvec, indexing='ij')
+    s2 = L ** 2
+    s2 += Mm ** 2
+    s2 += Nn ** 2
+    s2 = np.fft.ifftshift(s2)
+    n = 3.
+    nu = 5 / 2.
+    S = sigma ** 2 * 2 ** n * np.pi ** (n / 2.) * gamma(nu + n / 2.) * (2 * nu) ** nu \
+        / gamma(nu) / corr ** (2 * nu) * (2 * nu / corr ** 2 + 4 * np.pi ** 2 * s2) ** (-nu - n / 2.)
+    S = np.sqrt(S)
+    if seed is not None:
+        np.random.seed(seed)
+    Z = np.random.normal(size=S.shape) + 1j * np.random.normal(size=S.shape)
+    Y = S * Z
+    B = (np.fft.ifftn(Y, (nx, ny, nz), axes=(0, 1, 2))).real * (sx * nx) * (sy * ny) * (sz * nz)
+    B[::2, :, :] *= -1
+    B[:, ::2, :] *= -1
+    B[:, :, ::2] *= -1
+    B *= sigma / np.std(B)
+    return B

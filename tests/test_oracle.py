@@ -1,0 +1,190 @@
+"""The oracle against (a) golden vectors produced by the reference's own modules
+(tests/golden/make_golden.py), (b) the installed SciPy where it still ships the
+algorithm.  CPU only."""
+import numpy as np
+import pytest
+import scipy.integrate
+from scipy.interpolate import RegularGridInterpolator
+
+from oracle import ionotomo_oracle as O
+
+RTOL = 1e-12  # oracle vs reference-generated vectors (same algorithm, fp64)
+
+
+def test_interp_matches_reference_tricubic(golden):
+    g = golden("tricubic")
+    x, y, z = np.meshgrid(g["xvec"], g["yvec"], g["zvec"], indexing="ij")
+    M = x * y * z + x - y - 2 * z + x ** 2          # tests/test_tricubic.py:11
+    res = O.rgi_linear(g["xvec"], g["yvec"], g["zvec"], M, g["pts"], g["pts"], g["pts"])
+    np.testing.assert_allclose(res, g["res_batch"], rtol=RTOL, atol=1e-15)
+    # batch == per-point, the reference's own protocol (tests/test_tricubic.py:21-27)
+    np.testing.assert_array_equal(g["res_batch"][:50], g["res_scalar"])
+    one = np.array([O.rgi_linear(g["xvec"], g["yvec"], g["zvec"], M, p, p, p) for p in g["pts"][:50]])
+    np.testing.assert_array_equal(one, res[:50])
+    res = O.rgi_linear(g["xvec"], g["yvec"], g["zvec"], M, g["px"], g["py"], g["pz"])
+    np.testing.assert_allclose(res, g["res_rand"], rtol=RTOL, atol=1e-15)
+    res = O.rgi_linear(g["xvec"], g["yvec"], g["zvec"], M, g["ex"], g["ey"], g["ez"],
+                       bounds_error=False)
+    np.testing.assert_allclose(res, g["res_extrap"], rtol=RTOL, atol=1e-15)
+    assert bool(g["oob_raises"])
+    with pytest.raises(ValueError):
+        O.rgi_linear(g["xvec"], g["yvec"], g["zvec"], M, np.array([0.5, 1.2]),
+                     np.array([0.5, 0.5]), np.array([0.5, 0.5]))
+    with pytest.raises(ValueError):
+        O.rgi_linear(g["xvec"], g["yvec"], g["zvec"], M, np.array([np.nan]),
+                     np.array([0.5]), np.array([0.5]))
+
+
+def test_bisection_matches_reference(golden):
+    g = golden("tricubic")
+    idx = np.array([O.bisection(g["xvec"], v) for v in g["bvals"]])
+    np.testing.assert_array_equal(idx, g["bidx"])
+
+
+def test_interp_matches_installed_scipy():
+    rng = np.random.RandomState(0)
+    xv = np.sort(rng.uniform(0, 1, 13)); yv = np.linspace(-1, 2, 9); zv = np.linspace(0, 5, 17)
+    M = rng.normal(size=(13, 9, 17))
+    p = np.stack([rng.uniform(xv[0], xv[-1], 300), rng.uniform(-1, 2, 300), rng.uniform(0, 5, 300)], -1)
+    rgi = RegularGridInterpolator((xv, yv, zv), M, bounds_error=True)
+    np.testing.assert_allclose(O.rgi_linear(xv, yv, zv, M, p[:, 0], p[:, 1], p[:, 2]), rgi(p),
+                               rtol=1e-13, atol=1e-14)
+    rge = RegularGridInterpolator((xv, yv, zv), M, bounds_error=False, fill_value=None)
+    q = p * 1.7 - 0.4
+    np.testing.assert_allclose(O.rgi_linear(xv, yv, zv, M, q[:, 0], q[:, 1], q[:, 2], bounds_error=False),
+                               rge(q), rtol=1e-12, atol=1e-13)
+
+
+def test_simps_odd_matches_installed_scipy():
+    rng = np.random.RandomState(1)
+    x = np.sort(rng.uniform(size=(6, 5, 31)), axis=-1)
+    y = rng.normal(size=x.shape)
+    np.testing.assert_allclose(O.simps_avg(y, x), scipy.integrate.simpson(y, x=x, axis=-1),
+                               rtol=1e-12, atol=1e-14)
+
+
+def test_simps_even_is_avg_rule():
+    """even='avg' composed from installed-SciPy pieces (odd sub-ranges + trapezoids)."""
+    rng = np.random.RandomState(2)
+    for N in (2 + 2, 10, 30, 128):
+        x = np.sort(rng.uniform(size=(7, N)), axis=-1)
+        y = rng.normal(size=x.shape)
+        first = scipy.integrate.simpson(y[:, :-1], x=x[:, :-1], axis=-1) \
+            + 0.5 * (x[:, -1] - x[:, -2]) * (y[:, -1] + y[:, -2])
+        last = scipy.integrate.simpson(y[:, 1:], x=x[:, 1:], axis=-1) \
+            + 0.5 * (x[:, 1] - x[:, 0]) * (y[:, 1] + y[:, 0])
+        np.testing.assert_allclose(O.simps_avg(y, x), 0.5 * (first + last), rtol=1e-12, atol=1e-14)
+    # and it is NOT modern simpson for even N: the distinction matters
+    x = np.linspace(0, 1, 30); y = np.exp(3 * x)
+    assert abs(O.simps_avg(y, x) - scipy.integrate.simpson(y, x=x)) > 1e-8
+
+
+def test_simps_weights():
+    rng = np.random.RandomState(3)
+    for N in (3, 4, 5, 9, 10, 31, 64):
+        x = np.sort(rng.uniform(size=(3, N)), axis=-1)
+        y = rng.normal(size=x.shape)
+        w = O.simps_weights(x)
+        np.testing.assert_allclose((w * y).sum(-1), O.simps_avg(y, x), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(O.simps_weights_fast(x), w, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("tag", ["odd", "even"])
+def test_rays_match_reference_odeint(golden, tag):
+    g = golden("forward_" + tag)
+    Ns = int(g["Ns"])
+    rays = O.cast_ray(g["origins"], g["directions"], float(g["tmax"]), Ns)
+    # LSODA (rtol=atol~1.5e-8) vs closed form: SURVEY Appendix A.3 measured 7e-13 km
+    np.testing.assert_allclose(rays, g["rays"], rtol=0, atol=1e-9)
+    one = np.stack(O.integrate_ray_straight(g["single_origin"], g["single_direction"], float(g["tmax"]), Ns))
+    np.testing.assert_allclose(one, g["single"], rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(one, rays[1, 0, 2])
+
+
+@pytest.mark.parametrize("tag", ["odd", "even"])
+def test_forward_matches_reference(golden, tag):
+    g = golden("forward_" + tag)
+    rays = g["rays"]
+    dtec = O.forward_equation(rays, float(g["K_ne"]), g["xvec"], g["yvec"], g["zvec"], g["m"], int(g["i0"]))
+    scale = np.abs(g["dtec"]).max()
+    np.testing.assert_allclose(dtec, g["dtec"], rtol=0, atol=1e-11 * scale)
+    t0 = O.tec(rays[0], g["xvec"], g["yvec"], g["zvec"], O.ne_from_m(g["m"], float(g["K_ne"])))
+    np.testing.assert_allclose(t0, g["tec_a0"], rtol=RTOL)
+
+
+@pytest.mark.parametrize("tag", ["odd", "even"])
+def test_phase_forward_matches_reference(golden, tag):
+    g = golden("forward_" + tag)
+    ph = O.phase_forward_equation(g["mu"], g["clock"], g["const"], g["xvec"], g["yvec"], g["zvec"],
+                                  g["rays"], g["freqs"], K=1e11, i0=int(g["i0"]),
+                                  reference_axis_scramble=True)
+    np.testing.assert_allclose(ph, g["phase"], rtol=1e-10, atol=1e-10 * np.abs(g["phase"]).max())
+    pen = O.prior_penalty_mu(g["mu"], g["mu_prior"], g["xvec"], g["yvec"], g["zvec"], g["rays"],
+                             g["freqs"], K=1e11, i0=int(g["i0"]), reference_axis_scramble=True)
+    np.testing.assert_allclose(pen, g["penalty"], rtol=1e-10, atol=1e-10 * np.abs(g["penalty"]).max())
+
+
+def test_chord_adjoint_matches_reference(golden):
+    g = golden("chord")
+    rays = g["rays"]
+    Na, _, Nd = rays.shape[:3]
+    dense = np.zeros_like(g["dirac"])
+    for i in range(Na):
+        for k in range(Nd):
+            for (xi, yi, zi), ds in O.ray_dirac_sparse(rays[i, 0, k], g["xvec"], g["yvec"], g["zvec"]).items():
+                dense[i, k, xi, yi, zi] = ds
+    np.testing.assert_allclose(dense, g["dirac"], rtol=1e-12, atol=1e-12)
+    # do_gradient(rays, dd, ne_tci,...) = einsum(dirac, ne, dd): with CdCt+1e-15 == 1 and
+    # g-dobs == dd, K_ne e^m / TECU == ne
+    dd = g["dd"][:, None, :]
+    grad = O.gradient_chord(rays, dd, np.zeros_like(dd), 0, 1e13, g["xvec"], g["yvec"], g["zvec"],
+                            np.log(g["ne"]), np.ones_like(dd) - 1e-15)
+    np.testing.assert_allclose(grad, g["G"], rtol=1e-10, atol=1e-10 * np.abs(g["G"]).max())
+
+
+def test_line_search_matches_reference(golden):
+    g = golden("line_search")
+    np.testing.assert_allclose(O.vertex(*g["vx"][:3], *g["vy"][:3]), g["v1"], rtol=1e-9)
+    np.testing.assert_allclose(O.vertex(*g["vx"][3:], *g["vy"][3:]), g["v2"], rtol=1e-7)
+    eps, S, red = O.line_search(g["rays"], float(g["K_ne"]), g["xvec"], g["yvec"], g["zvec"], g["m0"],
+                                0, g["grad"], g["g"], g["dobs"], g["CdCt"])
+    np.testing.assert_allclose(eps, float(g["eps"]), rtol=1e-6)
+    np.testing.assert_allclose(S, float(g["S"]), rtol=1e-6)
+    np.testing.assert_allclose(O.misfit(g["g"], g["dobs"], g["CdCt"]), float(g["S0"]), rtol=1e-12)
+
+
+def test_synthetic_matches_reference(golden):
+    g = golden("synthetic")
+    dm = O.turbulent_realization(g["xvec"], g["yvec"], g["zvec"], np.log(2.), 20., 1234)
+    np.testing.assert_allclose(dm, g["dm"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(O.a_priori_model_(g["h"], 45.), g["chap45"], rtol=1e-13)
+    np.testing.assert_allclose(O.a_priori_model_(g["h"], 80., thin_f=True), g["chap80"], rtol=1e-13)
+
+
+def test_exact_adjoint_dot_product_and_fd(golden):
+    """A10 is the transpose of the dTEC forward: <G x, y> == <x, G^T y>, and it is the
+    gradient the reference's FD protocol checks (tests/test_inversion.py:71-87)."""
+    g = golden("forward_even")
+    xv, yv, zv, rays = g["xvec"], g["yvec"], g["zvec"], g["rays"]
+    i0 = int(g["i0"])
+    rng = np.random.RandomState(5)
+    xfield = rng.normal(size=g["ne"].shape)
+    yv_ = rng.normal(size=rays.shape[:3])
+    t = O.tec(rays, xv, yv, zv, xfield)
+    Gx = t - t[i0]
+    GTy = O.backproject(rays, xv, yv, zv, O.adjoint_ray_coefficients(yv_, i0))
+    assert abs((Gx * yv_).sum() - (xfield * GTy).sum()) <= 1e-12 * abs((Gx * yv_).sum())
+    K_ne, m = float(g["K_ne"]), g["m"]
+    dobs = g["dtec"] + 0.01 * rng.normal(size=g["dtec"].shape)
+    CdCt = np.full(dobs.shape, 0.01 ** 2)
+    gm = O.forward_equation(rays, K_ne, xv, yv, zv, m, i0)
+    grad = O.gradient_exact(rays, gm, dobs, i0, K_ne, xv, yv, zv, m, CdCt)
+    S0 = O.misfit(gm, dobs, CdCt)
+    idx = np.argsort(-np.abs(grad).ravel())[:5]
+    for f in idx:
+        v = np.unravel_index(f, m.shape)
+        mp = m.copy(); mp[v] += 1e-6
+        mm = m.copy(); mm[v] -= 1e-6
+        fd = (O.misfit(O.forward_equation(rays, K_ne, xv, yv, zv, mp, i0), dobs, CdCt)
+              - O.misfit(O.forward_equation(rays, K_ne, xv, yv, zv, mm, i0), dobs, CdCt)) / 2e-6
+        assert abs(fd - grad[v]) <= 1e-5 * abs(grad[v]) + 1e-9 * abs(S0)
