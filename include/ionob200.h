@@ -1,0 +1,117 @@
+/*
+ * ionob200.h -- C ABI of libionob200.so: the B200 (sm_100a) implementation of
+ * IonoTomo's ray-integral forward model and its adjoint.
+ *
+ * This is the drop-in boundary for that path.  The reference has no FFI layer
+ * (it is 100 % Python); each entry point below replaces the arithmetic of one
+ * reference function, cited as file:line under /root/reference/src/ionotomo/.
+ * The Python shims in ionotomo_b200/ bind these with ctypes and keep the
+ * reference's signatures; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array is fp64, C-order, DEVICE memory
+ *     unless the parameter name ends in _host;
+ *   - the caller owns every buffer; outputs are fully overwritten;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*,
+ *     NULL = legacy default stream) and re-entrant; the only library-owned
+ *     state is the opaque grid handle;
+ *   - return value: IONO_OK, or an error code with text in iono_last_error()
+ *     (thread-local).
+ */
+#ifndef IONOB200_H
+#define IONOB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IONO_OK 0
+#define IONO_EBADARG 1 /* NULL pointer, non-positive size, non-monotone axis ... */
+#define IONO_EOOB 2    /* reserved for host-side wrappers: a sample left the grid */
+#define IONO_ECUDA 3   /* CUDA runtime error, see iono_last_error() */
+
+#define IONO_ABI_VERSION 1
+
+/* Ray traversal order used by the forward/adjoint kernels (which rays the warps
+ * of one CTA process together).  Results do not depend on it (forward) or only
+ * to summation order (adjoint); it only steers L1/L2 locality. */
+#define IONO_ORDER_NATURAL 0 /* (a,t,d) with d fastest: consecutive warps take consecutive directions */
+#define IONO_ORDER_TIME 1    /* consecutive warps take consecutive times of one (antenna, direction) */
+#define IONO_ORDER_ANTENNA 2 /* consecutive warps take consecutive antennas of one (time, direction) */
+
+int iono_version(void);
+const char *iono_last_error(void);
+
+/* ---- grid handle -------------------------------------------------------
+ * Axis vectors of a TriCubic (geometry/tri_cubic.py:13-47).  Host pointers:
+ * they are a few KB and live on the host in the reference.  Builds the device
+ * cell tables {g[i], 1/(g[i+1]-g[i])} used by every interpolating kernel and
+ * records whether each axis is uniform (direct cell index) or needs bisection
+ * (geometry/tri_cubic.py:105-132). */
+typedef struct iono_grid *iono_grid_t;
+int iono_grid_create(const double *xvec_host, const double *yvec_host, const double *zvec_host,
+                     int nx, int ny, int nz, iono_grid_t *grid_out);
+int iono_grid_destroy(iono_grid_t grid);
+/* 1 if all three axes take the direct-index fast path */
+int iono_grid_is_uniform(iono_grid_t grid);
+
+/* ---- per-voxel transforms ----------------------------------------------
+ * ne_out[v] = exp(m[v]) * scale, scale = K_ne/TECU:
+ * inversion/forward_equation.py:41-43, inversion/gradient.py:49-51. */
+int iono_ne_from_m_f64(const double *m, int64_t nvox, double scale, double *ne_out, void *stream);
+/* out[v] = a[v] * b[v] (chain rule ne[v] * backprojection) */
+int iono_mul_f64(const double *a, const double *b, int64_t n, double *out, void *stream);
+
+/* ---- ray generation ----------------------------------------------------
+ * Straight rays, independent variable z: Fermat.integrate_ray
+ * (inversion/fermat.py:150-174 with euler_ode :48-84 at n=1) for every ray of
+ * cast_ray (geometry/calc_rays.py:61-96).
+ * origins, directions: (nrays,3); rays_out: (nrays,4,Ns) rows x,y,z,s. */
+int iono_cast_rays_straight_f64(const double *origins, const double *directions, int64_t nrays,
+                                double tmax, int Ns, double *rays_out, void *stream);
+
+/* ---- point-wise interpolation -------------------------------------------
+ * TriCubic.interp / .extrapolate (geometry/tri_cubic.py:69-75) == SciPy
+ * RegularGridInterpolator(method='linear').  M: (nx,ny,nz).  oob_count (device,
+ * 1 element) receives the number of points outside [g[0],g[-1]] on any axis or
+ * NaN -- the caller raises ValueError when extrapolate==0 and it is non-zero. */
+int iono_tci_interp_f64(iono_grid_t grid, const double *M, const double *x, const double *y,
+                        const double *z, int64_t n, int extrapolate, double *out,
+                        unsigned long long *oob_count, void *stream);
+
+/* ---- TEC forward ---------------------------------------------------------
+ * tec_out[ray] = simps(interp(ne; x,y,z), s) with simps = scipy's old
+ * even='avg' rule: do_forward_equation (inversion/forward_equation.py:13-33).
+ * rays: (Na,Nt,Nd,4,Ns); tec_out: (Na,Nt,Nd).  One warp per ray. */
+int iono_tec_forward_f64(iono_grid_t grid, const double *ne, const double *rays, int Na, int Nt,
+                         int Nd, int Ns, int order, double *tec_out,
+                         unsigned long long *oob_count, void *stream);
+/* dtec_out = tec - tec[i0,:,:] (inversion/forward_equation.py:50); may alias tec */
+int iono_dtec_f64(const double *tec, int Na, int Nt, int Nd, int i0, double *dtec_out, void *stream);
+
+/* ---- adjoint (exact transpose of the dTEC forward) ----
+ * coef_out[a,t,d] = dd[a,t,d] - [a==i0] * sum_i dd[i,t,d],
+ * dd = (g-dobs)/(CdCt+1e-15) (inversion/gradient.py:33-37). */
+int iono_adjoint_coef_f64(const double *g, const double *dobs, const double *CdCt, int Na, int Nt,
+                          int Nd, int i0, double *coef_out, void *stream);
+/* acc[v] (+)= sum_ray coef[ray] sum_s w_s(ray) phi_v(x_s); zero_first!=0 clears
+ * acc before accumulating.  acc: (nx,ny,nz).  The voxel gradient of the misfit
+ * is ne[v]*acc[v] (iono_mul_f64) after the cross-GPU sum of acc. */
+int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
+                         const double *coef, int order, int zero_first, double *acc,
+                         unsigned long long *oob_count, void *stream);
+
+/* ---- misfit ---------------------------------------------------------------
+ * out[0] = sum((g-dobs)^2/(CdCt+1e-15))/2 (inversion/line_search.py:48-49).
+ * Deterministic two-stage reduction; `scratch` needs iono_misfit_scratch_elems()
+ * doubles. */
+int64_t iono_misfit_scratch_elems(void);
+int iono_misfit_f64(const double *g, const double *dobs, const double *CdCt, int64_t n,
+                    double *scratch, double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IONOB200_H */

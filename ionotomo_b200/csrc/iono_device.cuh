@@ -1,0 +1,204 @@
+// Device-side building blocks shared by the ray-integral kernels (sm_100a).
+//
+//  * Axis tables and cell lookup  == SciPy RegularGridInterpolator(method='linear')
+//    index/weight semantics (reference: geometry/tri_cubic.py:22,69-75;
+//    SURVEY.md Appendix A.1).
+//  * Simpson weights              == scipy.integrate.simps(y, x, even='avg')
+//    (reference: inversion/forward_equation.py:28; restated by the reference in
+//    tomography/integrate.py:50-153), as a per-sample
+//    weight so that forward (gather) and adjoint (scatter) share one rule.
+//  * Warp-private TMA bulk-copy ring for streaming the materialised rays.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace iono {
+
+// ---------------------------------------------------------------------------
+// Grid description passed by value to kernels.
+// tab[i] = { g[i], 1/(g[i+1]-g[i]) } for i < n-1, tab[n-1] = { g[n-1], 0 }.
+// ---------------------------------------------------------------------------
+struct Axis {
+    const double2 *tab;  // device
+    int n;
+    int uniform;      // 1: direct cell index, 0: bisection
+    double inv_d;     // (n-1)/(g[n-1]-g[0])               (uniform only)
+    double c_guess;   // -g[0]*inv_d - 0.5                 (uniform only)
+    double g0, glast;
+};
+
+struct Grid {
+    Axis ax[3];
+};
+
+// 2^52 + 2^51: adding it rounds a double in (-2^31, 2^31) to the nearest integer,
+// which then sits in the low 32 bits of the mantissa.
+#define IONO_MAGIC 6755399441055744.0
+
+// Cell index i and in-cell coordinate t of SciPy's RGI for one axis:
+//   i = clip(searchsorted(g, x, 'right') - 1, 0, n-2),  t = (x - g[i]) / (g[i+1] - g[i]).
+// `tab` may point to shared or global memory.  oob |= (x < g[0] || x > g[n-1] || isnan(x)).
+template <bool UNIFORM>
+__device__ __forceinline__ void locate(const double2 *__restrict__ tab, const Axis &a, double x,
+                                       int &i, double &t, bool &oob) {
+    if (UNIFORM) {
+        double v = fma(x, a.inv_d, a.c_guess);               // (x-g0)/d - 0.5
+        i = __double2loint(v + IONO_MAGIC);                   // ~floor((x-g0)/d)
+        i = min(max(i, 0), a.n - 2);
+    } else {
+        int lo = 0, hi = a.n - 1;
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (x >= tab[mid].x) lo = mid; else hi = mid;
+        }
+        i = min(lo, a.n - 2);
+    }
+    double2 e = tab[i];
+    t = (x - e.x) * e.y;
+    if (!(t >= 0.0 && t < 1.0)) {
+        // Rare: guess off by one, x on/over the last node, outside the grid, or NaN.
+        while (i > 0 && x < tab[i].x) --i;
+        while (i < a.n - 2 && x >= tab[i + 1].x) ++i;
+        e = tab[i];
+        t = (x - e.x) * e.y;
+        oob = oob || !(x >= a.g0 && x <= a.glast);
+    }
+}
+
+// 1/d to ~1 ulp: hardware seed (rcp.approx.ftz.f64, ~2^-23) + two Newton steps.
+// d is a product of Simpson interval lengths: finite, normal, non-zero for any
+// strictly monotone s; d == 0 yields inf/NaN like the reference's division.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// Simpson 'avg' weight of sample i of an N-sample ray, given the abscissae
+// s[i-2..i+2] (entries outside [0,N) are never used).
+//   odd N : composite Simpson, triples start at 0,2,..,N-3 (non-uniform 3-point form)
+//   even N: 1/2 {Simpson on points 0..N-2 + trapezoid on the last interval}
+//         + 1/2 {trapezoid on the first interval + Simpson on points 1..N-1}
+// With hm=h[i-1], hp=h[i], h0=h[i-2], h3=h[i+1] every term shares 1/(6 hm hp):
+//   middle of a triple : (hm+hp)^3
+//   right end          : (h0+hm)(2hm-h0) hp
+//   left end           : (hp+h3)(2hp-h3) hm
+__device__ __forceinline__ double simpson_weight(int i, int N, double sm2, double sm1, double s0,
+                                                 double sp1, double sp2) {
+    const bool has_m = i >= 1, has_p = i <= N - 2;
+    double hm = s0 - sm1, hp = sp1 - s0;
+    if (!has_m) hm = hp;
+    if (!has_p) hp = hm;
+    const double h0 = (i >= 2) ? sm1 - sm2 : hm;
+    const double h3 = (i <= N - 3) ? sp2 - sp1 : hp;
+    const int par = i & 1;
+    double cm, cr, cl, trap = 0.0;
+    if (N & 1) {
+        cm = par ? 1.0 : 0.0;
+        cr = (!par && i >= 2) ? 1.0 : 0.0;
+        cl = (!par && i <= N - 3) ? 1.0 : 0.0;
+    } else {
+        cm = (par ? (i <= N - 3) : (i >= 2)) ? 0.5 : 0.0;
+        cr = (i >= 2 + par) ? 0.5 : 0.0;
+        cl = (i <= N - 4 + par) ? 0.5 : 0.0;
+        trap = 0.25 * (hp * (double)((i == 0) + (i == N - 2)) + hm * (double)((i == 1) + (i == N - 1)));
+    }
+    const double A = hm + hp;
+    double num = (cm * A) * (A * A);
+    num = fma(cr * (h0 + hm) * fma(2.0, hm, -h0), hp, num);
+    num = fma(cl * (hp + h3) * fma(2.0, hp, -h3), hm, num);
+    const double r = fast_rcp(6.0 * hm * hp);
+    return fma(num, r, trap);
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier + TMA 1-D bulk copy (cp.async.bulk): global -> shared, completion by
+// transaction bytes on an mbarrier.  Used as a warp-private ring: the warp's
+// lane 0 is the producer, all 32 lanes are consumers, so no "empty" barrier is
+// needed (a __syncwarp() orders the last read before the re-fill).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// bytes must be a multiple of 16; src and dst 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// grid gather: read-only path, keep in L1, prefer to keep in L2
+__device__ __forceinline__ double ld_grid(const double *p, uint64_t policy) {
+    double v;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+    return v;
+}
+// streaming read (ray data without the bulk path): do not allocate in L1, evict first from L2
+__device__ __forceinline__ double ld_stream(const double *p, uint64_t policy) {
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;"
+                 : "=d"(v)
+                 : "l"(p), "l"(policy));
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------
+// Ray traversal order.  Work index q in [0, n0*n1*n2) -> ray index
+// i0*st0 + i1*st1 + i2*st2 with q = i0 + n0*(i1 + n1*i2): consecutive q (the
+// warps of one CTA) walk axis 0 first.
+// ---------------------------------------------------------------------------
+struct RayOrder {
+    int n0, n1, n2;
+    long long st0, st1, st2;
+};
+__device__ __forceinline__ long long ray_of(const RayOrder &o, long long q) {
+    int i0 = (int)(q % o.n0);
+    long long r = q / o.n0;
+    int i1 = (int)(r % o.n1);
+    long long i2 = r / o.n1;
+    return i0 * o.st0 + i1 * o.st1 + i2 * o.st2;
+}
+
+}  // namespace iono

@@ -1,0 +1,44 @@
+"""``Fermat``: ray integration through the model frame.
+
+Mirrors ``inversion/fermat.py:5-174`` of the reference.  The shipped code is
+straight-ray in effect (``euler_ode`` hard-codes grad n = 0, ``fermat.py:53-55``;
+every production caller passes ``straight_line_approx=True``), with the
+z coordinate as independent variable (``type='z'``): the closed form
+``x = x0 + (px/pz)(z - z0)``, ``s = (z - z0)/pz`` on ``z = linspace(z0, tmax, N)``
+is evaluated on the GPU by ``iono_cast_rays_straight_f64``.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+
+
+class Fermat(object):
+    def __init__(self, ne_tci=None, frequency=120e6, type='z', straight_line_approx=True):
+        if type != 'z':
+            raise NotImplementedError("only type='z' (z as independent variable) is built; "
+                                      "it is the only mode calc_rays uses (calc_rays.py:142)")
+        self.type = type
+        self.frequency = frequency  # Hz
+        self.straight_line_approx = straight_line_approx
+        self.ne_tci = ne_tci
+
+    def cast(self, origins, directions, tmax, N):
+        """All rays at once: (..., 3) origins/directions -> (..., 4, N) rows x, y, z, s."""
+        lib = _lib.load()
+        want_numpy = not isinstance(origins, torch.Tensor)
+        o = _lib.to_device(origins)
+        d = _lib.to_device(directions)
+        assert o.shape == d.shape and o.shape[-1] == 3
+        lead = tuple(o.shape[:-1])
+        nrays = int(np.prod(lead)) if lead else 1
+        rays = torch.empty(lead + (4, int(N)), dtype=torch.float64, device=o.device)
+        _lib.call("iono_cast_rays_straight_f64", _lib.ptr(o), _lib.ptr(d), nrays, float(tmax), int(N),
+                                                   _lib.ptr(rays), _lib.stream_ptr())
+        return rays.cpu().numpy() if want_numpy else rays
+
+    def integrate_ray(self, origin, direction, tmax, N=100):
+        """One ray: returns ``x, y, z, s`` each of length ``N`` (fermat.py:150-174)."""
+        rays = self.cast(np.asarray(origin, dtype=np.float64).reshape(1, 3),
+                         np.asarray(direction, dtype=np.float64).reshape(1, 3), tmax, N)
+        return rays[0, 0], rays[0, 1], rays[0, 2], rays[0, 3]

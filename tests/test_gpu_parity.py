@@ -1,0 +1,241 @@
+"""Parity of the CUDA path (through the Python shims -> ctypes -> C ABI) against the CPU
+oracle and the reference-generated golden vectors.  Needs a B200: ``pytest -m gpu``.
+
+Tolerances: the north star asks for rel 1e-6 in fp64; the kernels differ from the oracle
+only by floating-point reassociation, so the tests assert 1e-11 or tighter (bit-exact where
+the arithmetic order is reproduced: ray generation, point-wise interpolation)."""
+import numpy as np
+import pytest
+
+from oracle import ionotomo_oracle as O
+from tests.problems import small_problem
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+@pytest.fixture(scope="module")
+def ib():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ionotomo_b200
+    return ionotomo_b200
+
+
+def relerr(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-300)
+
+
+# ---------------------------------------------------------------- interpolation
+def test_interp_golden_tricubic(ib, golden):
+    g = golden("tricubic")
+    x, y, z = np.meshgrid(g["xvec"], g["yvec"], g["zvec"], indexing="ij")
+    M = x * y * z + x - y - 2 * z + x ** 2
+    tci = ib.TriCubic(g["xvec"], g["yvec"], g["zvec"], M)
+    res = tci.interp(g["pts"], g["pts"], g["pts"])
+    np.testing.assert_allclose(res, g["res_batch"], rtol=1e-13, atol=1e-15)
+    # the reference's protocol: vectorised == scalar calls, bit-exact (tests/test_tricubic.py:21-27)
+    one = np.array([tci.interp(np.array([p]), np.array([p]), np.array([p]))[0] for p in g["pts"][:40]])
+    np.testing.assert_array_equal(one, res[:40])
+    np.testing.assert_allclose(tci.interp(g["px"], g["py"], g["pz"]), g["res_rand"], rtol=1e-13, atol=1e-15)
+    np.testing.assert_allclose(tci.extrapolate(g["ex"], g["ey"], g["ez"]), g["res_extrap"], rtol=1e-13, atol=1e-15)
+    with pytest.raises(ValueError):
+        tci.interp(np.array([0.5, 1.2]), np.array([0.5, 0.5]), np.array([0.5, 0.5]))
+    with pytest.raises(ValueError):
+        tci.interp(np.array([np.nan]), np.array([0.5]), np.array([0.5]))
+    # copy + shape semantics
+    t2 = tci.copy()
+    assert np.all(t2.M == tci.M) and t2.nx == 100
+    out = tci.interp(g["px"].reshape(20, 25), g["py"].reshape(20, 25), g["pz"].reshape(20, 25))
+    assert out.shape == (20, 25)
+    assert tci.interp(np.zeros(0), np.zeros(0), np.zeros(0)).shape == (0,)
+
+
+@pytest.mark.parametrize("uniform", [True, False])
+def test_interp_bit_exact_vs_oracle(ib, uniform):
+    P = small_problem(21, 1, 1, 1, 8, 17, 13, 19, uniform=uniform)
+    rng = P["rng"]
+    n = 20000
+    x = rng.uniform(P["xvec"][0], P["xvec"][-1], n)
+    y = rng.uniform(P["yvec"][0], P["yvec"][-1], n)
+    z = rng.uniform(P["zvec"][0], P["zvec"][-1], n)
+    # nodes, first/last planes
+    x[:17] = P["xvec"]; y[:13] = P["yvec"]; z[:19] = P["zvec"]
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["ne"])
+    np.testing.assert_array_equal(tci.interp(x, y, z), O.rgi_linear(P["xvec"], P["yvec"], P["zvec"], P["ne"], x, y, z))
+    xe, ye, ze = x * 1.5, y * 1.5 + 3., z * 1.2 - 50.
+    np.testing.assert_array_equal(tci.extrapolate(xe, ye, ze),
+                                  O.rgi_linear(P["xvec"], P["yvec"], P["zvec"], P["ne"], xe, ye, ze, bounds_error=False))
+
+
+# ---------------------------------------------------------------- ray generation
+@pytest.mark.parametrize("tag", ["odd", "even"])
+def test_rays_golden_and_bit_exact(ib, golden, tag):
+    g = golden("forward_" + tag)
+    Ns = int(g["Ns"])
+    tci = ib.TriCubic(g["xvec"], g["yvec"], g["zvec"], g["ne"])
+    fermat = ib.Fermat(ne_tci=tci, frequency=120e6, type='z', straight_line_approx=True)
+    rays = ib.cast_ray((g["origins"], g["directions"]), fermat, float(g["tmax"]), Ns)
+    assert rays.shape == g["rays"].shape
+    np.testing.assert_allclose(rays, g["rays"], rtol=0, atol=1e-9)          # reference ran LSODA
+    np.testing.assert_array_equal(rays, O.cast_ray(g["origins"], g["directions"], float(g["tmax"]), Ns))
+    x, y, z, s = fermat.integrate_ray(g["single_origin"], g["single_direction"], float(g["tmax"]), N=Ns)
+    np.testing.assert_allclose(np.stack([x, y, z, s]), g["single"], rtol=0, atol=1e-9)
+
+
+def test_calc_rays_array_inputs(ib):
+    P = small_problem(4, 5, 3, 7, 33, 8, 8, 8)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["ne"])
+    ants = P["origins"][:, 0, 0, :]
+    dirs = P["directions"][0]
+    rays = ib.calc_rays(ants, dirs, list(range(3)), None, None, None, tci, 120e6, True, 1000., None)
+    assert rays.shape == (5, 3, 7, 4, tci.nz)
+    np.testing.assert_array_equal(rays, O.cast_ray(P["origins"], P["directions"], 1000., tci.nz))
+
+
+# ---------------------------------------------------------------- forward
+@pytest.mark.parametrize("tag", ["odd", "even"])
+def test_forward_golden(ib, golden, tag):
+    g = golden("forward_" + tag)
+    m_tci = ib.TriCubic(g["xvec"], g["yvec"], g["zvec"], g["m"])
+    dtec = ib.forward_equation(g["rays"], float(g["K_ne"]), m_tci, int(g["i0"]))
+    assert dtec.shape == g["dtec"].shape and not np.any(np.isnan(dtec))
+    np.testing.assert_allclose(dtec, g["dtec"], rtol=0, atol=1e-10 * np.abs(g["dtec"]).max())
+    assert np.all(dtec[int(g["i0"])] == 0)
+    np.testing.assert_array_equal(dtec, ib.forward_equation_dask(g["rays"], float(g["K_ne"]), m_tci, int(g["i0"])))
+
+
+@pytest.mark.parametrize("Ns", [2, 3, 4, 5, 30, 31, 64, 65, 66, 127, 128, 130, 200, 257])
+@pytest.mark.parametrize("order", ["time", "natural", "antenna"])
+def test_forward_vs_oracle_sizes(ib, Ns, order):
+    P = small_problem(100 + Ns, 4, 3, 5, Ns, 14, 12, 16)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], Ns)
+    # make s non-uniform (general Simpson weights) while keeping x,y,z
+    rays[..., 3, :] = rays[..., 3, :] + 0.3 * np.sin(rays[..., 3, :] / 50.)
+    m_tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    dtec, tec = ib.forward_equation(rays, P["K_ne"], m_tci, 2, order=order, return_tec=True)
+    ref_tec = O.tec(rays, P["xvec"], P["yvec"], P["zvec"], O.ne_from_m(P["m"], P["K_ne"]))
+    assert relerr(tec, ref_tec) < TOL
+    ref = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], 2)
+    assert np.abs(dtec - ref).max() < TOL * np.abs(ref_tec).max()
+
+
+def test_forward_nonuniform_grid_and_config1(ib):
+    # BASELINE config 1: 10 antennas x 20 directions x 1 time, 50x50x30 grid, Ns = nz = 30
+    for uniform in (True, False):
+        P = small_problem(7, 10, 1, 20, 30, 50, 50, 30, uniform=uniform)
+        rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 30)
+        m_tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+        assert m_tci.grid().uniform == uniform
+        dtec, tec = ib.forward_equation(rays, P["K_ne"], m_tci, 0, return_tec=True)
+        ref_tec = O.tec(rays, P["xvec"], P["yvec"], P["zvec"], O.ne_from_m(P["m"], P["K_ne"]))
+        assert relerr(tec, ref_tec) < TOL
+
+
+def test_forward_out_of_bounds_raises(ib):
+    P = small_problem(9, 3, 1, 4, 16, 10, 10, 10)
+    rays = O.cast_ray(P["origins"], P["directions"], 1200., 16)      # tmax above the grid top
+    m_tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    with pytest.raises(ValueError):
+        ib.forward_equation(rays, P["K_ne"], m_tci, 0)
+    with pytest.raises(ValueError):
+        O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], 0)
+    # empty inputs
+    out = ib.forward_equation(np.zeros((0, 2, 3, 4, 8)), P["K_ne"], m_tci, 0)
+    assert out.shape == (0, 2, 3)
+
+
+def test_forward_device_tensors_and_linearity(ib):
+    import torch
+    P = small_problem(31, 6, 4, 9, 128, 32, 32, 128)
+    rays = torch.as_tensor(O.cast_ray(P["origins"], P["directions"], P["tmax"], 128)).cuda()
+    grid = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"]).grid()
+    from ionotomo_b200.inversion.forward_equation import tec_from_ne
+    a = torch.as_tensor(P["ne"]).cuda() / 1e13
+    b = torch.rand_like(a)
+    ta, tb, tab = tec_from_ne(rays, grid, a), tec_from_ne(rays, grid, b), tec_from_ne(rays, grid, 2 * a - 3 * b)
+    assert isinstance(ta, torch.Tensor) and ta.is_cuda
+    assert float((2 * ta - 3 * tb - tab).abs().max()) < 1e-12 * float(tab.abs().max())
+    # bit-reproducible run to run and across traversal orders
+    assert torch.equal(ta, tec_from_ne(rays, grid, a))
+    assert torch.equal(ta, tec_from_ne(rays, grid, a, order="natural"))
+    assert torch.equal(ta, tec_from_ne(rays, grid, a, order="antenna"))
+    # constant field integrates to the path length
+    ones = torch.ones_like(a)
+    t1 = tec_from_ne(rays, grid, ones)
+    assert float((t1 - rays[..., 3, -1]).abs().max()) < 1e-10 * float(t1.max())
+
+
+# ---------------------------------------------------------------- adjoint
+@pytest.mark.parametrize("Ns", [2, 3, 8, 9, 64, 66, 129])
+def test_backprojection_vs_oracle(ib, Ns):
+    import torch
+    from ionotomo_b200.inversion.gradient import backproject
+    P = small_problem(200 + Ns, 4, 3, 5, Ns, 14, 12, 16)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], Ns)
+    rays[..., 3, :] = rays[..., 3, :] + 0.3 * np.sin(rays[..., 3, :] / 50.)
+    coef = P["rng"].normal(size=rays.shape[:3])
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    acc = backproject(torch.as_tensor(rays).cuda(), tci.grid(), torch.as_tensor(coef).cuda(), P["m"].shape)
+    ref = O.backproject(rays, P["xvec"], P["yvec"], P["zvec"], coef)
+    assert np.abs(acc.cpu().numpy() - ref).max() < TOL * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("tag", ["odd", "even"])
+def test_gradient_vs_oracle_and_fd(ib, golden, tag):
+    g = golden("forward_" + tag)
+    xv, yv, zv, rays, m = g["xvec"], g["yvec"], g["zvec"], g["rays"], g["m"]
+    K_ne, i0 = float(g["K_ne"]), int(g["i0"])
+    rng = np.random.RandomState(5)
+    dobs = g["dtec"] + 0.01 * rng.normal(size=g["dtec"].shape)
+    CdCt = np.full(dobs.shape, 0.01 ** 2)
+    m_tci = ib.TriCubic(xv, yv, zv, m)
+    gm = ib.forward_equation(rays, K_ne, m_tci, i0)
+    grad = ib.compute_gradient(rays, gm, dobs, i0, K_ne, m_tci, m, CdCt, 1., 4, 5.)
+    ref = O.gradient_exact(rays, gm, dobs, i0, K_ne, xv, yv, zv, m, CdCt)
+    assert grad.shape == m.shape
+    assert np.abs(grad - ref).max() < TOL * np.abs(ref).max()
+    np.testing.assert_allclose(float(ib.misfit(gm, dobs, CdCt)), O.misfit(gm, dobs, CdCt), rtol=1e-13)
+    # the reference's finite-difference protocol (tests/test_inversion.py:71-87), central differences
+    for f in np.argsort(-np.abs(grad).ravel())[:4]:
+        v = np.unravel_index(f, m.shape)
+        Sp = []
+        for sgn in (+1, -1):
+            mp = m.copy(); mp[v] += sgn * 1e-6
+            Sp.append(float(ib.misfit(ib.forward_equation(rays, K_ne, ib.TriCubic(xv, yv, zv, mp), i0), dobs, CdCt)))
+        fd = (Sp[0] - Sp[1]) / 2e-6
+        assert abs(fd - grad[v]) <= 1e-5 * abs(grad[v])
+
+
+def test_adjoint_dot_product_config2_shape(ib):
+    """<G x, y> == <x, G^T y> at a LOFAR-like shape slice (62 antennas, Ns=128, 256x256x128 grid)."""
+    import torch
+    from ionotomo_b200.inversion.forward_equation import tec_from_ne
+    from ionotomo_b200.inversion.gradient import backproject
+    P = small_problem(77, 62, 4, 25, 128, 256, 256, 128)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    fermat = ib.Fermat(tci)
+    rays = ib.cast_ray((torch.as_tensor(P["origins"]).cuda(), torch.as_tensor(P["directions"]).cuda()), fermat, 1000., 128)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(P["m"].shape, dtype=torch.float64, device="cuda", generator=gen)
+    y = torch.randn(rays.shape[:3], dtype=torch.float64, device="cuda", generator=gen)
+    Gx = tec_from_ne(rays, tci.grid(), x)
+    GTy = backproject(rays, tci.grid(), y, P["m"].shape)
+    lhs, rhs = float((Gx * y).sum()), float((x * GTy).sum())
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), abs(rhs))
+    for order in ("natural", "antenna"):
+        GTy2 = backproject(rays, tci.grid(), y, P["m"].shape, order=order)
+        assert float((GTy2 - GTy).abs().max()) <= 1e-11 * float(GTy.abs().max())
+
+
+# ---------------------------------------------------------------- line search
+def test_line_search_golden(ib, golden):
+    g = golden("line_search")
+    np.testing.assert_allclose(ib.vertex(*g["vx"][:3], *g["vy"][:3]), g["v1"], rtol=1e-9)
+    m_tci = ib.TriCubic(g["xvec"], g["yvec"], g["zvec"], g["m0"])
+    eps, S, red = ib.line_search(g["rays"], float(g["K_ne"]), m_tci, 0, g["grad"], g["g"], g["dobs"], g["CdCt"])
+    np.testing.assert_allclose(eps, float(g["eps"]), rtol=1e-6)
+    np.testing.assert_allclose(S, float(g["S"]), rtol=1e-6)
+    np.testing.assert_allclose(red, float(g["red"]), rtol=1e-5, atol=1e-9)
