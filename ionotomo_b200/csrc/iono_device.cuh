@@ -87,25 +87,25 @@ __device__ __forceinline__ double fast_rcp(double d) {
 //   middle of a triple : (hm+hp)^3
 //   right end          : (h0+hm)(2hm-h0) hp
 //   left end           : (hp+h3)(2hp-h3) hm
-__device__ __forceinline__ double simpson_weight(int i, int N, double sm2, double sm1, double s0,
+__device__ __forceinline__ double simpson_weight(int i, int N, bool n_odd, double sm2, double sm1, double s0,
                                                  double sp1, double sp2) {
-    const bool has_m = i >= 1, has_p = i <= N - 2;
     double hm = s0 - sm1, hp = sp1 - s0;
-    if (!has_m) hm = hp;
-    if (!has_p) hp = hm;
+    if (i < 1) hm = hp;
+    if (i > N - 2) hp = hm;
     const double h0 = (i >= 2) ? sm1 - sm2 : hm;
     const double h3 = (i <= N - 3) ? sp2 - sp1 : hp;
     const int par = i & 1;
     double cm, cr, cl, trap = 0.0;
-    if (N & 1) {
+    if (n_odd) {   // warp-uniform branch
         cm = par ? 1.0 : 0.0;
-        cr = (!par && i >= 2) ? 1.0 : 0.0;
-        cl = (!par && i <= N - 3) ? 1.0 : 0.0;
+        cr = (par | (i < 2)) ? 0.0 : 1.0;
+        cl = (par | (i > N - 3)) ? 0.0 : 1.0;
     } else {
         cm = (par ? (i <= N - 3) : (i >= 2)) ? 0.5 : 0.0;
         cr = (i >= 2 + par) ? 0.5 : 0.0;
         cl = (i <= N - 4 + par) ? 0.5 : 0.0;
-        trap = 0.25 * (hp * (double)((i == 0) + (i == N - 2)) + hm * (double)((i == 1) + (i == N - 1)));
+        if (i < 2 || i > N - 3)
+            trap = 0.25 * (hp * (double)((i == 0) + (i == N - 2)) + hm * (double)((i == 1) + (i == N - 1)));
     }
     const double A = hm + hp;
     double num = (cm * A) * (A * A);
@@ -191,14 +191,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------
 struct RayOrder {
     int n0, n1, n2;
-    long long st0, st1, st2;
+    int st0, st1, st2;
 };
-__device__ __forceinline__ long long ray_of(const RayOrder &o, long long q) {
-    int i0 = (int)(q % o.n0);
-    long long r = q / o.n0;
-    int i1 = (int)(r % o.n1);
-    long long i2 = r / o.n1;
-    return i0 * o.st0 + i1 * o.st1 + i2 * o.st2;
+__device__ __forceinline__ long long ray_of(const RayOrder &o, int q) {
+    const int i0 = q % o.n0;
+    const int r = q / o.n0;
+    const int i1 = r % o.n1;
+    const int i2 = r / o.n1;
+    return (long long)(i0 * o.st0 + i1 * o.st1 + i2 * o.st2);
 }
 
 }  // namespace iono

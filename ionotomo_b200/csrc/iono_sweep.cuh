@@ -1,0 +1,355 @@
+// The ray sweep: forward (gather + warp reduce) and adjoint (scatter with fp64 reductions).
+// Included by iono_kernels.cu (one translation unit).
+//
+// Mapping
+//   * one warp per ray; a CTA's warps take consecutive work indices of the chosen
+//     traversal order (IONO_ORDER_*), persistent CTAs (one per SM) walk the rest with a
+//     static stride, so the result is bit-reproducible;
+//   * the ray's samples are streamed HBM -> shared memory in chunks of C samples by TMA 1-D
+//     bulk copies (cp.async.bulk + mbarrier complete_tx) into a warp-private ring; lane 0
+//     is the producer, the 32 lanes are the consumers;
+//   * lanes take consecutive samples of the chunk.  The grid is z-fastest and rays run
+//     near-vertically, so the corner reads of neighbouring lanes share 32-byte sectors;
+//     the corner values come through L1 (ld.global.nc) and the 67 MB grid stays in L2
+//     while the ray stream passes with an evict-first policy.
+#pragma once
+
+struct SweepParams {
+    Grid g;
+    const double *field;   // forward: ne (nx,ny,nz)
+    double *acc;           // adjoint: accumulator (nx,ny,nz)
+    const double *rays;    // (R,4,Ns)
+    const double *coef;    // adjoint: per-ray coefficient (R)
+    double *tec;           // forward: per-ray integral (R)
+    unsigned long long *oob_count;
+    int R;
+    int Ns;
+    int stages;            // ring depth per warp
+    RayOrder order;
+};
+
+// A stage holds x[C], y[C], z[C] and s[C+4] (two halo samples either side for the
+// Simpson weights).
+template <int C>
+struct StageLayout {
+    static constexpr int S_OFF = 3 * C;  // in doubles
+    static constexpr int DOUBLES = 4 * C + 4;
+    static constexpr int BYTES = ((DOUBLES * 8 + 127) / 128) * 128;
+};
+
+template <int C, bool BULK>
+__device__ __forceinline__ void fill_stage(double *stage, uint64_t *bar, const double *ray, int Ns, int c0,
+                                           int lane, uint64_t policy) {
+    const int n_c = min(C, Ns - c0);
+    const int s_lo = max(c0 - 2, 0), s_hi = min(c0 + C + 2, Ns);
+    double *sdst = stage + StageLayout<C>::S_OFF + (s_lo - (c0 - 2));
+    if (BULK) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, (uint32_t)((3 * n_c + (s_hi - s_lo)) * 8));
+            bulk_g2s(stage, ray + c0, n_c * 8, bar, policy);
+            bulk_g2s(stage + C, ray + Ns + c0, n_c * 8, bar, policy);
+            bulk_g2s(stage + 2 * C, ray + 2 * Ns + c0, n_c * 8, bar, policy);
+            bulk_g2s(sdst, ray + 3 * Ns + s_lo, (s_hi - s_lo) * 8, bar, policy);
+        }
+    } else {
+        for (int i = lane; i < n_c; i += 32) {
+            stage[i] = ld_stream(ray + c0 + i, policy);
+            stage[C + i] = ld_stream(ray + Ns + c0 + i, policy);
+            stage[2 * C + i] = ld_stream(ray + 2 * Ns + c0 + i, policy);
+        }
+        for (int i = lane; i < s_hi - s_lo; i += 32) sdst[i] = ld_stream(ray + 3 * Ns + s_lo + i, policy);
+    }
+}
+
+// Axis constants held in registers inside the sweep.
+struct AxisR {
+    double inv_d, c_guess, g0, glast;
+    int nm2;
+};
+__device__ __forceinline__ AxisR axis_regs(const Axis &a) {
+    AxisR r;
+    r.inv_d = a.inv_d; r.c_guess = a.c_guess; r.g0 = a.g0; r.glast = a.glast; r.nm2 = a.n - 2;
+    return r;
+}
+
+// Same semantics as iono::locate(), table in shared memory, constants in registers.
+template <bool UNIFORM>
+__device__ __forceinline__ void locate_s(const double2 *__restrict__ tab, const AxisR &a, double x, int &i,
+                                         double &t, bool &oob) {
+    if (UNIFORM) {
+        const double v = fma(x, a.inv_d, a.c_guess);
+        i = min(max(__double2loint(v + IONO_MAGIC), 0), a.nm2);
+    } else {
+        int lo = 0, hi = a.nm2 + 1;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (x >= tab[mid].x) lo = mid; else hi = mid;
+        }
+        i = min(lo, a.nm2);
+    }
+    double2 e = tab[i];
+    t = (x - e.x) * e.y;
+    if (!(t >= 0.0 && t < 1.0)) {
+        while (i > 0 && x < tab[i].x) --i;
+        while (i < a.nm2 && x >= tab[i + 1].x) ++i;
+        e = tab[i];
+        t = (x - e.x) * e.y;
+        oob = oob || !(x >= a.g0 && x <= a.glast);
+    }
+}
+
+// MODE 0: forward, MODE 1: adjoint
+template <int MODE, bool UNIFORM, int C, bool BULK, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int nx = p.g.ax[0].n, ny = p.g.ax[1].n, nz = p.g.ax[2].n;
+    const int stages = p.stages;
+
+    // shared: [axis tables][per-warp mbarriers][per-warp stages]
+    double2 *tabx = reinterpret_cast<double2 *>(smem_raw);
+    double2 *taby = tabx + nx;
+    double2 *tabz = taby + ny;
+    unsigned int off = ((unsigned int)(nx + ny + nz) * 16u + 127u) / 128u * 128u;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + off) + warp * stages;
+    off += ((unsigned int)(nwarp * stages) * 8u + 127u) / 128u * 128u;
+    unsigned char *ring = smem_raw + off + (unsigned int)(warp * stages) * StageLayout<C>::BYTES;
+
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) tabx[i] = p.g.ax[0].tab[i];
+    for (int i = threadIdx.x; i < ny; i += blockDim.x) taby[i] = p.g.ax[1].tab[i];
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) tabz[i] = p.g.ax[2].tab[i];
+    if (BULK && lane == 0)
+        for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+    if (BULK) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const uint64_t pol_stream = policy_evict_first();
+    const AxisR ax = axis_regs(p.g.ax[0]), ay = axis_regs(p.g.ax[1]), az = axis_regs(p.g.ax[2]);
+    const int Ns = p.Ns;
+    const bool n_odd = Ns & 1;
+    const int chunks = (Ns + C - 1) / C;
+    const int G = gridDim.x;
+    const double *const rays = p.rays;
+    const long long ray_doubles = 4LL * Ns;
+    const RayOrder order = p.order;
+
+    // Static schedule: bundle b = nwarp consecutive work indices; this CTA takes
+    // b = blockIdx.x, blockIdx.x + G, ...; this warp takes work index b*nwarp + warp.
+    const int n_bundles = (p.R + nwarp - 1) / nwarp;
+    int my_rays = (n_bundles > (int)blockIdx.x) ? (n_bundles - 1 - (int)blockIdx.x) / G + 1 : 0;
+    if (my_rays > 0 && ((int)blockIdx.x + (my_rays - 1) * G) * nwarp + warp >= p.R) --my_rays;
+    auto ray_index = [&](int k) -> long long { return ray_of(order, ((int)blockIdx.x + k * G) * nwarp + warp); };
+
+    // producer cursor (ray fk, chunk fc, stage fs) and consumer stage/phase
+    int fk = 0, fc = 0, fs = 0;
+    const double *fray = (my_rays > 0) ? rays + ray_index(0) * ray_doubles : rays;
+    auto produce = [&]() {
+        if (fk < my_rays) {
+            fill_stage<C, true>(reinterpret_cast<double *>(ring + fs * StageLayout<C>::BYTES), &bars[fs], fray, Ns,
+                                fc * C, lane, pol_stream);
+            fs = (fs + 1 == stages) ? 0 : fs + 1;
+            if (++fc == chunks) {
+                fc = 0;
+                if (++fk < my_rays) fray = rays + ray_index(fk) * ray_doubles;
+            }
+        }
+    };
+    if (BULK)
+        for (int s = 0; s < stages - 1; ++s) produce();
+
+    unsigned int n_oob = 0;
+    unsigned int phases = 0;   // bit s: parity to wait for on stage s
+    int us = 0;                // stage to consume
+    const int sy = nz, sx = ny * nz;   // element strides (nx*ny*nz < 2^31 checked on the host)
+
+    for (int k = 0; k < my_rays; ++k) {
+        const long long ray = ray_index(k);
+        const double *rayp = rays + ray * ray_doubles;
+        double acc = 0.0;
+        double coef = 0.0;
+        if (MODE == 1) coef = __ldg(p.coef + ray);
+        for (int chunk = 0; chunk < chunks; ++chunk) {
+            const int c0 = chunk * C;
+            double *stage = reinterpret_cast<double *>(ring + us * StageLayout<C>::BYTES);
+            if (BULK) {
+                produce();
+                mbar_wait(&bars[us], (phases >> us) & 1u);
+                phases ^= 1u << us;
+            } else {
+                fill_stage<C, false>(stage, nullptr, rayp, Ns, c0, lane, pol_stream);
+                __syncwarp();
+            }
+            const double *sx_ = stage, *sy_ = stage + C, *sz_ = stage + 2 * C;
+            const double *ss_ = stage + StageLayout<C>::S_OFF + 2;   // ss_[j] = s[c0 + j]
+            const int n_c = min(C, Ns - c0);
+#pragma unroll 2
+            for (int j = lane; j < n_c; j += 32) {
+                const int i = c0 + j;
+                int ix, iy, iz;
+                double tx, ty, tz;
+                bool oob = false;
+                locate_s<UNIFORM>(tabx, ax, sx_[j], ix, tx, oob);
+                locate_s<UNIFORM>(taby, ay, sy_[j], iy, ty, oob);
+                locate_s<UNIFORM>(tabz, az, sz_[j], iz, tz, oob);
+                n_oob += oob;
+                const double w = simpson_weight(i, Ns, n_odd, ss_[j - 2], ss_[j - 1], ss_[j], ss_[j + 1], ss_[j + 2]);
+                const int v = (ix * ny + iy) * nz + iz;
+                if (MODE == 0) {
+                    const double *c = p.field + v;
+                    const double v000 = __ldg(c), v001 = __ldg(c + 1);
+                    const double v010 = __ldg(c + sy), v011 = __ldg(c + sy + 1);
+                    const double v100 = __ldg(c + sx), v101 = __ldg(c + sx + 1);
+                    const double v110 = __ldg(c + sx + sy), v111 = __ldg(c + sx + sy + 1);
+                    const double c00 = fma(tz, v001 - v000, v000), c01 = fma(tz, v011 - v010, v010);
+                    const double c10 = fma(tz, v101 - v100, v100), c11 = fma(tz, v111 - v110, v110);
+                    const double c0_ = fma(ty, c01 - c00, c00), c1_ = fma(ty, c11 - c10, c10);
+                    acc = fma(w, fma(tx, c1_ - c0_, c0_), acc);
+                } else {
+                    double *c = p.acc + v;
+                    const double a = coef * w;
+                    const double ax1 = a * tx, ax0 = a - ax1;
+                    const double a01 = ax0 * ty, a00 = ax0 - a01;
+                    const double a11 = ax1 * ty, a10 = ax1 - a11;
+                    double hi;
+                    hi = a00 * tz; atomicAdd(c, a00 - hi); atomicAdd(c + 1, hi);
+                    hi = a01 * tz; atomicAdd(c + sy, a01 - hi); atomicAdd(c + sy + 1, hi);
+                    hi = a10 * tz; atomicAdd(c + sx, a10 - hi); atomicAdd(c + sx + 1, hi);
+                    hi = a11 * tz; atomicAdd(c + sx + sy, a11 - hi); atomicAdd(c + sx + sy + 1, hi);
+                }
+            }
+            us = (us + 1 == stages) ? 0 : us + 1;
+            __syncwarp();
+        }
+        if (MODE == 0) {
+            const double tot = warp_sum(acc);
+            if (lane == 0) p.tec[ray] = tot;
+        }
+    }
+    if (n_oob) atomicAdd(p.oob_count, (unsigned long long)n_oob);
+}
+
+struct SweepConfig {
+    int warps;    // per CTA
+    int stages;
+    int chunk;    // 64 or 128
+};
+
+static SweepConfig sweep_config(int mode, int Ns) {
+    SweepConfig c;
+    c.warps = 16;
+    c.stages = 2;
+    c.chunk = (Ns <= 64) ? 64 : 128;
+    const char *e;
+    if ((e = getenv("IONO_SWEEP_WARPS"))) c.warps = atoi(e);
+    if ((e = getenv("IONO_SWEEP_STAGES"))) c.stages = atoi(e);
+    if ((e = getenv("IONO_SWEEP_CHUNK"))) c.chunk = atoi(e);
+    (void)mode;
+    if (c.warps < 1) c.warps = 1;
+    if (c.warps > 24) c.warps = 24;
+    if (c.stages < 2) c.stages = 2;
+    if (c.stages > 8) c.stages = 8;
+    if (c.chunk != 64) c.chunk = 128;
+    return c;
+}
+
+static RayOrder make_order(int order, int Na, int Nt, int Nd) {
+    RayOrder o;
+    const int sa = Nt * Nd, st = Nd, sd = 1;
+    switch (order) {
+        case IONO_ORDER_TIME:      // t fastest, then a, then d
+            o.n0 = Nt; o.st0 = st; o.n1 = Na; o.st1 = sa; o.n2 = Nd; o.st2 = sd; break;
+        case IONO_ORDER_ANTENNA:   // a fastest, then t, then d
+            o.n0 = Na; o.st0 = sa; o.n1 = Nt; o.st1 = st; o.n2 = Nd; o.st2 = sd; break;
+        default:                   // memory order
+            o.n0 = Nd; o.st0 = sd; o.n1 = Nt; o.st1 = st; o.n2 = Na; o.st2 = sa; break;
+    }
+    return o;
+}
+
+template <int MODE, bool UNIFORM, int C, bool BULK, int MAXT>
+static int launch_sweep_t(const SweepParams &p, const SweepConfig &cfg, size_t smem, int ctas, cudaStream_t st) {
+    auto kern = ray_sweep_kernel<MODE, UNIFORM, C, BULK, MAXT>;
+    CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<ctas, cfg.warps * 32, smem, st>>>(p);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
+template <int MODE>
+static int launch_sweep(SweepParams p, iono_grid_t grid, cudaStream_t st) {
+    SweepConfig cfg = sweep_config(MODE, p.Ns);
+    p.stages = cfg.stages;
+    const size_t stage_bytes = cfg.chunk == 64 ? StageLayout<64>::BYTES : StageLayout<128>::BYTES;
+    size_t smem = (((size_t)(grid->nx + grid->ny + grid->nz) * sizeof(double2)) + 127) / 128 * 128;
+    smem += (((size_t)cfg.warps * cfg.stages * sizeof(uint64_t)) + 127) / 128 * 128;
+    smem += (size_t)cfg.warps * cfg.stages * stage_bytes;
+    if (smem > 227 * 1024) return fail(IONO_EBADARG, "ray sweep: shared-memory configuration exceeds 227 KB");
+    // TMA bulk copies need 16-byte aligned rows: even Ns and a 16-byte aligned base
+    const bool bulk = (p.Ns % 2 == 0) && (((uintptr_t)p.rays & 15) == 0) && !getenv("IONO_SWEEP_NO_BULK");
+    const int n_bundles = (p.R + cfg.warps - 1) / cfg.warps;
+    int ctas = sm_count();
+    if (ctas > n_bundles) ctas = n_bundles;
+    const bool uni = grid->uniform != 0;
+    const bool big = cfg.warps > 16;
+#define IONO_DISPATCH4(U, CC, B)                                                              \
+    do {                                                                                      \
+        if (big) return launch_sweep_t<MODE, U, CC, B, 768>(p, cfg, smem, ctas, st);          \
+        return launch_sweep_t<MODE, U, CC, B, 512>(p, cfg, smem, ctas, st);                   \
+    } while (0)
+    if (cfg.chunk == 64) {
+        if (uni) { if (bulk) IONO_DISPATCH4(true, 64, true); else IONO_DISPATCH4(true, 64, false); }
+        else     { if (bulk) IONO_DISPATCH4(false, 64, true); else IONO_DISPATCH4(false, 64, false); }
+    } else {
+        if (uni) { if (bulk) IONO_DISPATCH4(true, 128, true); else IONO_DISPATCH4(true, 128, false); }
+        else     { if (bulk) IONO_DISPATCH4(false, 128, true); else IONO_DISPATCH4(false, 128, false); }
+    }
+#undef IONO_DISPATCH4
+}
+
+static int sweep_size_check(iono_grid_t grid, long long R, int Ns) {
+    if (R * 4LL * Ns / 4 > 0x7fffffffLL * 1024LL) return fail(IONO_EBADARG, "ray sweep: ray array too large");
+    if (R > 0x7fffffffLL - 1024) return fail(IONO_EBADARG, "ray sweep: more than 2^31 rays");
+    if ((long long)grid->nx * grid->ny * grid->nz > 0x7fffffffLL)
+        return fail(IONO_EBADARG, "ray sweep: more than 2^31 voxels");
+    return IONO_OK;
+}
+
+extern "C" int iono_tec_forward_f64(iono_grid_t grid, const double *ne, const double *rays, int Na, int Nt, int Nd,
+                                    int Ns, int order, double *tec_out, unsigned long long *oob_count,
+                                    void *stream) {
+    const long long R = (long long)Na * Nt * Nd;
+    if (!grid || !ne || !oob_count || Na < 0 || Nt < 0 || Nd < 0 || Ns < 1 || (R > 0 && (!rays || !tec_out)))
+        return fail(IONO_EBADARG, "iono_tec_forward_f64: bad argument");
+    if (sweep_size_check(grid, R, Ns)) return IONO_EBADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
+    if (R == 0) return IONO_OK;
+    if (Ns < 2) {  // simps of a single sample is 0
+        CU_CHECK(cudaMemsetAsync(tec_out, 0, R * sizeof(double), st));
+        return IONO_OK;
+    }
+    SweepParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = grid->dev; p.field = ne; p.rays = rays; p.tec = tec_out; p.oob_count = oob_count;
+    p.R = (int)R; p.Ns = Ns; p.order = make_order(order, Na, Nt, Nd);
+    return launch_sweep<0>(p, grid, st);
+}
+
+extern "C" int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
+                                    const double *coef, int order, int zero_first, double *acc,
+                                    unsigned long long *oob_count, void *stream) {
+    const long long R = (long long)Na * Nt * Nd;
+    if (!grid || !acc || !oob_count || Na < 0 || Nt < 0 || Nd < 0 || Ns < 1 || (R > 0 && (!rays || !coef)))
+        return fail(IONO_EBADARG, "iono_tec_adjoint_f64: bad argument");
+    if (sweep_size_check(grid, R, Ns)) return IONO_EBADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
+    if (zero_first)
+        CU_CHECK(cudaMemsetAsync(acc, 0, (size_t)grid->nx * grid->ny * grid->nz * sizeof(double), st));
+    if (R == 0 || Ns < 2) return IONO_OK;
+    SweepParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = grid->dev; p.acc = acc; p.rays = rays; p.coef = coef; p.oob_count = oob_count;
+    p.R = (int)R; p.Ns = Ns; p.order = make_order(order, Na, Nt, Nd);
+    return launch_sweep<1>(p, grid, st);
+}

@@ -110,6 +110,8 @@ def simps_weights_fast(x):
     w = np.zeros_like(x)
 
     def add_triples(start, stop, scale):
+        if stop <= start:      # N < 3 (or N = 2,3 shifted): no triple
+            return
         h0 = h[..., start:stop:2]
         h1 = h[..., start + 1:stop + 1:2]
         hsum = h0 + h1
