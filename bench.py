@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""Benchmark of the ray-integral forward model + exact adjoint (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm
+
+One *step* = one forward + adjoint pass over the LOFAR-like synthetic case
+(BASELINE.json configs[1]: 62 stations x 200 directions x 100 times, 256x256x128 grid,
+Ns = 128 samples per ray, fp64): ne = K exp(m)/TECU, TEC integrals, dTEC, misfit,
+adjoint coefficients, back-projection, (allreduce across ranks), ne * acc.
+Weak scaling: every rank holds a full 62x100x200 ray block (consecutive time steps of a
+longer observation), the grid is replicated, the only collective is the allreduce of the
+voxel accumulator.
+
+Prints ONE JSON line (rank 0).  ``value`` is rays/s for the whole job with inputs resident
+in HBM; ``e2e`` is the same pass through the public host-array API
+(``misfit_and_gradient``) with every input copied host->device and every result copied
+back inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NA, NT, ND = 62, 100, 200
+NX, NY, NZ = 256, 256, 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nt", type=int, default=NT, help="time steps per rank (default: the named config)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--order", default=os.environ.get("IONO_BENCH_ORDER", "time"))
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------
+# CPU arm: the oracle (NumPy restatement of the reference's algorithm) on all host cores
+# ----------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(xvec, yvec, zvec, ne, K_ne):
+    _CPU.update(xvec=xvec, yvec=yvec, zvec=zvec, ne=ne, K_ne=K_ne)
+
+
+def _cpu_forward(args):
+    from oracle import ionotomo_oracle as O
+    origins, directions, tmax, Ns = args
+    rays = O.cast_ray(origins, directions, tmax, Ns)
+    return O.tec(rays, _CPU["xvec"], _CPU["yvec"], _CPU["zvec"], _CPU["ne"])
+
+
+def _cpu_adjoint(args):
+    from oracle import ionotomo_oracle as O
+    origins, directions, tmax, Ns, coef = args
+    rays = O.cast_ray(origins, directions, tmax, Ns)
+    return O.backproject(rays, _CPU["xvec"], _CPU["yvec"], _CPU["zvec"], coef)
+
+
+def cpu_workload(n_times):
+    """Host-side copy of the benchmark case restricted to the first ``n_times`` time steps
+    (same generator and seed as the GPU arm)."""
+    from ionotomo_b200.ionosphere.synthetic import make_workload
+    from oracle import ionotomo_oracle as O
+    w = make_workload(Na=NA, Nt=NT, Nd=ND, nx=NX, ny=NY, nz=NZ, device="cpu", t_slice=(0, n_times))
+    m = w["m_true"].numpy()
+    return dict(xvec=w["xvec"], yvec=w["yvec"], zvec=w["zvec"], ne=O.ne_from_m(m, w["K_ne"]), K_ne=w["K_ne"],
+                origins=w["origins"].numpy(), directions=w["directions"].numpy(), tmax=w["tmax"], Ns=w["Ns"])
+
+
+def cpu_pass(pool, cw, cores):
+    """One forward + adjoint pass of the oracle over the sample, time steps spread over the
+    worker processes (mirrors the reference's dask.multiprocessing fan-out,
+    inversion/forward_equation.py:53-67, inversion/gradient.py:52-54)."""
+    o, d = cw["origins"], cw["directions"]
+    nt = o.shape[1]
+    # one contiguous block of time steps per worker: each returns one TEC block / one voxel cube
+    edges = np.linspace(0, nt, min(cores, nt) + 1).astype(int)
+    blocks = [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+    parts = [(o[:, a:b], d[:, a:b], cw["tmax"], cw["Ns"]) for a, b in blocks]
+    tec = np.concatenate(pool.map(_cpu_forward, parts), axis=1)
+    g = tec - tec[0]
+    rng = np.random.RandomState(0)
+    dd = (g - (g + 0.01 * rng.normal(size=g.shape))) / (1e-4 + 1e-15)
+    coef = dd.copy()
+    coef[0] -= dd.sum(0)
+    acc = 0.0
+    for part in pool.imap_unordered(_cpu_adjoint, [p + (coef[:, a:b],) for (a, b), p in zip(blocks, parts)]):
+        acc = acc + part
+    return cw["ne"] * acc
+
+
+def run_cpu(steps, warmup, target_seconds=12.0):
+    """Time the oracle on a bounded sample; returns (rays_per_s, cores, sample description)."""
+    import multiprocessing as mp
+    cores = min(os.cpu_count() or 1, 64)    # each worker returns a 67 MB cube per pass
+    n_times = max(1, min(NT, cores))        # one time step (12 400 rays) per worker and pass
+    cw = cpu_workload(n_times)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_cpu_init, initargs=(cw["xvec"], cw["yvec"], cw["zvec"], cw["ne"], cw["K_ne"])) as pool:
+        t = time.time()
+        cpu_pass(pool, cw, cores)           # calibration / warm-up
+        one = time.time() - t
+        for _ in range(max(0, warmup - 1)):
+            cpu_pass(pool, cw, cores)
+        steps = max(1, min(steps, int(target_seconds / max(one, 1e-3)) or 1))
+        t = time.time()
+        for _ in range(steps):
+            cpu_pass(pool, cw, cores)
+        dt = (time.time() - t) / steps
+    rays = NA * n_times * ND
+    sample = "%d of %d time steps (%d rays) per step, %d timed steps, NumPy oracle, %d processes" % (
+        n_times, NT, rays, steps, cores)
+    return rays / dt, cores, sample, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rps, cores, sample, dt = run_cpu(args.steps, args.warmup, target_seconds=60.0)
+    line = {
+        "impl": "reference", "metric": "forward+adjoint ray passes per second", "value": rps, "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, NT),
+        "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is Python and cannot be imported on this image (astropy/h5py/dask absent, "
+                "scipy.integrate.simps removed); this arm times oracle/ (its NumPy restatement, pinned to "
+                "golden vectors from the reference's own modules) on all host cores",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, nt):
+    return {"workload": "LOFAR-like forward+adjoint: %d stations x %d directions x %d times per GPU, "
+                        "%dx%dx%d grid, Ns=%d, fp64 (BASELINE.json configs[1..2])" % (NA, ND, nt, NX, NY, NZ, NZ),
+            "rays_per_gpu": NA * nt * ND, "grid": [NX, NY, NZ], "samples_per_ray": NZ, "box": "tight",
+            "sharding": "time blocks per rank, grid replicated, allreduce(acc) fp64",
+            "l2_policy": "inputs larger than L2 (%.2f GB of rays per pass); no flush" % (NA * nt * ND * 4 * NZ * 8 / 1e9),
+            "seed": 1234, "i0": 0, "tmax_km": 1000.0}
+
+
+# ----------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ----------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # before CUDA is initialised in this process (the workers are forked)
+        rps, cores, sample, _ = run_cpu(3, 1)
+        cpu = {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import ionotomo_b200 as ib
+    from ionotomo_b200 import _lib, sharding
+    from ionotomo_b200.ionosphere.synthetic import make_workload
+    from ionotomo_b200.inversion.forward_equation import _ne_from_m, tec_from_ne
+    from ionotomo_b200.inversion.gradient import adjoint_coefficients, backproject, misfit
+    from ionotomo_b200.inversion.host_stream import misfit_and_gradient
+
+    nt = args.nt
+    w = make_workload(Na=NA, Nt=nt * world, Nd=ND, nx=NX, ny=NY, nz=NZ, device="cuda",
+                      t_slice=(rank * nt, (rank + 1) * nt))
+    m_true = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_true"])
+    m_tci = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_prior"])      # model being fitted
+    grid = m_tci.grid()
+    rays = ib.cast_ray((w["origins"], w["directions"]), ib.Fermat(m_tci), w["tmax"], w["Ns"])
+    del w["origins"], w["directions"]
+    Na, Nt, Nd, _, Ns = rays.shape
+    R, V = Na * Nt * Nd, NX * NY * NZ
+    i0 = 0
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    dobs = ib.forward_equation(rays, w["K_ne"], m_true, i0, order=args.order)
+    dobs = dobs + 0.01 * torch.randn(dobs.shape, dtype=torch.float64, device="cuda", generator=gen)
+    CdCt = torch.full_like(dobs, 0.01 ** 2)
+    K_ne = w["K_ne"]
+    m_dev = m_tci.device_M()
+    acc = torch.empty((NX, NY, NZ), dtype=torch.float64, device="cuda")
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    kt = {"fwd": [], "adj": []}
+
+    def step(timed):
+        ne = _ne_from_m(m_dev, K_ne)
+        e0, e1 = ev(), ev()
+        e0.record()
+        tec = tec_from_ne(rays, grid, ne, order=args.order, check_bounds=False)
+        e1.record()
+        g = torch.empty_like(tec)
+        _lib.call("iono_dtec_f64", _lib.ptr(tec), Na, Nt, Nd, i0, _lib.ptr(g), _lib.stream_ptr())
+        S = misfit(g, dobs, CdCt)
+        coef = adjoint_coefficients(g, dobs, CdCt, i0)
+        e2, e3 = ev(), ev()
+        e2.record()
+        backproject(rays, grid, coef, (NX, NY, NZ), order=args.order, check_bounds=False, out=acc)
+        e3.record()
+        sharding.allreduce_sum_(acc)
+        _lib.call("iono_mul_f64", _lib.ptr(ne), _lib.ptr(acc), V, _lib.ptr(acc), _lib.stream_ptr())
+        if timed:
+            kt["fwd"].append((e0, e1))
+            kt["adj"].append((e2, e3))
+        return S
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    fence()
+    l0 = _lib.launch_count
+    t_wall0 = time.time()
+    start, stop = ev(), ev()
+    start.record()
+    for _ in range(args.steps):
+        S = step(True)
+    stop.record()
+    fence()
+    t_wall1 = time.time()
+    launches = _lib.launch_count - l0
+    ms = start.elapsed_time(stop) / args.steps
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    fwd_ms = float(np.mean([a.elapsed_time(b) for a, b in kt["fwd"]]))
+    adj_ms = float(np.mean([a.elapsed_time(b) for a, b in kt["adj"]]))
+    clocks = sampler.window(t_wall0, t_wall1) if sampler else None
+
+    # ---- end to end through the host-array API -------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        rays_h = torch.empty(rays.shape, dtype=torch.float64, pin_memory=True)
+        rays_h.copy_(rays)
+        m_h = torch.empty(m_dev.shape, dtype=torch.float64, pin_memory=True).copy_(m_dev).numpy()
+        dobs_h = torch.empty(dobs.shape, dtype=torch.float64, pin_memory=True).copy_(dobs).numpy()
+        C_h = torch.empty(dobs.shape, dtype=torch.float64, pin_memory=True).copy_(CdCt).numpy()
+        m_host_tci = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], m_h)
+        red = sharding.allreduce_sum_ if world > 1 else None
+        e2e_steps = max(2, min(args.steps, 4))
+        for _ in range(1):
+            misfit_and_gradient(rays_h, K_ne, m_host_tci, i0, dobs_h, C_h, order=args.order, reduce_fn=red)
+        fence()
+        t0 = time.time()
+        for _ in range(e2e_steps):
+            g_h, S_h, grad_h = misfit_and_gradient(rays_h, K_ne, m_host_tci, i0, dobs_h, C_h, order=args.order,
+                                                   reduce_fn=red)
+        fence()
+        dt = (time.time() - t0) / e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt[0])
+        e2e = {"value": R * world / dt, "unit": "rays/s",
+               "h2d_bytes_per_step": int(rays_h.numel() * 8 + m_h.nbytes + dobs_h.nbytes + C_h.nbytes),
+               "d2h_bytes_per_step": int(g_h.nbytes + grad_h.nbytes + 8), "ms_per_step": dt * 1e3,
+               "steps": e2e_steps,
+               "api": "ionotomo_b200.inversion.host_stream.misfit_and_gradient(rays_host, K_ne, m_tci, i0, dobs, CdCt)"}
+        del rays_h
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, peak_src = peaks()
+    bytes_fwd = R * (4 * Ns * 8 + 8) + V * 8
+    bytes_adj = R * (4 * Ns * 8 + 8) + 2 * V * 8
+    kernels = {
+        "ray_sweep_forward": {"ms": fwd_ms, "algorithmic_bytes": bytes_fwd,
+                              "achieved_gbs": bytes_fwd / fwd_ms / 1e6, "frac": bytes_fwd / fwd_ms / 1e6 / hbm,
+                              "rays_per_s": R / fwd_ms * 1e3},
+        "ray_sweep_adjoint": {"ms": adj_ms, "algorithmic_bytes": bytes_adj,
+                              "achieved_gbs": bytes_adj / adj_ms / 1e6, "frac": bytes_adj / adj_ms / 1e6 / hbm,
+                              "rays_per_s": R / adj_ms * 1e3},
+    }
+    dom = "ray_sweep_adjoint" if adj_ms >= fwd_ms else "ray_sweep_forward"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    line = {
+        "metric": "forward+adjoint ray passes per second", "value": R * world / ms * 1e3, "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(world, nt), dx_km=w["dx_km"], dy_km=w["dy_km"], dz_km=w["dz_km"],
+                       ray_order=args.order),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": hbm,
+                     "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src},
+        "kernels": kernels,
+        "pass_frac_of_hbm_roofline": (bytes_fwd + bytes_adj) / ms / 1e6 / hbm,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "misfit": float(S),
+    }
+    print(json.dumps(line), flush=True)
+    if sampler:
+        sampler.stop()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,14 @@ int64_t iono_misfit_scratch_elems(void);
 int iono_misfit_f64(const double *g, const double *dobs, const double *CdCt, int64_t n,
                     double *scratch, double *out, void *stream);
 
+/* ---- host <-> device staging ---------------------------------------------------
+ * Strided block copy of `height` rows of `width_bytes` from pinned or pageable HOST memory
+ * to DEVICE memory (cudaMemcpy2DAsync).  Used to stream time blocks rays[:, t0:t1] of a
+ * host-resident (Na,Nt,Nd,4,Ns) ray array -- the layout the reference's callers hold
+ * (geometry/calc_rays.py:78-92) -- while the previous block is being integrated. */
+int iono_copy2d_h2d(void *dst_dev, int64_t dst_pitch_bytes, const void *src_host, int64_t src_pitch_bytes,
+                    int64_t width_bytes, int64_t height, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

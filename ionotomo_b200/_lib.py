@@ -38,6 +38,7 @@ SIGNATURES = {
     "iono_tec_adjoint_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "iono_misfit_scratch_elems": (_i64, []),
     "iono_misfit_f64": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "iono_copy2d_h2d": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
 }
 
 # kernels launched per C call (for bench.py's ``gpu_launches``; memsets are not counted)

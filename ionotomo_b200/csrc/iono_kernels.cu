@@ -400,3 +400,17 @@ extern "C" int iono_misfit_f64(const double *g, const double *dobs, const double
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
 }
+
+// ---------------------------------------------------------------------------
+// host -> device strided staging
+// ---------------------------------------------------------------------------
+extern "C" int iono_copy2d_h2d(void *dst, int64_t dpitch, const void *src, int64_t spitch, int64_t width,
+                               int64_t height, void *stream) {
+    if (width < 0 || height < 0 || dpitch < width || spitch < width)
+        return fail(IONO_EBADARG, "iono_copy2d_h2d: bad argument");
+    if (width == 0 || height == 0) return IONO_OK;
+    if (!dst || !src) return fail(IONO_EBADARG, "iono_copy2d_h2d: NULL pointer");
+    CU_CHECK(cudaMemcpy2DAsync(dst, (size_t)dpitch, src, (size_t)spitch, (size_t)width, (size_t)height,
+                               cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return IONO_OK;
+}

@@ -1,0 +1,102 @@
+"""Forward + gradient for HOST-resident inputs, with the ray array streamed through the GPU.
+
+The reference's callers hold ``rays`` as a NumPy array (``geometry/calc_rays.py:78-92``) and
+call ``forward_equation`` then ``compute_gradient`` on it every iteration
+(``tests/test_inversion.py:30-39``).  At the LOFAR scale that array is 5 GB, so a drop-in
+call is bound by the host link.  ``misfit_and_gradient`` makes one pass: time blocks
+``rays[:, t0:t1]`` are copied host -> device on a side stream (``iono_copy2d_h2d``) into a
+double buffer while the previous block is integrated and back-projected.  A time block is
+self-contained for the exact adjoint because the reference-antenna coupling
+(``tec - tec[i0]``, ``forward_equation.py:50``) only links rays of the same (time, direction).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .forward_equation import _ne_from_m, tec_from_ne
+from .gradient import adjoint_coefficients
+
+
+def pin(a):
+    """A pinned float64 torch view of a NumPy array (copies once into pinned memory)."""
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+    return t if t.is_pinned() else t.pin_memory()
+
+
+def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_times=None, check_bounds=True,
+                        reduce_fn=None):
+    """``(dtec, S, gradient)`` as NumPy/float from host arrays.
+
+    ``rays`` may be a NumPy array or a (preferably pinned) CPU tensor of shape
+    ``(Na, Nt, Nd, 4, Ns)``.  Equivalent to ``forward_equation`` + misfit + ``compute_gradient``
+    of this package (and to the reference's ``func_and_gradient`` sketch,
+    tests/test_inversion.py:30-39, with the exact adjoint).
+    """
+    _lib.require_cuda()
+    lib = _lib.load()
+    rays_h = rays if isinstance(rays, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rays, dtype=np.float64))
+    assert rays_h.device.type == "cpu" and rays_h.dtype == torch.float64 and rays_h.is_contiguous()
+    Na, Nt, Nd, four, Ns = rays_h.shape
+    dev = torch.device("cuda", torch.cuda.current_device())
+    row_bytes = Nd * 4 * Ns * 8
+    if block_times is None:   # ~256 MB blocks
+        block_times = max(1, min(Nt, (256 << 20) // max(1, Na * row_bytes)))
+    main = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    side.wait_stream(main)
+    bufs = [torch.empty((Na, block_times, Nd, 4, Ns), dtype=torch.float64, device=dev) for _ in range(2)]
+    for t in bufs:
+        t.record_stream(side)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    blocks = [(t0, min(Nt, t0 + block_times)) for t0 in range(0, Nt, block_times)]
+
+    def upload(b):
+        t0, t1 = blocks[b]
+        w = (t1 - t0) * row_bytes
+        with torch.cuda.stream(side):
+            if b >= 2:
+                side.wait_event(free[b % 2])
+            src = rays_h.data_ptr() + t0 * row_bytes
+            _lib.call("iono_copy2d_h2d", ctypes.c_void_p(bufs[b % 2].data_ptr()), w, ctypes.c_void_p(src),
+                      Nt * row_bytes, w, Na, ctypes.c_void_p(side.cuda_stream))
+            ready[b % 2].record(side)
+
+    m_dev = m_tci.device_M()
+    ne = _ne_from_m(m_dev, K_ne)
+    dobs_d, C_d = _lib.to_device(dobs), _lib.to_device(CdCt)
+    dtec = torch.empty((Na, Nt, Nd), dtype=torch.float64, device=dev)
+    acc = torch.zeros(tuple(m_dev.shape), dtype=torch.float64, device=dev)
+    oob = torch.zeros(1, dtype=torch.int64, device=dev)
+    oob_tot = torch.zeros(1, dtype=torch.int64, device=dev)
+    grid = m_tci.grid()
+    if blocks:
+        upload(0)
+    for b, (t0, t1) in enumerate(blocks):
+        if b + 1 < len(blocks):
+            upload(b + 1)
+        main.wait_event(ready[b % 2])
+        tb = t1 - t0
+        # the 2-D copy packs the block densely, also the last, shorter one
+        rb = bufs[b % 2].reshape(-1)[:Na * tb * Nd * 4 * Ns].reshape(Na, tb, Nd, 4, Ns)
+        tec = tec_from_ne(rb, grid, ne, order=order, check_bounds=False)
+        d = torch.empty_like(tec)
+        _lib.call("iono_dtec_f64", _lib.ptr(tec), Na, tb, Nd, int(i0), _lib.ptr(d), _lib.stream_ptr())
+        dtec[:, t0:t1] = d
+        coef = adjoint_coefficients(d, dobs_d[:, t0:t1].contiguous(), C_d[:, t0:t1].contiguous(), i0)
+        _lib.call("iono_tec_adjoint_f64", grid.handle, _lib.ptr(rb), Na, tb, Nd, Ns, _lib.ptr(coef),
+                  _lib.ORDERS[order], 0, _lib.ptr(acc), ctypes.c_void_p(oob.data_ptr()), _lib.stream_ptr())
+        oob_tot += oob
+        free[b % 2].record(main)
+    if reduce_fn is not None:
+        acc = reduce_fn(acc)
+    from .gradient import misfit
+    S = misfit(dtec, dobs_d, C_d)
+    _lib.call("iono_mul_f64", _lib.ptr(ne), _lib.ptr(acc), acc.numel(), _lib.ptr(acc), _lib.stream_ptr())
+    if check_bounds and int(oob_tot.item()) != 0:
+        raise ValueError("One of the requested xi is out of bounds (%d ray samples outside the grid)"
+                         % int(oob_tot.item()))
+    main.wait_stream(side)
+    return dtec.cpu().numpy(), float(S), acc.cpu().numpy()

@@ -1,0 +1,71 @@
+"""Multi-process (gloo, world_size 2, CPU) check of the ray-sharding scheme: time-sharded
+forward needs no exchange, and the allreduce of per-shard backprojections equals the
+single-process adjoint.  The compute here is the oracle (CPU); the GPU kernels plug into the
+same hooks (ionotomo_b200.sharding.allreduce_sum_ as ``reduce_fn``)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import ionotomo_oracle as O
+    from tests.problems import small_problem
+    from ionotomo_b200 import sharding
+    P = small_problem(42, 4, 5, 6, 16, 10, 9, 12)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 16)
+    i0 = 1
+    g = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], i0)
+    rng = np.random.RandomState(0)
+    dobs = g + 0.01 * rng.normal(size=g.shape)
+    CdCt = np.full(g.shape, 1e-4)
+    t0, t1 = sharding.time_shard(rays.shape[1], rank, world)
+    # forward on the shard alone reproduces the full forward on those times
+    g_loc = O.forward_equation(rays[:, t0:t1], P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], i0)
+    assert np.array_equal(g_loc, g[:, t0:t1])
+    dd = O.weighted_residual(g_loc, dobs[:, t0:t1], CdCt[:, t0:t1])
+    acc = O.backproject(rays[:, t0:t1], P["xvec"], P["yvec"], P["zvec"], O.adjoint_ray_coefficients(dd, i0))
+    acc_t = torch.from_numpy(acc)
+    sharding.allreduce_sum_(acc_t)
+    S = sharding.sharded_misfit(torch.tensor(O.misfit(g_loc, dobs[:, t0:t1], CdCt[:, t0:t1])))
+    grad = O.ne_from_m(P["m"], P["K_ne"]) * acc_t.numpy()
+    ref = O.gradient_exact(rays, g, dobs, i0, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], CdCt)
+    ok = np.abs(grad - ref).max() <= 1e-12 * np.abs(ref).max() and abs(S - O.misfit(g, dobs, CdCt)) <= 1e-12 * S
+    assert sharding.world() == (rank, world)
+    if rank == 0:
+        out.put(bool(ok))
+    dist.destroy_process_group()
+
+
+def test_time_shard_partition():
+    from ionotomo_b200.sharding import time_shard
+    for Nt in (1, 7, 100, 101):
+        for world in (1, 2, 3, 8):
+            blocks = [time_shard(Nt, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == Nt
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_sharded_gradient_gloo_world2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) is True
