@@ -98,6 +98,37 @@ __device__ __forceinline__ void locate_s(const double2 *__restrict__ tab, const 
     }
 }
 
+// Adjoint scatter of one sample per lane: a * (trilinear hat weights) into the 8 corners of
+// cell v.  Lanes hold consecutive samples of one ray, so the cell of lane l+1 is usually the
+// one directly above the cell of lane l (v+1: same column, next z node); then the upper-node
+// share of lane l and the lower-node share of lane l+1 hit the same four addresses.  They
+// are combined with a shuffle so that the pair costs one fp64 reduction instead of two.
+__device__ __forceinline__ void scatter_sample(double *__restrict__ accp, int v, int sy, int sx, double a,
+                                               double tx, double ty, double tz, int lane, bool valid) {
+    if (!valid) { a = 0.0; v = -2; }
+    const double ax1 = a * tx, ax0 = a - ax1;
+    const double a01 = ax0 * ty, a00 = ax0 - a01;
+    const double a11 = ax1 * ty, a10 = ax1 - a11;
+    const double h00 = a00 * tz, h01 = a01 * tz, h10 = a10 * tz, h11 = a11 * tz;
+    double l00 = a00 - h00, l01 = a01 - h01, l10 = a10 - h10, l11 = a11 - h11;
+    const unsigned full = 0xffffffffu;
+    const int v_next = __shfl_down_sync(full, v, 1);
+    const int v_prev = __shfl_up_sync(full, v, 1);
+    const bool give = (lane < 31) && (v_next == v + 1);      // my upper share goes to lane+1
+    const bool take = (lane > 0) && (v_prev == v - 1);       // I absorb lane-1's upper share
+    const double p00 = __shfl_up_sync(full, h00, 1), p01 = __shfl_up_sync(full, h01, 1);
+    const double p10 = __shfl_up_sync(full, h10, 1), p11 = __shfl_up_sync(full, h11, 1);
+    if (take) { l00 += p00; l01 += p01; l10 += p10; l11 += p11; }
+    if (valid) {
+        double *c = accp + v;
+        atomicAdd(c, l00); atomicAdd(c + sy, l01); atomicAdd(c + sx, l10); atomicAdd(c + sx + sy, l11);
+        if (!give) {
+            atomicAdd(c + 1, h00); atomicAdd(c + sy + 1, h01);
+            atomicAdd(c + sx + 1, h10); atomicAdd(c + sx + sy + 1, h11);
+        }
+    }
+}
+
 // MODE 0: forward, MODE 1: adjoint
 template <int MODE, bool UNIFORM, int C, bool BULK, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p) {
@@ -183,7 +214,10 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
             const double *ss_ = stage + StageLayout<C>::S_OFF + 2;   // ss_[j] = s[c0 + j]
             const int n_c = min(C, Ns - c0);
 #pragma unroll 2
-            for (int j = lane; j < n_c; j += 32) {
+            for (int jb = 0; jb < n_c; jb += 32) {
+                const int j = jb + lane;
+                const bool valid = j < n_c;
+                if (MODE == 0 && !valid) continue;
                 const int i = c0 + j;
                 int ix, iy, iz;
                 double tx, ty, tz;
@@ -191,7 +225,7 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
                 locate_s<UNIFORM>(tabx, ax, sx_[j], ix, tx, oob);
                 locate_s<UNIFORM>(taby, ay, sy_[j], iy, ty, oob);
                 locate_s<UNIFORM>(tabz, az, sz_[j], iz, tz, oob);
-                n_oob += oob;
+                n_oob += (oob && valid);
                 const double w = simpson_weight(i, Ns, n_odd, ss_[j - 2], ss_[j - 1], ss_[j], ss_[j + 1], ss_[j + 2]);
                 const int v = (ix * ny + iy) * nz + iz;
                 if (MODE == 0) {
@@ -205,16 +239,7 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
                     const double c0_ = fma(ty, c01 - c00, c00), c1_ = fma(ty, c11 - c10, c10);
                     acc = fma(w, fma(tx, c1_ - c0_, c0_), acc);
                 } else {
-                    double *c = p.acc + v;
-                    const double a = coef * w;
-                    const double ax1 = a * tx, ax0 = a - ax1;
-                    const double a01 = ax0 * ty, a00 = ax0 - a01;
-                    const double a11 = ax1 * ty, a10 = ax1 - a11;
-                    double hi;
-                    hi = a00 * tz; atomicAdd(c, a00 - hi); atomicAdd(c + 1, hi);
-                    hi = a01 * tz; atomicAdd(c + sy, a01 - hi); atomicAdd(c + sy + 1, hi);
-                    hi = a10 * tz; atomicAdd(c + sx, a10 - hi); atomicAdd(c + sx + 1, hi);
-                    hi = a11 * tz; atomicAdd(c + sx + sy, a11 - hi); atomicAdd(c + sx + sy + 1, hi);
+                    scatter_sample(p.acc, v, sy, sx, coef * w, tx, ty, tz, lane, valid);
                 }
             }
             us = (us + 1 == stages) ? 0 : us + 1;
@@ -236,14 +261,13 @@ struct SweepConfig {
 
 static SweepConfig sweep_config(int mode, int Ns) {
     SweepConfig c;
-    c.warps = 16;
+    c.warps = (mode == 0) ? 24 : 16;
     c.stages = 2;
     c.chunk = (Ns <= 64) ? 64 : 128;
     const char *e;
     if ((e = getenv("IONO_SWEEP_WARPS"))) c.warps = atoi(e);
     if ((e = getenv("IONO_SWEEP_STAGES"))) c.stages = atoi(e);
     if ((e = getenv("IONO_SWEEP_CHUNK"))) c.chunk = atoi(e);
-    (void)mode;
     if (c.warps < 1) c.warps = 1;
     if (c.warps > 24) c.warps = 24;
     if (c.stages < 2) c.stages = 2;
