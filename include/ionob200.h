@@ -103,6 +103,23 @@ int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, i
                          const double *coef, int order, int zero_first, double *acc,
                          unsigned long long *oob_count, void *stream);
 
+/* ---- voxel-binned back-projector (adjoint without atomics) ----------------------
+ * The same linear map as iono_tec_adjoint_f64, assembled once per ray geometry in
+ * voxel-major sparse form (sorted (voxel, ray, weight) triples; needs ~12 B per
+ * distinct (voxel, ray) pair, ~520 pairs per ray at the LOFAR case) and then applied
+ * as a gather: out[v] = scale[v] * sum_ray A[v,ray] * coef[ray]  (scale may be NULL).
+ * Worth it when the rays are reused across iterations, as in every reference driver
+ * (tests/test_inversion.py:30-39, bfgs_dask.py:207-340, iterative_newton.py:954-1017).
+ * create() synchronises the stream; apply() is asynchronous and bit-reproducible. */
+typedef struct iono_backprojector *iono_backprojector_t;
+int iono_backprojector_create(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
+                              iono_backprojector_t *bp_out, unsigned long long *oob_count, void *stream);
+int iono_backprojector_apply_f64(iono_backprojector_t bp, const double *coef, const double *scale,
+                                 double *out, void *stream);
+long long iono_backprojector_nnz(iono_backprojector_t bp);
+long long iono_backprojector_bytes(iono_backprojector_t bp);
+int iono_backprojector_destroy(iono_backprojector_t bp);
+
 /* ---- misfit ---------------------------------------------------------------
  * out[0] = sum((g-dobs)^2/(CdCt+1e-15))/2 (inversion/line_search.py:48-49).
  * Deterministic two-stage reduction; `scratch` needs iono_misfit_scratch_elems()

@@ -1,0 +1,445 @@
+// Voxel-binned back-projector: the adjoint without atomics.
+// Included by iono_kernels.cu (one translation unit).
+//
+// The scatter formulation of the adjoint (ray_sweep_kernel<ADJ>) is bound by the rate at
+// which an SM can issue global reductions (measured: one warp-level RED per ~39 cycles,
+// whatever the type, lane count or sector count -- tools/probes/atomics_probe.cu).  Inside
+// an inversion the ray geometry is fixed while the model and the residuals change every
+// iteration (reference driver loop: tests/test_inversion.py:30-39, bfgs_dask.py:207-340), so
+// the linear operator  acc[v] = sum_ray coef[ray] * A[v,ray],
+//     A[v,ray] = sum_s w_s(ray) * phi_v(x_s(ray))     (Simpson-avg weights x trilinear hats)
+// can be assembled ONCE per geometry in voxel-major (CSC-like) form and then applied as a
+// pure gather: one warp per voxel streams that voxel's (ray, weight) list, gathers coef[ray]
+// from L2 and reduces with shuffles.  No atomics, bit-reproducible, and the result is the
+// same matrix the forward kernel applies, so <Gx,y> = <x,G^T y> still holds to rounding.
+//
+// Assembly (all on the GPU): emit 8 (voxel<<32|ray, weight) pairs per sample, radix-sort by
+// key (CUB), sum runs of equal key (a ray visits a voxel through 1-3 consecutive samples),
+// split the keys into a ray-index array and voxel offsets.
+#pragma once
+#include <cub/cub.cuh>
+#include <cuda/std/functional>
+
+struct iono_backprojector {
+    unsigned int *ray_idx;   // [nnz]
+    double *weight;          // [nnz]
+    long long *ptr;          // [n_rows+1] entry offsets of the non-empty rows
+    unsigned int *row_voxel; // [n_rows] voxel index of each non-empty row
+    long long n_rows;
+    int *long_rows;          // voxels whose entries span more than one segment
+    int n_long;
+    double *partial;         // [2 * nseg] per-segment sums of the straddling rows
+    int2 *items;             // [nseg] first and last row of every segment
+    long long nnz;
+    long long V;
+    long long R;
+    int Na, Nt, Nd;
+    double *coef_perm;       // [R] coefficients in the internal ray order (a, d, t)
+    int device;
+};
+
+// Internal ray numbering of the back-projector: time fastest, (a*Nd + d)*Nt + t.  Rays of one
+// (antenna, direction) at consecutive times are nearly identical and meet in the same voxels,
+// so with this order a voxel's sorted entry list references runs of adjacent coefficients
+// (4 per 32-byte sector) instead of one sector per entry.
+__global__ void __launch_bounds__(256) permute_coef_kernel(const double *__restrict__ coef, int Na, int Nt, int Nd,
+                                                            double *__restrict__ out) {
+    __shared__ double tile[32][33];
+    // per antenna: (Nt, Nd) -> (Nd, Nt), 32x32 tiles
+    const int tiles_d = (Nd + 31) / 32, tiles_t = (Nt + 31) / 32;
+    const int per_a = tiles_d * tiles_t;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int b = blockIdx.x; b < Na * per_a; b += gridDim.x) {
+        const int a = b / per_a, r = b % per_a;
+        const int t0 = (r / tiles_d) * 32, d0 = (r % tiles_d) * 32;
+        const double *src = coef + (long long)a * Nt * Nd;
+        double *dst = out + (long long)a * Nt * Nd;
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8)
+            if (t0 + j < Nt && d0 + tx < Nd) tile[j][tx] = src[(long long)(t0 + j) * Nd + d0 + tx];
+        __syncthreads();
+        for (int j = ty; j < 32; j += 8)
+            if (d0 + j < Nd && t0 + tx < Nt) dst[(long long)(d0 + j) * Nt + t0 + tx] = tile[tx][j];
+    }
+}
+
+template <bool UNIFORM>
+__global__ void __launch_bounds__(256) emit_entries_kernel(Grid g, const double *__restrict__ rays, int R, int Nt,
+                                                            int Nd, int Ns,
+                                                            unsigned long long *__restrict__ keys,
+                                                            double *__restrict__ vals,
+                                                            unsigned long long *oob_count) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    const int ny = g.ax[1].n, nz = g.ax[2].n;
+    const bool n_odd = Ns & 1;
+    unsigned int n_oob = 0;
+    for (int ray = warp_global; ray < R; ray += n_warps) {
+        const double *rp = rays + (long long)ray * 4 * Ns;
+        const double *sp = rp + 3 * Ns;
+        for (int i = lane; i < Ns; i += 32) {
+            int ix, iy, iz;
+            double tx, ty, tz;
+            bool oob = false;
+            locate<UNIFORM>(g.ax[0].tab, g.ax[0], __ldg(rp + i), ix, tx, oob);
+            locate<UNIFORM>(g.ax[1].tab, g.ax[1], __ldg(rp + Ns + i), iy, ty, oob);
+            locate<UNIFORM>(g.ax[2].tab, g.ax[2], __ldg(rp + 2 * Ns + i), iz, tz, oob);
+            n_oob += oob;
+            const double sm2 = (i >= 2) ? __ldg(sp + i - 2) : 0.0, sm1 = (i >= 1) ? __ldg(sp + i - 1) : 0.0;
+            const double s0 = __ldg(sp + i);
+            const double sp1 = (i + 1 < Ns) ? __ldg(sp + i + 1) : 0.0, sp2 = (i + 2 < Ns) ? __ldg(sp + i + 2) : 0.0;
+            const double a = simpson_weight(i, Ns, n_odd, sm2, sm1, s0, sp1, sp2);
+            const unsigned long long v = (unsigned long long)((ix * ny + iy) * nz + iz);
+            const unsigned long long sy = nz, sx = (unsigned long long)ny * nz;
+            const double ax1 = a * tx, ax0 = a - ax1;
+            const double a01 = ax0 * ty, a00 = ax0 - a01;
+            const double a11 = ax1 * ty, a10 = ax1 - a11;
+            const long long e = ((long long)ray * Ns + i) * 8;
+            const int ra = ray / (Nt * Nd), rem = ray - ra * (Nt * Nd);
+            const int rt = rem / Nd, rd = rem - rt * Nd;
+            const unsigned long long r = (unsigned long long)((ra * Nd + rd) * Nt + rt);
+            double hi;
+            hi = a00 * tz; keys[e + 0] = ((v) << 32) | r;              vals[e + 0] = a00 - hi;
+                           keys[e + 1] = ((v + 1) << 32) | r;          vals[e + 1] = hi;
+            hi = a01 * tz; keys[e + 2] = ((v + sy) << 32) | r;         vals[e + 2] = a01 - hi;
+                           keys[e + 3] = ((v + sy + 1) << 32) | r;     vals[e + 3] = hi;
+            hi = a10 * tz; keys[e + 4] = ((v + sx) << 32) | r;         vals[e + 4] = a10 - hi;
+                           keys[e + 5] = ((v + sx + 1) << 32) | r;     vals[e + 5] = hi;
+            hi = a11 * tz; keys[e + 6] = ((v + sx + sy) << 32) | r;    vals[e + 6] = a11 - hi;
+                           keys[e + 7] = ((v + sx + sy + 1) << 32) | r; vals[e + 7] = hi;
+        }
+    }
+    if (n_oob) atomicAdd(oob_count, (unsigned long long)n_oob);
+}
+
+__global__ void __launch_bounds__(256) split_keys_kernel(const unsigned long long *__restrict__ keys, long long n,
+                                                          unsigned int *__restrict__ ray_idx) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride)
+        ray_idx[e] = (unsigned int)(keys[e] & 0xffffffffull);
+}
+
+struct KeyVoxel {
+    __host__ __device__ __forceinline__ unsigned int operator()(unsigned long long k) const {
+        return (unsigned int)(k >> 32);
+    }
+};
+
+// Apply = a balanced sweep over the ENTRY stream, not over voxels: row lengths range from 0 to
+// ~1e6 (heavy voxels sit under the array core, where every ray of a station starts in the same
+// cell), so the entry index space is cut into segments of BP_SEG entries, one CTA each:
+//   1. products weight[k]*coef[ray_idx[k]] of the segment -> shared memory (coalesced, 4 loads
+//      in flight per thread);
+//   2. every row (voxel) that intersects the segment is summed from shared memory by one warp;
+//      rows completely inside are written to out[], the (at most two) rows that continue into
+//      a neighbouring segment go to partial[2*seg + slot];
+//   3. a small kernel adds the partials of each straddling row in segment order.
+// slot 0: the row covers the segment's first entry; slot 1: the row begins inside the segment.
+// Everything is a fixed reduction tree: bit-reproducible.
+constexpr int BP_SEG = 2048;
+
+// voxel (row) that contains entry k: largest v with ptr[v] <= k
+__device__ __forceinline__ long long row_of_entry(const long long *__restrict__ ptr, long long V, long long k) {
+    long long lo = 0, hi = V;   // invariant: ptr[lo] <= k < ptr[hi]
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (__ldg(ptr + mid) <= k) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Build time: first and last row of every segment.
+__global__ void __launch_bounds__(256) segment_rows_kernel(const long long *__restrict__ ptr, long long V,
+                                                            long long nnz, int2 *__restrict__ seg_rows) {
+    const long long nseg = (nnz + BP_SEG - 1) / BP_SEG;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long seg = (long long)blockIdx.x * blockDim.x + threadIdx.x; seg < nseg; seg += stride) {
+        const long long k0 = seg * BP_SEG, k1 = min(k0 + (long long)BP_SEG, nnz);
+        seg_rows[seg] = make_int2((int)row_of_entry(ptr, V, k0), (int)row_of_entry(ptr, V, k1 - 1));
+    }
+}
+
+// Build time: rows that span more than one segment.
+__global__ void __launch_bounds__(256) find_straddling_rows_kernel(const long long *__restrict__ ptr, long long V,
+                                                                    int *__restrict__ rows, int *count, int cap) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride) {
+        const long long b = ptr[v], e = ptr[v + 1];
+        if (e > b && b / BP_SEG != (e - 1) / BP_SEG) {
+            const int k = atomicAdd(count, 1);
+            if (k < cap) rows[k] = (int)v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *__restrict__ seg_rows,
+                                                                    const long long *__restrict__ ptr,
+                                                                    const unsigned int *__restrict__ row_voxel,
+                                                                    const unsigned int *__restrict__ ray_idx,
+                                                                    const double *__restrict__ weight,
+                                                                    const double *__restrict__ coef,
+                                                                    const double *__restrict__ scale, long long nnz,
+                                                                    double *__restrict__ out,
+                                                                    double *__restrict__ partial) {
+    // double-buffered segment of the entry stream, filled by TMA bulk copies
+    extern __shared__ __align__(128) unsigned char bp_smem[];
+    double (*w_s)[BP_SEG] = reinterpret_cast<double (*)[BP_SEG]>(bp_smem);
+    unsigned int (*r_s)[BP_SEG] = reinterpret_cast<unsigned int (*)[BP_SEG]>(bp_smem + 2 * BP_SEG * 8);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(bp_smem + 2 * BP_SEG * 12);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long nseg = (nnz + BP_SEG - 1) / BP_SEG;
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const uint64_t pol = policy_evict_first();
+    auto issue = [&](long long seg, int buf) {   // arrays are padded to a whole number of segments
+        mbar_expect_tx(&bar[buf], BP_SEG * 12);
+        bulk_g2s(w_s[buf], weight + seg * BP_SEG, BP_SEG * 8, &bar[buf], pol);
+        bulk_g2s(r_s[buf], ray_idx + seg * BP_SEG, BP_SEG * 4, &bar[buf], pol);
+    };
+    if (threadIdx.x == 0 && (long long)blockIdx.x < nseg) issue(blockIdx.x, 0);
+    unsigned int phase = 0;
+    int buf = 0;
+    for (long long seg = blockIdx.x; seg < nseg; seg += gridDim.x, buf ^= 1) {
+        const long long k0 = seg * BP_SEG, k1 = min(k0 + (long long)BP_SEG, nnz);
+        if (threadIdx.x == 0 && seg + gridDim.x < nseg) issue(seg + gridDim.x, buf ^ 1);
+        mbar_wait(&bar[buf], (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        // 1. products in place: BP_SEG/256 independent coefficient gathers per thread
+        double *prod = w_s[buf];
+        {
+            constexpr int PER = BP_SEG / 256;
+            double c[PER];
+#pragma unroll
+            for (int u = 0; u < PER; ++u) c[u] = __ldg(coef + r_s[buf][threadIdx.x + u * 256]);
+#pragma unroll
+            for (int u = 0; u < PER; ++u) prod[threadIdx.x + u * 256] *= c[u];
+        }
+        __syncthreads();
+        // 2. one warp per row
+        const int2 rr = seg_rows[seg];
+        for (int r = rr.x + warp; r <= rr.y; r += 8) {
+            const long long b = __ldg(ptr + r), e = __ldg(ptr + r + 1);
+            const int lo = (int)(max(b, k0) - k0), hi = (int)(min(e, k1) - k0);
+            double s0 = 0.0, s1 = 0.0;
+            int j = lo + lane;
+            for (; j + 32 < hi; j += 64) { s0 += prod[j]; s1 += prod[j + 32]; }
+            if (j < hi) s0 += prod[j];
+            const double s = warp_sum(s0 + s1);
+            if (lane == 0) {
+                if (b >= k0 && e <= k1) {
+                    const unsigned int v = __ldg(row_voxel + r);
+                    out[v] = scale ? s * __ldg(scale + v) : s;
+                } else {
+                    partial[2 * seg + (b > k0 ? 1 : 0)] = s;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// One warp per straddling row: add its partials in segment order.
+__global__ void __launch_bounds__(256) backproject_combine_kernel(const int *__restrict__ rows, int n_rows,
+                                                                   const long long *__restrict__ ptr,
+                                                                   const unsigned int *__restrict__ row_voxel,
+                                                                   const double *__restrict__ partial,
+                                                                   const double *__restrict__ scale,
+                                                                   double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int r = warp_global; r < n_rows; r += n_warps) {
+        const long long row = rows[r];
+        const long long v = row_voxel[row];
+        const long long b = ptr[row], e = ptr[row + 1];
+        const long long s_first = b / BP_SEG, s_last = (e - 1) / BP_SEG;
+        double s = 0.0;
+        for (long long sg = s_first + lane; sg <= s_last; sg += 32) {
+            const int slot = (sg == s_first && b > sg * BP_SEG) ? 1 : 0;
+            s += partial[2 * sg + slot];
+        }
+        s = warp_sum(s);
+        if (lane == 0) out[v] = scale ? s * scale[v] : s;
+    }
+}
+
+extern "C" int iono_backprojector_destroy(iono_backprojector_t h) {
+    if (!h) return IONO_OK;
+    cudaFree(h->ray_idx);
+    cudaFree(h->weight);
+    cudaFree(h->ptr);
+    cudaFree(h->row_voxel);
+    cudaFree(h->long_rows);
+    cudaFree(h->partial);
+    cudaFree(h->items);
+    cudaFree(h->coef_perm);
+    delete h;
+    return IONO_OK;
+}
+
+extern "C" long long iono_backprojector_nnz(iono_backprojector_t h) { return h ? h->nnz : 0; }
+extern "C" long long iono_backprojector_bytes(iono_backprojector_t h) {
+    return h ? h->nnz * 12 + (h->n_rows + 1) * 12 : 0;
+}
+
+extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
+                                         iono_backprojector_t *out, unsigned long long *oob_count, void *stream) {
+    const long long R = (long long)Na * Nt * Nd;
+    if (!grid || !out || !oob_count || Na < 0 || Nt < 0 || Nd < 0 || Ns < 1 || (R > 0 && !rays))
+        return fail(IONO_EBADARG, "iono_backprojector_create: bad argument");
+    if (sweep_size_check(grid, R, Ns)) return IONO_EBADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long V = (long long)grid->nx * grid->ny * grid->nz;
+    const long long N = (Ns >= 2) ? R * Ns * 8 : 0;
+    CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
+
+    iono_backprojector *h = new iono_backprojector();
+    h->ray_idx = nullptr; h->weight = nullptr; h->ptr = nullptr; h->row_voxel = nullptr; h->n_rows = 0; h->long_rows = nullptr; h->n_long = 0; h->partial = nullptr; h->items = nullptr;
+    h->nnz = 0; h->V = V; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->coef_perm = nullptr;
+    cudaGetDevice(&h->device);
+    unsigned long long *k0 = nullptr, *k1 = nullptr, *uk = nullptr;
+    double *v0 = nullptr, *v1 = nullptr;
+    long long *d_runs = nullptr;
+    void *tmp = nullptr;
+    cudaError_t e = cudaSuccess;
+    auto cleanup = [&]() {
+        cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(uk); cudaFree(d_runs); cudaFree(tmp);
+    };
+#define BP_TRY(expr)                                                                              \
+    do {                                                                                          \
+        e = (expr);                                                                               \
+        if (e != cudaSuccess) {                                                                   \
+            cleanup();                                                                            \
+            iono_backprojector_destroy(h);                                                        \
+            return fail(IONO_ECUDA, "iono_backprojector_create: %s: %s", #expr, cudaGetErrorString(e)); \
+        }                                                                                         \
+    } while (0)
+
+    BP_TRY(cudaMalloc(&h->coef_perm, (size_t)(R > 0 ? R : 1) * sizeof(double)));
+    long long M = 0;
+    if (N > 0) {
+        BP_TRY(cudaMalloc(&k0, N * 8));
+        BP_TRY(cudaMalloc(&v0, N * 8));
+        BP_TRY(cudaMalloc(&k1, N * 8));
+        BP_TRY(cudaMalloc(&v1, N * 8));
+        const int ctas = sm_count() * 8;
+        if (grid->uniform)
+            emit_entries_kernel<true><<<ctas, 256, 0, st>>>(grid->dev, rays, (int)R, Nt, Nd, Ns, k0, v0, oob_count);
+        else
+            emit_entries_kernel<false><<<ctas, 256, 0, st>>>(grid->dev, rays, (int)R, Nt, Nd, Ns, k0, v0, oob_count);
+        BP_TRY(cudaGetLastError());
+        // sort by (voxel, ray): only the populated key bits
+        int rbits = 1, vbits = 1;
+        while ((1LL << rbits) < R) ++rbits;
+        while ((1LL << vbits) < V) ++vbits;
+        (void)rbits;
+        const int end_bit = 32 + vbits;
+        cub::DoubleBuffer<unsigned long long> dk(k0, k1);
+        cub::DoubleBuffer<double> dv(v0, v1);
+        size_t tmp_bytes = 0;
+        BP_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, N, 0, end_bit, st));
+        BP_TRY(cudaMalloc(&tmp, tmp_bytes));
+        BP_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, N, 0, end_bit, st));
+        cudaFree(tmp); tmp = nullptr;
+        unsigned long long *ks = dk.Current(), *kalt = dk.Alternate();
+        double *vs = dv.Current(), *valt = dv.Alternate();
+        // merge runs of equal (voxel, ray): unique keys -> kalt, sums -> valt
+        BP_TRY(cudaMalloc(&d_runs, sizeof(long long)));
+        tmp_bytes = 0;
+        BP_TRY(cub::DeviceReduce::ReduceByKey(nullptr, tmp_bytes, ks, kalt, vs, valt, d_runs, ::cuda::std::plus<>{}, N, st));
+        BP_TRY(cudaMalloc(&tmp, tmp_bytes));
+        BP_TRY(cub::DeviceReduce::ReduceByKey(tmp, tmp_bytes, ks, kalt, vs, valt, d_runs, ::cuda::std::plus<>{}, N, st));
+        BP_TRY(cudaMemcpyAsync(&M, d_runs, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        BP_TRY(cudaStreamSynchronize(st));
+        cudaFree(tmp); tmp = nullptr;
+        // release the sorted inputs before allocating the final arrays
+        if (ks == k0) { cudaFree(k0); k0 = nullptr; cudaFree(v0); v0 = nullptr; }
+        else          { cudaFree(k1); k1 = nullptr; cudaFree(v1); v1 = nullptr; }
+        const long long Mpad = ((M + BP_SEG - 1) / BP_SEG) * BP_SEG + BP_SEG;   // whole segments (TMA copies)
+        BP_TRY(cudaMalloc(&h->ray_idx, Mpad * sizeof(unsigned int)));
+        BP_TRY(cudaMalloc(&h->weight, Mpad * sizeof(double)));
+        BP_TRY(cudaMemsetAsync(h->ray_idx, 0, Mpad * sizeof(unsigned int), st));
+        BP_TRY(cudaMemsetAsync(h->weight, 0, Mpad * sizeof(double), st));
+        BP_TRY(cudaMemcpyAsync(h->weight, valt, M * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        split_keys_kernel<<<ew_grid(M), 256, 0, st>>>(kalt, M, h->ray_idx);
+        BP_TRY(cudaGetLastError());
+        // non-empty rows: run-length encode the voxel part of the sorted unique keys
+        {
+            const long long max_rows = (M < V ? M : V) + 1;
+            long long *d_len = nullptr;
+            BP_TRY(cudaMalloc(&h->row_voxel, (size_t)max_rows * sizeof(unsigned int)));
+            BP_TRY(cudaMalloc(&h->ptr, (size_t)(max_rows + 1) * sizeof(long long)));
+            e = cudaMalloc(&d_len, (size_t)max_rows * sizeof(long long));
+            if (e != cudaSuccess) { cleanup(); iono_backprojector_destroy(h); return fail(IONO_ECUDA, "cudaMalloc(row lengths): %s", cudaGetErrorString(e)); }
+            cub::TransformInputIterator<unsigned int, KeyVoxel, const unsigned long long *> vox(kalt, KeyVoxel());
+            tmp_bytes = 0;
+            e = cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, vox, h->row_voxel, d_len, d_runs, M, st);
+            if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes);
+            if (e == cudaSuccess) e = cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, vox, h->row_voxel, d_len, d_runs, M, st);
+            long long nr = 0;
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&nr, d_runs, sizeof(long long), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            cudaFree(tmp); tmp = nullptr;
+            if (e == cudaSuccess) {
+                h->n_rows = nr;
+                tmp_bytes = 0;
+                e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, h->ptr, nr, st);
+                if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes);
+                if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_len, h->ptr, nr, st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(h->ptr + nr, &M, sizeof(long long), cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                cudaFree(tmp); tmp = nullptr;
+            }
+            cudaFree(d_len);
+            if (e != cudaSuccess) { cleanup(); iono_backprojector_destroy(h); return fail(IONO_ECUDA, "iono_backprojector_create: row table: %s", cudaGetErrorString(e)); }
+        }
+        // segment tables
+        const long long nseg = (M + BP_SEG - 1) / BP_SEG;
+        int *d_count = reinterpret_cast<int *>(d_runs);
+        BP_TRY(cudaMalloc(&h->partial, (size_t)(2 * nseg + 2) * sizeof(double)));
+        BP_TRY(cudaMalloc(&h->items, (size_t)(nseg + 1) * sizeof(int2)));
+        BP_TRY(cudaMalloc(&h->long_rows, (size_t)(nseg + 1) * sizeof(int)));   // <= one straddler per boundary
+        BP_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+        if (nseg > 0) {
+            segment_rows_kernel<<<ew_grid(nseg), 256, 0, st>>>(h->ptr, h->n_rows, M, h->items);
+            BP_TRY(cudaGetLastError());
+            find_straddling_rows_kernel<<<ew_grid(h->n_rows), 256, 0, st>>>(h->ptr, h->n_rows, h->long_rows, d_count,
+                                                                          (int)nseg + 1);
+            BP_TRY(cudaGetLastError());
+        }
+        BP_TRY(cudaMemcpyAsync(&h->n_long, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BP_TRY(cudaStreamSynchronize(st));
+    }
+#undef BP_TRY
+    cleanup();
+    h->nnz = M;
+    *out = h;
+    return IONO_OK;
+}
+
+extern "C" int iono_backprojector_apply_f64(iono_backprojector_t h, const double *coef, const double *scale,
+                                            double *out, void *stream) {
+    if (!h || !out || (h->R > 0 && !coef)) return fail(IONO_EBADARG, "iono_backprojector_apply_f64: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = sm_count() * 8;
+    CU_CHECK(cudaMemsetAsync(out, 0, (size_t)h->V * sizeof(double), st));   // voxels no ray touches
+    if (h->nnz == 0) return IONO_OK;
+    permute_coef_kernel<<<ctas, 256, 0, st>>>(coef, h->Na, h->Nt, h->Nd, h->coef_perm);
+    CU_CHECK(cudaGetLastError());
+    const long long nseg = (h->nnz + BP_SEG - 1) / BP_SEG;
+    const long long cap = (long long)sm_count() * 4;
+    const int bp_smem_bytes = 2 * BP_SEG * 12 + 64;
+    CU_CHECK(cudaFuncSetAttribute(backproject_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  bp_smem_bytes));
+    backproject_segments_kernel<<<(int)(nseg < cap ? nseg : cap), 256, bp_smem_bytes, st>>>(
+        h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, out, h->partial);
+    CU_CHECK(cudaGetLastError());
+    if (h->n_long > 0) {
+        backproject_combine_kernel<<<(h->n_long + 7) / 8, 256, 0, st>>>(h->long_rows, h->n_long, h->ptr,
+                                                                        h->row_voxel, h->partial, scale, out);
+        CU_CHECK(cudaGetLastError());
+    }
+    return IONO_OK;
+}

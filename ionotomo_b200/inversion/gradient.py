@@ -46,14 +46,62 @@ def backproject(rays_dev, grid, coef, shape, order="time", check_bounds=True, ou
     return acc
 
 
+class BackProjector(object):
+    """Voxel-binned form of the adjoint for a fixed ray geometry (``iono_backprojector_*``).
+
+    Build once per solve (the reference computes its rays once per solve too,
+    inversion_pipeline.py:195-197), then every ``compute_gradient(..., backprojector=bp)`` is an
+    atomics-free gather.  ``apply(coef)`` equals ``backproject(rays, grid, coef)`` to rounding.
+    """
+
+    def __init__(self, rays, tci, check_bounds=True):
+        lib = _lib.load()
+        rays_dev = _lib.to_device(rays)
+        Na, Nt, Nd, four, Ns = rays_dev.shape
+        assert four == 4
+        self.shape = (tci.nx, tci.ny, tci.nz)
+        self.ray_shape = (Na, Nt, Nd)
+        self.device = rays_dev.device
+        self._grid = tci.grid()          # keep the grid handle alive
+        oob = torch.zeros(1, dtype=torch.int64, device=rays_dev.device)
+        h = ctypes.c_void_p()
+        _lib.call("iono_backprojector_create", self._grid.handle, _lib.ptr(rays_dev), Na, Nt, Nd, Ns,
+                  ctypes.byref(h), ctypes.c_void_p(oob.data_ptr()), _lib.stream_ptr())
+        self.handle = h
+        self.nnz = int(lib.iono_backprojector_nnz(h))
+        self.nbytes = int(lib.iono_backprojector_bytes(h))
+        if check_bounds and int(oob.item()) != 0:
+            raise ValueError("One of the requested xi is out of bounds (%d ray samples outside the grid)"
+                             % int(oob.item()))
+
+    def apply(self, coef, scale=None, out=None):
+        """``out[v] = scale[v] * sum_ray A[v,ray] coef[ray]`` (``scale`` optional)."""
+        coef = _lib.to_device(coef)
+        assert tuple(coef.shape) == self.ray_shape
+        acc = out if out is not None else torch.empty(self.shape, dtype=torch.float64, device=coef.device)
+        _lib.call("iono_backprojector_apply_f64", self.handle, _lib.ptr(coef),
+                  _lib.ptr(scale) if scale is not None else None, _lib.ptr(acc), _lib.stream_ptr())
+        return acc
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.load().iono_backprojector_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
 def compute_gradient(rays, g, dobs, i0, K_ne, m_tci, m_prior, CdCt, sigma_m, Nkernel, size_cell, cov_obj=None,
-                     order="time", check_bounds=True, reduce_fn=None):
+                     order="time", check_bounds=True, reduce_fn=None, backprojector=None):
     """Same signature as the reference (gradient.py:66).  ``m_prior``, ``sigma_m``,
     ``Nkernel``, ``size_cell``, ``cov_obj`` are accepted for compatibility; the reference
     computes the prior term and discards it (gradient.py:56-58).
 
     ``reduce_fn(acc)`` (optional) is applied to the backprojection before the ``ne[v]``
     factor -- the hook for the cross-GPU allreduce when rays are sharded.
+    ``backprojector`` (optional ``BackProjector`` built from the same rays and grid axes) replaces
+    the atomic scatter by the pre-assembled voxel-binned gather.
     """
     lib = _lib.load()
     want_numpy = not isinstance(rays, torch.Tensor)
@@ -61,7 +109,11 @@ def compute_gradient(rays, g, dobs, i0, K_ne, m_tci, m_prior, CdCt, sigma_m, Nke
     g_d, dobs_d, C_d = _lib.to_device(g), _lib.to_device(dobs), _lib.to_device(CdCt)
     m_dev = m_tci.device_M()
     coef = adjoint_coefficients(g_d, dobs_d, C_d, i0)
-    acc = backproject(rays_dev, m_tci.grid(), coef, tuple(m_dev.shape), order=order, check_bounds=check_bounds)
+    if backprojector is not None:
+        acc = backprojector.apply(coef)
+    else:
+        acc = backproject(rays_dev, m_tci.grid(), coef, tuple(m_dev.shape), order=order,
+                          check_bounds=check_bounds)
     if reduce_fn is not None:
         acc = reduce_fn(acc)
     ne = _ne_from_m(m_dev, K_ne)

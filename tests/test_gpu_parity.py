@@ -230,6 +230,46 @@ def test_adjoint_dot_product_config2_shape(ib):
         assert float((GTy2 - GTy).abs().max()) <= 1e-11 * float(GTy.abs().max())
 
 
+@pytest.mark.parametrize("Ns", [2, 9, 64, 130])
+def test_binned_backprojector_vs_oracle(ib, Ns):
+    import torch
+    P = small_problem(300 + Ns, 4, 3, 5, Ns, 14, 12, 16)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], Ns)
+    rays[..., 3, :] = rays[..., 3, :] + 0.3 * np.sin(rays[..., 3, :] / 50.)
+    coef = P["rng"].normal(size=rays.shape[:3])
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    bp = ib.BackProjector(rays, tci)
+    assert 0 < bp.nnz <= rays.shape[0] * rays.shape[1] * rays.shape[2] * Ns * 8
+    acc = bp.apply(coef)
+    ref = O.backproject(rays, P["xvec"], P["yvec"], P["zvec"], coef)
+    assert np.abs(acc.cpu().numpy() - ref).max() < TOL * np.abs(ref).max()
+    assert torch.equal(acc, bp.apply(coef))                      # bit-reproducible
+    scale = torch.rand(P["m"].shape, dtype=torch.float64, device="cuda")
+    assert torch.allclose(bp.apply(coef, scale=scale), acc * scale, rtol=1e-15, atol=0)
+    # through compute_gradient
+    g = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], 1)
+    dobs = g + 0.01 * P["rng"].normal(size=g.shape)
+    CdCt = np.full(g.shape, 1e-4)
+    grad = ib.compute_gradient(rays, g, dobs, 1, P["K_ne"], tci, P["m"], CdCt, 1., 4, 5., backprojector=bp)
+    ref = O.gradient_exact(rays, g, dobs, 1, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], CdCt)
+    assert np.abs(grad - ref).max() < TOL * np.abs(ref).max()
+    with pytest.raises(ValueError):
+        ib.BackProjector(O.cast_ray(P["origins"], P["directions"], 1300., 8), tci)
+
+
+def test_binned_backprojector_matches_scatter_lofar_slice(ib):
+    import torch
+    from ionotomo_b200.inversion.gradient import backproject
+    P = small_problem(78, 62, 3, 20, 128, 256, 256, 128)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    rays = ib.cast_ray((torch.as_tensor(P["origins"]).cuda(), torch.as_tensor(P["directions"]).cuda()),
+                       ib.Fermat(tci), 1000., 128)
+    y = torch.randn(rays.shape[:3], dtype=torch.float64, device="cuda")
+    a = backproject(rays, tci.grid(), y, P["m"].shape)
+    b = ib.BackProjector(rays, tci).apply(y)
+    assert float((a - b).abs().max()) <= 1e-11 * float(a.abs().max())
+
+
 # ---------------------------------------------------------------- line search
 def test_line_search_golden(ib, golden):
     g = golden("line_search")

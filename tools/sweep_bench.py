@@ -51,6 +51,20 @@ def main():
         for o, wp, s, c, b in [("time", 16, 3, 64, 1), ("natural", 16, 3, 64, 1), ("antenna", 16, 3, 64, 1),
                                ("time", 16, 2, 128, 1), ("time", 16, 4, 64, 1), ("time", 12, 3, 64, 1),
                                ("time", 8, 3, 64, 1), ("time", 16, 3, 64, 0)]]
+    if os.environ.get("BINNED", "1") != "0":
+        import time
+        torch.cuda.synchronize(); t0 = time.time()
+        bp = ib.BackProjector(rays, tci)
+        torch.cuda.synchronize(); t_build = time.time() - t0
+        acc = torch.empty(tuple(ne.shape), dtype=torch.float64, device="cuda")
+        tb = timeit(lambda: bp.apply(coef, scale=ne, out=acc))
+        ref = backproject(rays, tci.grid(), coef, tuple(ne.shape), check_bounds=False) * ne
+        err = float((acc - ref).abs().max() / ref.abs().max())
+        print(json.dumps(dict(binned_adjoint_ms=round(tb[0], 3), binned_frac=round(bytes_a / (tb[0] * 1e-3) / HBM, 3),
+                              nnz=bp.nnz, nnz_per_ray=round(bp.nnz / R, 1), gbytes=round(bp.nbytes / 1e9, 2),
+                              actual_gbs=round((bp.nbytes + 16 * V) / (tb[0] * 1e-3) / 1e9, 1),
+                              build_s=round(t_build, 3), rel_diff_vs_scatter=err)), flush=True)
+        del bp, ref
     for c in configs:
         os.environ["IONO_SWEEP_WARPS"] = str(c["warps"])
         os.environ["IONO_SWEEP_STAGES"] = str(c["stages"])
