@@ -72,13 +72,17 @@ __device__ __forceinline__ AxisR axis_regs(const Axis &a) {
     return r;
 }
 
-// Same semantics as iono::locate(), table in shared memory, constants in registers.
+// Same semantics as iono::locate(), split into the common case (direct index, one table read,
+// t by multiplication) and a rarely taken repair step; table in shared memory, constants in
+// registers.
 template <bool UNIFORM>
-__device__ __forceinline__ void locate_s(const double2 *__restrict__ tab, const AxisR &a, double x, int &i,
-                                         double &t, bool &oob) {
+__device__ __forceinline__ void locate_fast(const double2 *__restrict__ tab, const AxisR &a, double x, int &i,
+                                            double &t) {
     if (UNIFORM) {
         const double v = fma(x, a.inv_d, a.c_guess);
-        i = min(max(__double2loint(v + IONO_MAGIC), 0), a.nm2);
+        // unsigned min also catches negative guesses (they wrap to huge values); the repair step
+        // walks back from the last cell in that (out-of-bounds) case
+        i = (int)min((unsigned int)__double2loint(v + IONO_MAGIC), (unsigned int)a.nm2);
     } else {
         int lo = 0, hi = a.nm2 + 1;
         while (hi - lo > 1) {
@@ -87,15 +91,20 @@ __device__ __forceinline__ void locate_s(const double2 *__restrict__ tab, const 
         }
         i = min(lo, a.nm2);
     }
-    double2 e = tab[i];
+    const double2 e = tab[i];
     t = (x - e.x) * e.y;
-    if (!(t >= 0.0 && t < 1.0)) {
-        while (i > 0 && x < tab[i].x) --i;
-        while (i < a.nm2 && x >= tab[i + 1].x) ++i;
-        e = tab[i];
-        t = (x - e.x) * e.y;
-        oob = oob || !(x >= a.g0 && x <= a.glast);
-    }
+}
+// t in [0,1)  <=>  the high word, read as unsigned, is below that of 1.0 (negative numbers and
+// NaN have larger high words)
+__device__ __forceinline__ bool in_unit(double t) { return (unsigned int)__double2hiint(t) < 0x3FF00000u; }
+
+__device__ __forceinline__ void locate_repair(const double2 *__restrict__ tab, int nm2, double g0, double glast,
+                                           double x, int &i, double &t, bool &oob) {
+    while (i > 0 && x < tab[i].x) --i;
+    while (i < nm2 && x >= tab[i + 1].x) ++i;
+    const double2 e = tab[i];
+    t = (x - e.x) * e.y;
+    oob = oob || !(x >= g0 && x <= glast);
 }
 
 // Adjoint scatter of one sample per lane: a * (trilinear hat weights) into the 8 corners of
@@ -169,11 +178,23 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
     const int n_bundles = (p.R + nwarp - 1) / nwarp;
     int my_rays = (n_bundles > (int)blockIdx.x) ? (n_bundles - 1 - (int)blockIdx.x) / G + 1 : 0;
     if (my_rays > 0 && ((int)blockIdx.x + (my_rays - 1) * G) * nwarp + warp >= p.R) --my_rays;
-    auto ray_index = [&](int k) -> long long { return ray_of(order, ((int)blockIdx.x + k * G) * nwarp + warp); };
+    // work index of this warp's k-th ray: q_k = (blockIdx.x + k*G)*nwarp + warp; its (i0,i1,i2)
+    // digits in the traversal order are advanced incrementally (no divisions in the loop)
+    const int q0 = (int)blockIdx.x * nwarp + warp, qstep = G * nwarp;
+    const int d0 = qstep % order.n0, d1 = (qstep / order.n0) % order.n1, d2 = qstep / (order.n0 * order.n1);
+    struct Cursor { int i0, i1, i2; };
+    auto cursor_init = [&]() { Cursor c; c.i0 = q0 % order.n0; c.i1 = (q0 / order.n0) % order.n1; c.i2 = q0 / (order.n0 * order.n1); return c; };
+    auto cursor_ray = [&](const Cursor &c) -> long long { return (long long)(c.i0 * order.st0 + c.i1 * order.st1 + c.i2 * order.st2); };
+    auto cursor_next = [&](Cursor &c) {
+        c.i0 += d0; if (c.i0 >= order.n0) { c.i0 -= order.n0; ++c.i1; }
+        c.i1 += d1; if (c.i1 >= order.n1) { c.i1 -= order.n1; ++c.i2; }
+        c.i2 += d2;
+    };
+    Cursor pc = cursor_init(), cc = pc;   // producer / consumer
 
     // producer cursor (ray fk, chunk fc, stage fs) and consumer stage/phase
     int fk = 0, fc = 0, fs = 0;
-    const double *fray = (my_rays > 0) ? rays + ray_index(0) * ray_doubles : rays;
+    const double *fray = rays + ((my_rays > 0) ? cursor_ray(pc) * ray_doubles : 0);
     auto produce = [&]() {
         if (fk < my_rays) {
             fill_stage<C, true>(reinterpret_cast<double *>(ring + fs * StageLayout<C>::BYTES), &bars[fs], fray, Ns,
@@ -181,7 +202,7 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
             fs = (fs + 1 == stages) ? 0 : fs + 1;
             if (++fc == chunks) {
                 fc = 0;
-                if (++fk < my_rays) fray = rays + ray_index(fk) * ray_doubles;
+                if (++fk < my_rays) { cursor_next(pc); fray = rays + cursor_ray(pc) * ray_doubles; }
             }
         }
     };
@@ -194,7 +215,8 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
     const int sy = nz, sx = ny * nz;   // element strides (nx*ny*nz < 2^31 checked on the host)
 
     for (int k = 0; k < my_rays; ++k) {
-        const long long ray = ray_index(k);
+        if (k > 0) cursor_next(cc);
+        const long long ray = cursor_ray(cc);
         const double *rayp = rays + ray * ray_doubles;
         double acc = 0.0;
         double coef = 0.0;
@@ -221,11 +243,19 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
                 const int i = c0 + j;
                 int ix, iy, iz;
                 double tx, ty, tz;
-                bool oob = false;
-                locate_s<UNIFORM>(tabx, ax, sx_[j], ix, tx, oob);
-                locate_s<UNIFORM>(taby, ay, sy_[j], iy, ty, oob);
-                locate_s<UNIFORM>(tabz, az, sz_[j], iz, tz, oob);
-                n_oob += (oob && valid);
+                const double px = sx_[j], py = sy_[j], pz = sz_[j];
+                locate_fast<UNIFORM>(tabx, ax, px, ix, tx);
+                locate_fast<UNIFORM>(taby, ay, py, iy, ty);
+                locate_fast<UNIFORM>(tabz, az, pz, iz, tz);
+                if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
+                    // rare: a sample on a cell edge with the guess one off, on the last node, outside
+                    // the grid, or NaN
+                    bool oob = false;
+                    locate_repair(tabx, ax.nm2, ax.g0, ax.glast, px, ix, tx, oob);
+                    locate_repair(taby, ay.nm2, ay.g0, ay.glast, py, iy, ty, oob);
+                    locate_repair(tabz, az.nm2, az.g0, az.glast, pz, iz, tz, oob);
+                    n_oob += (oob && valid);
+                }
                 const double w = simpson_weight(i, Ns, n_odd, ss_[j - 2], ss_[j - 1], ss_[j], ss_[j + 1], ss_[j + 2]);
                 const int v = (ix * ny + iy) * nz + iz;
                 if (MODE == 0) {
@@ -269,7 +299,7 @@ static SweepConfig sweep_config(int mode, int Ns) {
     if ((e = getenv("IONO_SWEEP_STAGES"))) c.stages = atoi(e);
     if ((e = getenv("IONO_SWEEP_CHUNK"))) c.chunk = atoi(e);
     if (c.warps < 1) c.warps = 1;
-    if (c.warps > 24) c.warps = 24;
+    if (c.warps > 32) c.warps = 32;
     if (c.stages < 2) c.stages = 2;
     if (c.stages > 8) c.stages = 8;
     if (c.chunk != 64) c.chunk = 128;
@@ -314,10 +344,10 @@ static int launch_sweep(SweepParams p, iono_grid_t grid, cudaStream_t st) {
     int ctas = sm_count();
     if (ctas > n_bundles) ctas = n_bundles;
     const bool uni = grid->uniform != 0;
-    const bool big = cfg.warps > 16;
 #define IONO_DISPATCH4(U, CC, B)                                                              \
     do {                                                                                      \
-        if (big) return launch_sweep_t<MODE, U, CC, B, 768>(p, cfg, smem, ctas, st);          \
+        if (cfg.warps > 24) return launch_sweep_t<MODE, U, CC, B, 1024>(p, cfg, smem, ctas, st); \
+        if (cfg.warps > 16) return launch_sweep_t<MODE, U, CC, B, 768>(p, cfg, smem, ctas, st);  \
         return launch_sweep_t<MODE, U, CC, B, 512>(p, cfg, smem, ctas, st);                   \
     } while (0)
     if (cfg.chunk == 64) {
