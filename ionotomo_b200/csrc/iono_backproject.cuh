@@ -34,6 +34,7 @@ struct iono_backprojector {
     long long V;
     long long R;
     int Na, Nt, Nd;
+    int seg;                 // entries per segment
     double *coef_perm;       // [R] coefficients in the internal ray order (a, d, t)
     int device;
 };
@@ -137,7 +138,7 @@ struct KeyVoxel {
 //   3. a small kernel adds the partials of each straddling row in segment order.
 // slot 0: the row covers the segment's first entry; slot 1: the row begins inside the segment.
 // Everything is a fixed reduction tree: bit-reproducible.
-constexpr int BP_SEG = 2048;
+constexpr int BP_SEG_DEFAULT = 1024;   // entries per segment (IONO_BP_SEG=1024|2048 at create time)
 
 // voxel (row) that contains entry k: largest v with ptr[v] <= k
 __device__ __forceinline__ long long row_of_entry(const long long *__restrict__ ptr, long long V, long long k) {
@@ -151,7 +152,7 @@ __device__ __forceinline__ long long row_of_entry(const long long *__restrict__ 
 
 // Build time: first and last row of every segment.
 __global__ void __launch_bounds__(256) segment_rows_kernel(const long long *__restrict__ ptr, long long V,
-                                                            long long nnz, int2 *__restrict__ seg_rows) {
+                                                            long long nnz, int BP_SEG, int2 *__restrict__ seg_rows) {
     const long long nseg = (nnz + BP_SEG - 1) / BP_SEG;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long seg = (long long)blockIdx.x * blockDim.x + threadIdx.x; seg < nseg; seg += stride) {
@@ -162,7 +163,8 @@ __global__ void __launch_bounds__(256) segment_rows_kernel(const long long *__re
 
 // Build time: rows that span more than one segment.
 __global__ void __launch_bounds__(256) find_straddling_rows_kernel(const long long *__restrict__ ptr, long long V,
-                                                                    int *__restrict__ rows, int *count, int cap) {
+                                                                    int BP_SEG, int *__restrict__ rows, int *count,
+                                                                    int cap) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride) {
         const long long b = ptr[v], e = ptr[v + 1];
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(256) find_straddling_rows_kernel(const long lo
     }
 }
 
+template <int BP_SEG>
 __global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *__restrict__ seg_rows,
                                                                     const long long *__restrict__ ptr,
                                                                     const unsigned int *__restrict__ row_voxel,
@@ -187,6 +190,8 @@ __global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *_
     double (*w_s)[BP_SEG] = reinterpret_cast<double (*)[BP_SEG]>(bp_smem);
     unsigned int (*r_s)[BP_SEG] = reinterpret_cast<unsigned int (*)[BP_SEG]>(bp_smem + 2 * BP_SEG * 8);
     uint64_t *bar = reinterpret_cast<uint64_t *>(bp_smem + 2 * BP_SEG * 12);
+    double *part = reinterpret_cast<double *>(bp_smem + 2 * BP_SEG * 12 + 16);   // [8]
+    int *next_row = reinterpret_cast<int *>(bp_smem + 2 * BP_SEG * 12 + 16 + 64);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long nseg = (nnz + BP_SEG - 1) / BP_SEG;
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
@@ -201,25 +206,53 @@ __global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *_
     if (threadIdx.x == 0 && (long long)blockIdx.x < nseg) issue(blockIdx.x, 0);
     unsigned int phase = 0;
     int buf = 0;
+    constexpr int PER = BP_SEG / 256;
     for (long long seg = blockIdx.x; seg < nseg; seg += gridDim.x, buf ^= 1) {
         const long long k0 = seg * BP_SEG, k1 = min(k0 + (long long)BP_SEG, nnz);
-        if (threadIdx.x == 0 && seg + gridDim.x < nseg) issue(seg + gridDim.x, buf ^ 1);
+        const int2 rr = seg_rows[seg];
+        if (threadIdx.x == 0) {
+            if (seg + gridDim.x < nseg) issue(seg + gridDim.x, buf ^ 1);
+            *next_row = rr.x + 8;
+        }
         mbar_wait(&bar[buf], (phase >> buf) & 1u);
         phase ^= 1u << buf;
-        // 1. products in place: BP_SEG/256 independent coefficient gathers per thread
         double *prod = w_s[buf];
-        {
-            constexpr int PER = BP_SEG / 256;
-            double c[PER];
+        double c[PER];
 #pragma unroll
-            for (int u = 0; u < PER; ++u) c[u] = __ldg(coef + r_s[buf][threadIdx.x + u * 256]);
+        for (int u = 0; u < PER; ++u) c[u] = __ldg(coef + r_s[buf][threadIdx.x + u * 256]);
+        if (rr.x == rr.y) {
+            // the whole segment lies in one (long) row: block-wide sum, no staging of products
+            // (padding entries beyond nnz have weight 0)
+            double s = 0.0;
 #pragma unroll
-            for (int u = 0; u < PER; ++u) prod[threadIdx.x + u * 256] *= c[u];
+            for (int u = 0; u < PER; ++u) s = fma(prod[threadIdx.x + u * 256], c[u], s);
+            s = warp_sum(s);
+            if (lane == 0) part[warp] = s;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                double t = threadIdx.x < 8 ? part[threadIdx.x] : 0.0;
+                t = warp_sum(t);
+                if (threadIdx.x == 0) {
+                    const long long b = ptr[rr.x], e = ptr[rr.x + 1];
+                    if (b >= k0 && e <= k1) {
+                        const unsigned int v = row_voxel[rr.x];
+                        out[v] = scale ? t * scale[v] : t;
+                    } else {
+                        partial[2 * seg + (b > k0 ? 1 : 0)] = t;
+                    }
+                }
+            }
+            __syncthreads();
+            continue;
         }
+        // 1. products in place
+#pragma unroll
+        for (int u = 0; u < PER; ++u) prod[threadIdx.x + u * 256] *= c[u];
         __syncthreads();
-        // 2. one warp per row
-        const int2 rr = seg_rows[seg];
-        for (int r = rr.x + warp; r <= rr.y; r += 8) {
+        // 2. rows are handed to warps dynamically (a long row keeps one warp busy while the
+        //    others move on); each row is still summed by a fixed lane pattern
+        int r = rr.x + warp;
+        while (r <= rr.y) {
             const long long b = __ldg(ptr + r), e = __ldg(ptr + r + 1);
             const int lo = (int)(max(b, k0) - k0), hi = (int)(min(e, k1) - k0);
             double s0 = 0.0, s1 = 0.0;
@@ -234,7 +267,9 @@ __global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *_
                 } else {
                     partial[2 * seg + (b > k0 ? 1 : 0)] = s;
                 }
+                r = atomicAdd(next_row, 1);
             }
+            r = __shfl_sync(0xffffffffu, r, 0);
         }
         __syncthreads();
     }
@@ -242,7 +277,7 @@ __global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *_
 
 // One warp per straddling row: add its partials in segment order.
 __global__ void __launch_bounds__(256) backproject_combine_kernel(const int *__restrict__ rows, int n_rows,
-                                                                   const long long *__restrict__ ptr,
+                                                                   int BP_SEG, const long long *__restrict__ ptr,
                                                                    const unsigned int *__restrict__ row_voxel,
                                                                    const double *__restrict__ partial,
                                                                    const double *__restrict__ scale,
@@ -296,6 +331,9 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
     CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
 
     iono_backprojector *h = new iono_backprojector();
+    h->seg = BP_SEG_DEFAULT;
+    if (const char *es = getenv("IONO_BP_SEG")) h->seg = (atoi(es) == 2048) ? 2048 : 1024;
+    const int BP_SEG = h->seg;
     h->ray_idx = nullptr; h->weight = nullptr; h->ptr = nullptr; h->row_voxel = nullptr; h->n_rows = 0; h->long_rows = nullptr; h->n_long = 0; h->partial = nullptr; h->items = nullptr;
     h->nnz = 0; h->V = V; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->coef_perm = nullptr;
     cudaGetDevice(&h->device);
@@ -403,9 +441,9 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
         BP_TRY(cudaMalloc(&h->long_rows, (size_t)(nseg + 1) * sizeof(int)));   // <= one straddler per boundary
         BP_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), st));
         if (nseg > 0) {
-            segment_rows_kernel<<<ew_grid(nseg), 256, 0, st>>>(h->ptr, h->n_rows, M, h->items);
+            segment_rows_kernel<<<ew_grid(nseg), 256, 0, st>>>(h->ptr, h->n_rows, M, BP_SEG, h->items);
             BP_TRY(cudaGetLastError());
-            find_straddling_rows_kernel<<<ew_grid(h->n_rows), 256, 0, st>>>(h->ptr, h->n_rows, h->long_rows, d_count,
+            find_straddling_rows_kernel<<<ew_grid(h->n_rows), 256, 0, st>>>(h->ptr, h->n_rows, BP_SEG, h->long_rows, d_count,
                                                                           (int)nseg + 1);
             BP_TRY(cudaGetLastError());
         }
@@ -428,16 +466,28 @@ extern "C" int iono_backprojector_apply_f64(iono_backprojector_t h, const double
     if (h->nnz == 0) return IONO_OK;
     permute_coef_kernel<<<ctas, 256, 0, st>>>(coef, h->Na, h->Nt, h->Nd, h->coef_perm);
     CU_CHECK(cudaGetLastError());
+    const int BP_SEG = h->seg;
     const long long nseg = (h->nnz + BP_SEG - 1) / BP_SEG;
-    const long long cap = (long long)sm_count() * 4;
-    const int bp_smem_bytes = 2 * BP_SEG * 12 + 64;
-    CU_CHECK(cudaFuncSetAttribute(backproject_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  bp_smem_bytes));
-    backproject_segments_kernel<<<(int)(nseg < cap ? nseg : cap), 256, bp_smem_bytes, st>>>(
-        h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, out, h->partial);
+    const int bp_smem_bytes = 2 * BP_SEG * 12 + 16 + 64 + 16;
+    int per_sm = (227 * 1024) / (bp_smem_bytes + 1024);
+    if (per_sm > 8) per_sm = 8;
+    if (const char *ec = getenv("IONO_BP_CTAS")) per_sm = atoi(ec);
+    const long long cap = (long long)sm_count() * per_sm;
+    const int ctas_seg = (int)(nseg < cap ? nseg : cap);
+    if (BP_SEG == 2048) {
+        CU_CHECK(cudaFuncSetAttribute(backproject_segments_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      bp_smem_bytes));
+        backproject_segments_kernel<2048><<<ctas_seg, 256, bp_smem_bytes, st>>>(
+            h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, out, h->partial);
+    } else {
+        CU_CHECK(cudaFuncSetAttribute(backproject_segments_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      bp_smem_bytes));
+        backproject_segments_kernel<1024><<<ctas_seg, 256, bp_smem_bytes, st>>>(
+            h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, out, h->partial);
+    }
     CU_CHECK(cudaGetLastError());
     if (h->n_long > 0) {
-        backproject_combine_kernel<<<(h->n_long + 7) / 8, 256, 0, st>>>(h->long_rows, h->n_long, h->ptr,
+        backproject_combine_kernel<<<(h->n_long + 7) / 8, 256, 0, st>>>(h->long_rows, h->n_long, BP_SEG, h->ptr,
                                                                         h->row_voxel, h->partial, scale, out);
         CU_CHECK(cudaGetLastError());
     }
