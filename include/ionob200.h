@@ -103,6 +103,20 @@ int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, i
                          const double *coef, int order, int zero_first, double *acc,
                          unsigned long long *oob_count, void *stream);
 
+/* ---- phase-domain ray integrals (reference generation B) -------------------------
+ * out[ray,f] = simps(g_f(ne(x_s)), s), n_f = sqrt(1 - ne/(1.2404e-2 nu_f^2)):
+ *   dmu == NULL : g_f = 1 - n_f                (forward_equation, iterative_newton.py:108-119)
+ *   dmu != NULL : g_f = (ne/n_f) * dmu(x_s)    (prior_penalty_mu, iterative_newton.py:157-179)
+ * ne, dmu: (nx,ny,nz) grids; freqs_host: Nf <= 8 frequencies in Hz (host); out: (Na,Nt,Nd,Nf). */
+int iono_phase_integrals_f64(iono_grid_t grid, const double *ne, const double *dmu, const double *rays,
+                             int Na, int Nt, int Nd, int Ns, const double *freqs_host, int Nf, int order,
+                             double *out, unsigned long long *oob_count, void *stream);
+/* penalty == 0: out = const[a] + 2 pi nu clock[a,t] - (2 pi nu/c)(I - I[i0])   (iterative_newton.py:107-123)
+ * penalty != 0: out = -(2 pi nu/(2 n_p c))(I - I[i0])                          (iterative_newton.py:166-183) */
+int iono_phase_assemble_f64(const double *integrals, int Na, int Nt, int Nd, int Nf, int i0,
+                            const double *freqs_host, const double *clock, const double *konst, int penalty,
+                            double *out, void *stream);
+
 /* ---- voxel-binned back-projector (adjoint without atomics) ----------------------
  * The same linear map as iono_tec_adjoint_f64, assembled once per ray geometry in
  * voxel-major sparse form (sorted (voxel, ray, weight) triples; needs ~12 B per

@@ -14,6 +14,8 @@
 //     while the ray stream passes with an evict-first policy.
 #pragma once
 
+#define IONO_MAX_FREQS 8
+
 struct SweepParams {
     Grid g;
     const double *field;   // forward: ne (nx,ny,nz)
@@ -26,6 +28,12 @@ struct SweepParams {
     int Ns;
     int stages;            // ring depth per warp
     RayOrder order;
+    // phase-domain integrals (MODE 2): out_nf[ray*nf + f] = simps(g_f(ne(x_s)) [* field2(x_s)], s)
+    const double *field2;  // optional second grid (mu_prior - mu) for the prior penalty
+    double *out_nf;
+    int nf;
+    double neg_inv_np[IONO_MAX_FREQS];   // -1/(1.2404e-2 nu_f^2)
+    struct Freqs { double a[IONO_MAX_FREQS], s[IONO_MAX_FREQS]; };
 };
 
 // A stage holds x[C], y[C], z[C] and s[C+4] (two halo samples either side for the
@@ -138,7 +146,20 @@ __device__ __forceinline__ void scatter_sample(double *__restrict__ accp, int v,
     }
 }
 
-// MODE 0: forward, MODE 1: adjoint
+__device__ __forceinline__ double trilerp(const double *__restrict__ c, int sy, int sx, double tx, double ty,
+                                          double tz) {
+    const double v000 = __ldg(c), v001 = __ldg(c + 1);
+    const double v010 = __ldg(c + sy), v011 = __ldg(c + sy + 1);
+    const double v100 = __ldg(c + sx), v101 = __ldg(c + sx + 1);
+    const double v110 = __ldg(c + sx + sy), v111 = __ldg(c + sx + sy + 1);
+    const double c00 = fma(tz, v001 - v000, v000), c01 = fma(tz, v011 - v010, v010);
+    const double c10 = fma(tz, v101 - v100, v100), c11 = fma(tz, v111 - v110, v110);
+    const double c0_ = fma(ty, c01 - c00, c00), c1_ = fma(ty, c11 - c10, c10);
+    return fma(tx, c1_ - c0_, c0_);
+}
+
+// MODE 0: TEC forward, MODE 1: adjoint scatter, MODE 2: phase-domain integrals per frequency
+// (inversion/iterative_newton.py:108-119 and :157-179)
 template <int MODE, bool UNIFORM, int C, bool BULK, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -220,6 +241,11 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
         const double *rayp = rays + ray * ray_doubles;
         double acc = 0.0;
         double coef = 0.0;
+        double accf[IONO_MAX_FREQS];
+        if (MODE == 2) {
+#pragma unroll
+            for (int f = 0; f < IONO_MAX_FREQS; ++f) accf[f] = 0.0;
+        }
         if (MODE == 1) coef = __ldg(p.coef + ray);
         for (int chunk = 0; chunk < chunks; ++chunk) {
             const int c0 = chunk * C;
@@ -239,7 +265,7 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
             for (int jb = 0; jb < n_c; jb += 32) {
                 const int j = jb + lane;
                 const bool valid = j < n_c;
-                if (MODE == 0 && !valid) continue;
+                if (MODE != 1 && !valid) continue;
                 const int i = c0 + j;
                 int ix, iy, iz;
                 double tx, ty, tz;
@@ -259,15 +285,19 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
                 const double w = simpson_weight(i, Ns, n_odd, ss_[j - 2], ss_[j - 1], ss_[j], ss_[j + 1], ss_[j + 2]);
                 const int v = (ix * ny + iy) * nz + iz;
                 if (MODE == 0) {
-                    const double *c = p.field + v;
-                    const double v000 = __ldg(c), v001 = __ldg(c + 1);
-                    const double v010 = __ldg(c + sy), v011 = __ldg(c + sy + 1);
-                    const double v100 = __ldg(c + sx), v101 = __ldg(c + sx + 1);
-                    const double v110 = __ldg(c + sx + sy), v111 = __ldg(c + sx + sy + 1);
-                    const double c00 = fma(tz, v001 - v000, v000), c01 = fma(tz, v011 - v010, v010);
-                    const double c10 = fma(tz, v101 - v100, v100), c11 = fma(tz, v111 - v110, v110);
-                    const double c0_ = fma(ty, c01 - c00, c00), c1_ = fma(ty, c11 - c10, c10);
-                    acc = fma(w, fma(tx, c1_ - c0_, c0_), acc);
+                    acc = fma(w, trilerp(p.field + v, sy, sx, tx, ty, tz), acc);
+                } else if (MODE == 2) {
+                    const double ne_s = trilerp(p.field + v, sy, sx, tx, ty, tz);
+                    const bool penalty = p.field2 != nullptr;
+                    const double dmu_s = penalty ? trilerp(p.field2 + v, sy, sx, tx, ty, tz) : 0.0;
+#pragma unroll
+                    for (int f = 0; f < IONO_MAX_FREQS; ++f)
+                        if (f < p.nf) {
+                            // n = sqrt(1 - ne/n_p);  integrand (1 - n)  or  (ne/n) * dmu
+                            const double n = sqrt(fma(ne_s, p.neg_inv_np[f], 1.0));
+                            const double g = penalty ? (ne_s / n) * dmu_s : (1.0 - n);
+                            accf[f] = fma(w, g, accf[f]);
+                        }
                 } else {
                     scatter_sample(p.acc, v, sy, sx, coef * w, tx, ty, tz, lane, valid);
                 }
@@ -278,6 +308,14 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
         if (MODE == 0) {
             const double tot = warp_sum(acc);
             if (lane == 0) p.tec[ray] = tot;
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int f = 0; f < IONO_MAX_FREQS; ++f)
+                if (f < p.nf) {
+                    const double tot = warp_sum(accf[f]);
+                    if (lane == 0) p.out_nf[ray * p.nf + f] = tot;
+                }
         }
     }
     if (n_oob) atomicAdd(p.oob_count, (unsigned long long)n_oob);
@@ -291,7 +329,7 @@ struct SweepConfig {
 
 static SweepConfig sweep_config(int mode, int Ns) {
     SweepConfig c;
-    c.warps = (mode == 0) ? 24 : 16;
+    c.warps = (mode == 0) ? 24 : 16;   // phase mode carries 8 accumulators: 16 warps
     c.stages = 2;
     c.chunk = (Ns <= 64) ? 64 : 128;
     const char *e;
@@ -299,7 +337,8 @@ static SweepConfig sweep_config(int mode, int Ns) {
     if ((e = getenv("IONO_SWEEP_STAGES"))) c.stages = atoi(e);
     if ((e = getenv("IONO_SWEEP_CHUNK"))) c.chunk = atoi(e);
     if (c.warps < 1) c.warps = 1;
-    if (c.warps > 32) c.warps = 32;
+    if (c.warps > 24) c.warps = 24;
+    if (mode == 2 && c.warps > 16) c.warps = 16;
     if (c.stages < 2) c.stages = 2;
     if (c.stages > 8) c.stages = 8;
     if (c.chunk != 64) c.chunk = 128;
@@ -346,8 +385,7 @@ static int launch_sweep(SweepParams p, iono_grid_t grid, cudaStream_t st) {
     const bool uni = grid->uniform != 0;
 #define IONO_DISPATCH4(U, CC, B)                                                              \
     do {                                                                                      \
-        if (cfg.warps > 24) return launch_sweep_t<MODE, U, CC, B, 1024>(p, cfg, smem, ctas, st); \
-        if (cfg.warps > 16) return launch_sweep_t<MODE, U, CC, B, 768>(p, cfg, smem, ctas, st);  \
+        if (MODE != 2 && cfg.warps > 16) return launch_sweep_t<MODE, U, CC, B, 768>(p, cfg, smem, ctas, st); \
         return launch_sweep_t<MODE, U, CC, B, 512>(p, cfg, smem, ctas, st);                   \
     } while (0)
     if (cfg.chunk == 64) {
@@ -406,4 +444,74 @@ extern "C" int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na
     p.g = grid->dev; p.acc = acc; p.rays = rays; p.coef = coef; p.oob_count = oob_count;
     p.R = (int)R; p.Ns = Ns; p.order = make_order(order, Na, Nt, Nd);
     return launch_sweep<1>(p, grid, st);
+}
+
+// ---------------------------------------------------------------------------
+// phase-domain ray integrals (generation B of the reference)
+// ---------------------------------------------------------------------------
+extern "C" int iono_phase_integrals_f64(iono_grid_t grid, const double *ne, const double *dmu, const double *rays,
+                                        int Na, int Nt, int Nd, int Ns, const double *freqs_host, int Nf, int order,
+                                        double *out, unsigned long long *oob_count, void *stream) {
+    const long long R = (long long)Na * Nt * Nd;
+    if (!grid || !ne || !oob_count || !freqs_host || Na < 0 || Nt < 0 || Nd < 0 || Ns < 1 || Nf < 1 ||
+        Nf > IONO_MAX_FREQS || (R > 0 && (!rays || !out)))
+        return fail(IONO_EBADARG, "iono_phase_integrals_f64: bad argument (1 <= Nf <= 8)");
+    if (sweep_size_check(grid, R, Ns)) return IONO_EBADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
+    if (R == 0) return IONO_OK;
+    if (Ns < 2) {
+        CU_CHECK(cudaMemsetAsync(out, 0, R * Nf * sizeof(double), st));
+        return IONO_OK;
+    }
+    SweepParams p;
+    memset(&p, 0, sizeof(p));
+    p.g = grid->dev; p.field = ne; p.field2 = dmu; p.rays = rays; p.out_nf = out; p.oob_count = oob_count;
+    p.R = (int)R; p.Ns = Ns; p.nf = Nf; p.order = make_order(order, Na, Nt, Nd);
+    for (int f = 0; f < Nf; ++f) p.neg_inv_np[f] = -1.0 / (1.2404e-2 * freqs_host[f] * freqs_host[f]);
+    return launch_sweep<2>(p, grid, st);
+}
+
+// out[a,t,d,f] = base[a,t,f] - scale[f] * (I[a,t,d,f] - I[i0,t,d,f]),
+// base = const[a] + 2 pi nu_f clock[a,t] (phase) or 0 (penalty: pass clock = konst = NULL)
+__global__ void __launch_bounds__(256) phase_assemble_kernel(const double *__restrict__ I, int Na, int Nt, int Nd,
+                                                              int Nf, int i0, const double *__restrict__ clock,
+                                                              const double *__restrict__ konst, SweepParams::Freqs fr,
+                                                              double *__restrict__ out) {
+    const long long n = (long long)Na * Nt * Nd * Nf;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long per_a = (long long)Nt * Nd * Nf;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const int f = (int)(k % Nf);
+        const long long a = k / per_a, rem = k - a * per_a;
+        const long long t = rem / ((long long)Nd * Nf);
+        const double ref = I[(long long)i0 * per_a + rem];
+        double base = 0.0;
+        if (clock) base = konst[a] + fr.a[f] * clock[a * Nt + t];
+        out[k] = base - fr.s[f] * (I[k] - ref);
+    }
+}
+
+extern "C" int iono_phase_assemble_f64(const double *integrals, int Na, int Nt, int Nd, int Nf, int i0,
+                                       const double *freqs_host, const double *clock, const double *konst,
+                                       int penalty, double *out, void *stream) {
+    const long long n = (long long)Na * Nt * Nd * Nf;
+    if (Na < 0 || Nt < 0 || Nd < 0 || Nf < 1 || Nf > IONO_MAX_FREQS || !freqs_host)
+        return fail(IONO_EBADARG, "iono_phase_assemble_f64: bad argument");
+    if (n == 0) return IONO_OK;
+    if (!integrals || !out || i0 < 0 || i0 >= Na || (!penalty && (!clock || !konst)))
+        return fail(IONO_EBADARG, "iono_phase_assemble_f64: bad argument");
+    SweepParams::Freqs fr;
+    const double c = 299792458.0, two_pi = 6.283185307179586476925286766559;
+    for (int f = 0; f < Nf; ++f) {
+        const double a_ = two_pi * freqs_host[f];
+        const double n_p = 1.2404e-2 * freqs_host[f] * freqs_host[f];
+        fr.a[f] = a_;
+        fr.s[f] = penalty ? a_ / (2 * n_p * c) : a_ / c;   // iterative_newton.py:166-181 / :110-121
+    }
+    phase_assemble_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(integrals, Na, Nt, Nd, Nf, i0,
+                                                                        penalty ? nullptr : clock,
+                                                                        penalty ? nullptr : konst, fr, out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
 }

@@ -270,6 +270,53 @@ def test_binned_backprojector_matches_scatter_lofar_slice(ib):
     assert float((a - b).abs().max()) <= 1e-11 * float(a.abs().max())
 
 
+# ---------------------------------------------------------------- phase domain (generation B)
+@pytest.mark.parametrize("tag", ["odd", "even"])
+def test_phase_forward_and_penalty_vs_oracle(ib, golden, tag):
+    from ionotomo_b200.inversion import iterative_newton as newton
+    g = golden("forward_" + tag)
+    xv, yv, zv, rays = g["xvec"], g["yvec"], g["zvec"], g["rays"]
+    i0 = int(g["i0"])
+    tci = ib.TriCubic(xv, yv, zv, g["ne"])
+    ph = newton.forward_equation((g["mu"], g["clock"], g["const"]), tci, rays, g["freqs"], K=1e11, i0=i0)
+    ref = O.phase_forward_equation(g["mu"], g["clock"], g["const"], xv, yv, zv, rays, g["freqs"], K=1e11, i0=i0)
+    assert ph.shape == ref.shape == g["phase"].shape
+    # the ionospheric term is a small difference of large integrals: compare on its own scale
+    ion_scale = np.abs(ref - (g["const"][:, None, None, None]
+                              + 2 * np.pi * g["freqs"][None, None, None, :] * g["clock"][:, :, None, None])).max()
+    assert np.abs(ph - ref).max() < 1e-9 * ion_scale + 1e-13 * np.abs(ref).max()
+    # like the reference, the call leaves tci.M = K exp(mu)
+    np.testing.assert_allclose(tci.M, 1e11 * np.exp(g["mu"]).reshape(tci.M.shape), rtol=1e-14)
+    pen = newton.prior_penalty_mu((g["mu"], g["clock"], g["const"]), (g["mu_prior"], g["clock"], g["const"]),
+                                  tci, rays, g["freqs"], K=1e11, i0=i0)
+    refp = O.prior_penalty_mu(g["mu"], g["mu_prior"], xv, yv, zv, rays, g["freqs"], K=1e11, i0=i0)
+    assert np.abs(pen - refp).max() < 1e-10 * np.abs(refp).max()
+    # the oracle itself is pinned to the reference's output through its axis-scramble switch
+    refs = O.phase_forward_equation(g["mu"], g["clock"], g["const"], xv, yv, zv, rays, g["freqs"], K=1e11,
+                                    i0=i0, reference_axis_scramble=True)
+    np.testing.assert_allclose(refs, g["phase"], rtol=1e-10, atol=1e-10 * np.abs(g["phase"]).max())
+
+
+def test_phase_forward_many_freqs_device(ib):
+    import torch
+    from ionotomo_b200.inversion import iterative_newton as newton
+    P = small_problem(55, 5, 3, 6, 64, 20, 18, 40)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 64)
+    freqs = np.linspace(110e6, 170e6, 8)
+    mu = np.log(P["ne"] / 1e11)
+    clock = 1e-9 * P["rng"].normal(size=(5, 3))
+    const = 0.1 * P["rng"].normal(size=5)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], torch.as_tensor(P["ne"]).cuda())
+    ph = newton.forward_equation((torch.as_tensor(mu).cuda(), clock, const), tci, torch.as_tensor(rays).cuda(),
+                                 freqs, K=1e11, i0=2)
+    assert ph.is_cuda and tuple(ph.shape) == (5, 3, 6, 8)
+    ref = O.phase_forward_equation(mu.ravel(), clock, const, P["xvec"], P["yvec"], P["zvec"], rays, freqs, K=1e11, i0=2)
+    ion = ref - (const[:, None, None, None] + 2 * np.pi * freqs[None, None, None, :] * clock[:, :, None, None])
+    assert np.abs(ph.cpu().numpy() - ref).max() < 1e-9 * np.abs(ion).max() + 1e-13 * np.abs(ref).max()
+    with pytest.raises(Exception):
+        newton.forward_equation((mu, clock, const), tci, rays, np.linspace(1e8, 2e8, 9), K=1e11, i0=0)
+
+
 # ---------------------------------------------------------------- line search
 def test_line_search_golden(ib, golden):
     g = golden("line_search")
