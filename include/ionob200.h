@@ -103,6 +103,14 @@ int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, i
                          const double *coef, int order, int zero_first, double *acc,
                          unsigned long long *oob_count, void *stream);
 
+/* ---- chord-length adjoint (the reference's generation-A gradient) ----------------
+ * acc[v] (+)= sum_ray dd[ray] * l(ray,v): l = chord of the line first->last sample through the
+ * box centred on node v, for the voxels within +-1 cell of any sample (geometry/ray_dirac.py:5-34,
+ * geometry/slab_method.py:19-58); the gradient is ne[v]*acc[v] (inversion/gradient.py:15-20).
+ * dd: (Na,Nt,Nd) weighted residuals.  Compatibility kernel, fp64 atomics. */
+int iono_chord_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
+                           const double *dd, int zero_first, double *acc, void *stream);
+
 /* ---- phase-domain ray integrals (reference generation B) -------------------------
  * out[ray,f] = simps(g_f(ne(x_s)), s), n_f = sqrt(1 - ne/(1.2404e-2 nu_f^2)):
  *   dmu == NULL : g_f = 1 - n_f                (forward_equation, iterative_newton.py:108-119)

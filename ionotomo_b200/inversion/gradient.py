@@ -124,6 +124,29 @@ def compute_gradient(rays, g, dobs, i0, K_ne, m_tci, m_prior, CdCt, sigma_m, Nke
 compute_gradient_dask = compute_gradient
 
 
+def compute_gradient_chord(rays, g, dobs, i0, K_ne, m_tci, m_prior, CdCt, sigma_m, Nkernel, size_cell,
+                           cov_obj=None, bug_compat=False):
+    """The reference's own generation-A gradient (gradient.py:22-62): chord lengths of each ray
+    through the cell-centred voxel boxes (``get_ray_dirac``), times ``ne[v]``, times the weighted
+    residual -- **not** the transpose of the forward (no Simpson weights, no reference-antenna
+    term).  ``bug_compat=True`` also applies ``gradient -= gradient[i0, ...]`` (gradient.py:55),
+    which indexes grid-x rather than the antenna axis."""
+    want_numpy = not isinstance(rays, torch.Tensor)
+    rays_dev = _lib.to_device(rays)
+    Na, Nt, Nd, _, Ns = rays_dev.shape
+    g_d, dobs_d, C_d = _lib.to_device(g), _lib.to_device(dobs), _lib.to_device(CdCt)
+    dd = ((g_d - dobs_d) / (C_d + 1e-15)).contiguous()
+    m_dev = m_tci.device_M()
+    acc = torch.empty(tuple(m_dev.shape), dtype=torch.float64, device=rays_dev.device)
+    _lib.call("iono_chord_adjoint_f64", m_tci.grid().handle, _lib.ptr(rays_dev), Na, Nt, Nd, Ns, _lib.ptr(dd), 1,
+              _lib.ptr(acc), _lib.stream_ptr())
+    ne = _ne_from_m(m_dev, K_ne)
+    _lib.call("iono_mul_f64", _lib.ptr(ne), _lib.ptr(acc), acc.numel(), _lib.ptr(acc), _lib.stream_ptr())
+    if bug_compat:
+        acc = acc - acc[int(i0), ...]
+    return acc.cpu().numpy() if want_numpy else acc
+
+
 def misfit(g, dobs, CdCt):
     """``S = sum((g-dobs)^2/(CdCt+1e-15))/2`` (line_search.py:48-49) as a 0-d CUDA tensor."""
     lib = _lib.load()

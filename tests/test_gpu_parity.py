@@ -270,6 +270,31 @@ def test_binned_backprojector_matches_scatter_lofar_slice(ib):
     assert float((a - b).abs().max()) <= 1e-11 * float(a.abs().max())
 
 
+# ---------------------------------------------------------------- chord-length adjoint (generation A)
+def test_chord_adjoint_golden_and_oracle(ib, golden):
+    from ionotomo_b200.inversion.gradient import compute_gradient_chord
+    g = golden("chord")
+    rays = g["rays"]
+    dd = g["dd"][:, None, :]
+    tci = ib.TriCubic(g["xvec"], g["yvec"], g["zvec"], np.log(g["ne"]))
+    # do_gradient(rays, dd, ne_tci, ...) == einsum(dirac, ne, dd): choose g-dobs = dd, CdCt+1e-15 = 1, K_ne = TECU
+    grad = compute_gradient_chord(rays, dd, np.zeros_like(dd), 0, 1e13, tci, None, np.ones_like(dd) - 1e-15,
+                                  1., 3, 5.)
+    np.testing.assert_allclose(grad, g["G"], rtol=1e-10, atol=1e-10 * np.abs(g["G"]).max())
+    # a larger, seeded case against the sparse oracle restatement, incl. the i0 quirk
+    P = small_problem(91, 3, 2, 4, 17, 9, 8, 12)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 17)
+    gm = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], 1)
+    dobs = gm + 0.01 * P["rng"].normal(size=gm.shape)
+    CdCt = np.full(gm.shape, 1e-4)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    for bug in (False, True):
+        got = compute_gradient_chord(rays, gm, dobs, 1, P["K_ne"], tci, None, CdCt, 1., 3, 5., bug_compat=bug)
+        ref = O.gradient_chord(rays, gm, dobs, 1, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], CdCt,
+                               bug_compat=bug)
+        assert np.abs(got - ref).max() < 1e-10 * np.abs(ref).max()
+
+
 # ---------------------------------------------------------------- phase domain (generation B)
 @pytest.mark.parametrize("tag", ["odd", "even"])
 def test_phase_forward_and_penalty_vs_oracle(ib, golden, tag):
