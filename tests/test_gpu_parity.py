@@ -351,3 +351,29 @@ def test_line_search_golden(ib, golden):
     np.testing.assert_allclose(eps, float(g["eps"]), rtol=1e-6)
     np.testing.assert_allclose(S, float(g["S"]), rtol=1e-6)
     np.testing.assert_allclose(red, float(g["red"]), rtol=1e-5, atol=1e-9)
+
+
+# ---------------------------------------------------------------- inversion driver
+@pytest.mark.parametrize("binned", [True, False])
+def test_lbfgs_inversion_reduces_misfit(ib, binned):
+    import torch
+    from ionotomo_b200.inversion.solver import InversionProblem, lbfgs_solve
+    P = small_problem(5, 8, 3, 12, 32, 24, 24, 32)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 32)
+    m_true = P["m"]
+    dobs = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], m_true, 0)
+    dobs = dobs + 0.001 * P["rng"].normal(size=dobs.shape)
+    CdCt = np.full(dobs.shape, 0.001 ** 2)
+    # start from the smooth (unperturbed) profile
+    X, Y, Z = np.meshgrid(P["xvec"], P["yvec"], P["zvec"], indexing="ij")
+    ne0 = 1e11 * np.exp(-((Z - 300.) / 150.) ** 2) + 1e9
+    m0 = np.log(ne0 / P["K_ne"])
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], m0)
+    prob = InversionProblem(rays, P["K_ne"], tci, 0, dobs, CdCt, binned=binned)
+    m, info = lbfgs_solve(prob, torch.as_tensor(m0).cuda(), n_iter=15)
+    S = info["S"]
+    assert len(S) >= 5 and all(b <= a for a, b in zip(S, S[1:]))
+    assert S[-1] < 0.05 * S[0]
+    # the driver's first evaluation equals the oracle's misfit
+    g0 = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], m0, 0)
+    np.testing.assert_allclose(S[0], O.misfit(g0, dobs, CdCt), rtol=1e-10)

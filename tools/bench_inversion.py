@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3]: iterative tomographic inversion (L-BFGS, 50 iterations) on a
+512x512x256 grid with a synthetic turbulent ionosphere, rays of the LOFAR-like case
+(62 x 100 x 200, Ns = nz = 256).  Prints one JSON line with the time per iteration."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ionotomo_b200 as ib
+from ionotomo_b200.ionosphere.synthetic import make_workload
+from ionotomo_b200.inversion.solver import InversionProblem, lbfgs_solve
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--grid", type=int, nargs=3, default=[512, 512, 256])
+ap.add_argument("--nt", type=int, default=100)
+ap.add_argument("--iters", type=int, default=50)
+ap.add_argument("--scatter", action="store_true")
+args = ap.parse_args()
+nx, ny, nz = args.grid
+w = make_workload(Nt=args.nt, nx=nx, ny=ny, nz=nz)
+m_true = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_true"])
+rays = ib.cast_ray((w["origins"], w["directions"]), ib.Fermat(m_true), w["tmax"], w["Ns"])
+del w["origins"], w["directions"]
+dobs = ib.forward_equation(rays, w["K_ne"], m_true, 0)
+dobs = dobs + 0.01 * torch.randn_like(dobs)
+CdCt = torch.full_like(dobs, 1e-4)
+free, total = torch.cuda.mem_get_info()
+need = rays.shape[0] * rays.shape[1] * rays.shape[2] * w["Ns"] * 8 * 40
+if not args.scatter and need > 0.9 * free:
+    raise SystemExit("not enough free HBM for the operator assembly: need ~%.0f GB, free %.0f GB" % (need / 1e9, free / 1e9))
+torch.cuda.synchronize()
+t0 = time.time()
+prob = InversionProblem(rays, w["K_ne"], ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_prior"]), 0, dobs, CdCt,
+                        binned=not args.scatter)
+torch.cuda.synchronize()
+t_build = time.time() - t0
+t0 = time.time()
+m, info = lbfgs_solve(prob, w["m_prior"], n_iter=args.iters)
+torch.cuda.synchronize()
+dt = time.time() - t0
+err0 = float((w["m_prior"] - w["m_true"]).abs().mean())
+err1 = float((m - w["m_true"]).abs().mean())
+print(json.dumps({
+    "config": "L-BFGS inversion, %dx%dx%d grid, %d rays x %d samples" % (nx, ny, nz, rays.shape[0] * rays.shape[1] * rays.shape[2], w["Ns"]),
+    "iterations": len(info["S"]) - 1, "seconds": dt, "s_per_iteration": dt / max(1, len(info["S"]) - 1),
+    "n_forward": info["n_forward"], "n_gradient": info["n_gradient"], "operator_build_s": t_build,
+    "operator_gb": (prob.bp.nbytes / 1e9) if prob.bp else 0.0, "adjoint": "scatter" if args.scatter else "binned",
+    "misfit_first": info["S"][0], "misfit_last": info["S"][-1], "mean_abs_model_error": [err0, err1],
+    "peak_hbm_gb": torch.cuda.max_memory_allocated() / 1e9}))
