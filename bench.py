@@ -8,9 +8,10 @@ One *step* = one forward + adjoint pass over the LOFAR-like synthetic case
 (BASELINE.json configs[1]: 62 stations x 200 directions x 100 times, 256x256x128 grid,
 Ns = 128 samples per ray, fp64): ne = K exp(m)/TECU, TEC integrals, dTEC, misfit,
 adjoint coefficients, back-projection, (allreduce across ranks), ne * acc.
-Weak scaling: every rank holds a full 62x100x200 ray block (consecutive time steps of a
-longer observation), the grid is replicated, the only collective is the allreduce of the
-voxel accumulator.
+Weak scaling: every rank holds a full 62x100x200 ray block (its own 200 directions of a
+200*N-direction field, same 100 time steps, same 4-degree field of view and therefore the
+same grid), the grid is replicated, the only collective is the allreduce of the voxel
+accumulator.
 
 Prints ONE JSON line (rank 0).  ``value`` is rays/s for the whole job with inputs resident
 in HBM; ``e2e`` is the same pass through the public host-array API
@@ -164,7 +165,7 @@ def workload_config(n_gpus, nt):
     return {"workload": "LOFAR-like forward+adjoint: %d stations x %d directions x %d times per GPU, "
                         "%dx%dx%d grid, Ns=%d, fp64 (BASELINE.json configs[1..2])" % (NA, ND, nt, NX, NY, NZ, NZ),
             "rays_per_gpu": NA * nt * ND, "grid": [NX, NY, NZ], "samples_per_ray": NZ, "box": "tight",
-            "sharding": "time blocks per rank, grid replicated, allreduce(acc) fp64",
+            "sharding": "direction blocks per rank (reference antenna local), grid replicated, allreduce(acc) fp64",
             "l2_policy": "inputs larger than L2 (%.2f GB of rays per pass); no flush" % (NA * nt * ND * 4 * NZ * 8 / 1e9),
             "seed": 1234, "i0": 0, "tmax_km": 1000.0}
 
@@ -248,8 +249,8 @@ def main():
     from ionotomo_b200.inversion.host_stream import misfit_and_gradient
 
     nt = args.nt
-    w = make_workload(Na=NA, Nt=nt * world, Nd=ND, nx=NX, ny=NY, nz=NZ, device="cuda",
-                      t_slice=(rank * nt, (rank + 1) * nt))
+    w = make_workload(Na=NA, Nt=nt, Nd=ND * world, nx=NX, ny=NY, nz=NZ, device="cuda",
+                      d_slice=(rank * ND, (rank + 1) * ND))
     m_true = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_true"])
     m_tci = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_prior"])      # model being fitted
     grid = m_tci.grid()

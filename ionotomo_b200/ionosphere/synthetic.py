@@ -119,11 +119,12 @@ def tight_axes(ants, dirs_t, nx, ny, nz, tmax=1000., pad_cells=20, zlim=(-100., 
 
 
 def make_workload(Na=62, Nt=100, Nd=200, nx=256, ny=256, nz=128, seed=1234, device="cuda", tmax=1000.,
-                  isotropic_spacing=None, t_slice=None):
+                  isotropic_spacing=None, t_slice=None, d_slice=None):
     """The LOFAR-like benchmark case (BASELINE.json configs[1..2]) as device tensors.
 
-    ``t_slice=(t0, t1)`` keeps only that block of time steps (ray sharding across GPUs:
-    the grid and the full-problem geometry are identical on every rank)."""
+    ``t_slice=(t0, t1)`` / ``d_slice=(d0, d1)`` keep only that block of time steps / directions
+    (ray sharding across GPUs: the grid and the full-problem geometry are identical on every
+    rank; both axes keep the reference antenna local)."""
     ants = lofar_stations_enu_km()[:Na]
     dirs_t = track_directions(directions_in_fov(Nd, 4., seed), Nt)
     if isotropic_spacing is None:
@@ -140,9 +141,11 @@ def make_workload(Na=62, Nt=100, Nd=200, nx=256, ny=256, nz=128, seed=1234, devi
     ne_true = ne_prior * torch.exp(dm)
     K_ne = float(ne_true.mean())
     t0, t1 = (0, Nt) if t_slice is None else t_slice
+    d0, d1 = (0, Nd) if d_slice is None else d_slice
+    Nd_total, Nd = Nd, d1 - d0
     o = torch.as_tensor(ants, device=dev)[:, None, None, :].expand(Na, t1 - t0, Nd, 3).contiguous()
-    d = torch.as_tensor(dirs_t[t0:t1], device=dev)[None].expand(Na, t1 - t0, Nd, 3).contiguous()
+    d = torch.as_tensor(dirs_t[t0:t1, d0:d1], device=dev)[None].expand(Na, t1 - t0, Nd, 3).contiguous()
     return dict(xvec=xvec, yvec=yvec, zvec=zvec, K_ne=K_ne, m_true=torch.log(ne_true / K_ne),
                 m_prior=torch.log(ne_prior / K_ne), origins=o, directions=d, tmax=tmax, Ns=nz,
-                Na=Na, Nt=t1 - t0, Nd=Nd, Nt_total=Nt, seed=seed,
+                Na=Na, Nt=t1 - t0, Nd=Nd, Nt_total=Nt, Nd_total=Nd_total, seed=seed,
                 dx_km=float(xvec[1] - xvec[0]), dy_km=float(yvec[1] - yvec[0]), dz_km=float(zvec[1] - zvec[0]))
