@@ -377,3 +377,38 @@ def test_lbfgs_inversion_reduces_misfit(ib, binned):
     # the driver's first evaluation equals the oracle's misfit
     g0 = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], m0, 0)
     np.testing.assert_allclose(S[0], O.misfit(g0, dobs, CdCt), rtol=1e-10)
+
+
+# ---------------------------------------------------------------- host-array streaming API
+@pytest.mark.parametrize("block_times", [None, 1, 2, 3])
+def test_host_stream_misfit_and_gradient(ib, block_times):
+    from ionotomo_b200.inversion.host_stream import misfit_and_gradient
+    P = small_problem(64, 5, 7, 6, 32, 16, 14, 24)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 32)
+    i0 = 3
+    g_ref = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], i0)
+    dobs = g_ref + 0.01 * P["rng"].normal(size=g_ref.shape)
+    CdCt = 1e-4 * (1. + P["rng"].uniform(size=g_ref.shape))
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    dtec, S, grad = misfit_and_gradient(rays, P["K_ne"], tci, i0, dobs, CdCt, block_times=block_times)
+    tec_scale = np.abs(O.tec(rays, P["xvec"], P["yvec"], P["zvec"], O.ne_from_m(P["m"], P["K_ne"]))).max()
+    assert np.abs(dtec - g_ref).max() < TOL * tec_scale
+    np.testing.assert_allclose(S, O.misfit(dtec, dobs, CdCt), rtol=1e-12)
+    ref = O.gradient_exact(rays, dtec, dobs, i0, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], CdCt)
+    assert np.abs(grad - ref).max() < 1e-10 * np.abs(ref).max()
+    # same numbers as the two-call path
+    g2 = ib.forward_equation(rays, P["K_ne"], tci, i0)
+    np.testing.assert_array_equal(dtec, g2)
+
+
+def test_tricubic_inner_and_model_coordinates(ib):
+    P = small_problem(3, 1, 1, 1, 8, 9, 10, 11)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    other = P["rng"].normal(size=P["m"].shape)
+    np.testing.assert_allclose(tci.inner(other), O.tci_inner(P["xvec"], P["yvec"], P["zvec"], other, P["m"]), rtol=1e-12)
+    X, Y, Z = tci.get_model_coordinates()
+    assert X.shape == (9 * 10 * 11,) and X[0] == P["xvec"][0] and Z[1] == P["zvec"][1] and Y[11] == P["yvec"][1]
+    flat = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"].ravel())       # flat M is reshaped (tri_cubic.py:52-54)
+    assert flat.M.shape == (9, 10, 11)
+    with pytest.raises(AssertionError):
+        ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], np.full(P["m"].shape, np.nan))
