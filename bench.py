@@ -174,46 +174,64 @@ def workload_config(n_gpus, nt):
 # clocks
 # ----------------------------------------------------------------------------------
 class ClockSampler(object):
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons every ~5 ms through NVML (pynvml) in a thread;
+    falls back to polling nvidia-smi."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.stop_flag, self.proc, self.max_mhz = [], False, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = None
+            try:   # the NVML index can differ from the CUDA index: match by UUID
+                import torch
+                uuid = str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
         except Exception:
-            self.proc = None
+            self.nv = None
+            self.thread = threading.Thread(target=self._poll_smi, args=(index,), daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.time(), mhz, mask))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _poll_smi(self, index):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.active"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.max_mhz = float(f[1])
+                self.rows.append((time.time(), float(f[0]), int(f[2], 16)))
+            except Exception:
+                time.sleep(0.05)
 
     def window(self, t0, t1):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ts, line in self.rows:
-            if ts < t0 or ts > t1 + 0.15:
-                continue
-            f = [x.strip() for x in line.split(",")]
-            try:
-                sm.append(float(f[0]))
-                mx = max(mx, float(f[1]))
-            except Exception:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        sel = [(m, k) for ts, m, k in self.rows if t0 <= ts <= t1]
+        reasons = sorted(n for n, bit in self.REASONS.items() if any(k & bit for _, k in sel))
+        return {"sm_mhz": float(np.median([m for m, _ in sel])) if sel else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(sel)}
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
+        self.stop_flag = True
 
 
 # ----------------------------------------------------------------------------------
@@ -310,7 +328,6 @@ def main():
             torch.cuda.synchronize()
 
     sampler = ClockSampler(local) if rank == 0 else None
-    time.sleep(0.3 if sampler else 0.0)
     t_load0 = time.time()
     for _ in range(args.warmup):
         step(False)
@@ -367,12 +384,13 @@ def main():
         red = sharding.allreduce_sum_ if world > 1 else None
         e2e_steps = max(2, min(args.steps, 4))
         for _ in range(1):
-            misfit_and_gradient(rays_h, K_ne, m_host_tci, i0, dobs_h, C_h, order=args.order, reduce_fn=red)
+            misfit_and_gradient(rays_h, K_ne, m_host_tci, i0, dobs_h, C_h, order=args.order, reduce_fn=red,
+                                copy_results=False)
         fence()
         t0 = time.time()
         for _ in range(e2e_steps):
             g_h, S_h, grad_h = misfit_and_gradient(rays_h, K_ne, m_host_tci, i0, dobs_h, C_h, order=args.order,
-                                                   reduce_fn=red)
+                                                   reduce_fn=red, copy_results=False)
         fence()
         dt = (time.time() - t0) / e2e_steps
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")

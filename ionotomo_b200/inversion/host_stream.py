@@ -25,15 +25,34 @@ def pin(a):
     return t if t.is_pinned() else t.pin_memory()
 
 
+_pinned_out = {}
+_staging = {}
+
+
+def _pinned_like(key, shape):
+    """Cached pinned host buffer for results (device -> host copies at full PCIe speed)."""
+    t = _pinned_out.get(key)
+    if t is None or tuple(t.shape) != tuple(shape):
+        t = torch.empty(tuple(shape), dtype=torch.float64, pin_memory=True)
+        _pinned_out[key] = t
+    return t
+
+
 def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_times=None, check_bounds=True,
-                        reduce_fn=None):
+                        reduce_fn=None, timings=None, copy_results=True):
     """``(dtec, S, gradient)`` as NumPy/float from host arrays.
 
     ``rays`` may be a NumPy array or a (preferably pinned) CPU tensor of shape
     ``(Na, Nt, Nd, 4, Ns)``.  Equivalent to ``forward_equation`` + misfit + ``compute_gradient``
     of this package (and to the reference's ``func_and_gradient`` sketch,
     tests/test_inversion.py:30-39, with the exact adjoint).
+
+    Results are read back into cached *pinned* host buffers.  With ``copy_results=False`` the
+    returned arrays are views of those buffers (valid until the next call) -- what an optimiser
+    loop wants; the default returns private copies.
     """
+    import time as _time
+    _t0 = _time.time()
     _lib.require_cuda()
     lib = _lib.load()
     rays_h = rays if isinstance(rays, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rays, dtype=np.float64))
@@ -44,13 +63,18 @@ def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_t
     if block_times is None:   # ~256 MB blocks
         block_times = max(1, min(Nt, (256 << 20) // max(1, Na * row_bytes)))
     main = torch.cuda.current_stream()
-    side = torch.cuda.Stream()
+    # staging buffers, copy stream and events are cached across calls: allocating and freeing
+    # 2 x 256 MB per pass (cudaMalloc/cudaFree synchronise) costs more than the compute
+    key = (dev.index, Na * block_times * Nd * 4 * Ns)
+    st = _staging.get(key)
+    if st is None:
+        st = {"side": torch.cuda.Stream(),
+              "bufs": [torch.empty(key[1], dtype=torch.float64, device=dev) for _ in range(2)],
+              "ready": [torch.cuda.Event() for _ in range(2)], "free": [torch.cuda.Event() for _ in range(2)]}
+        _staging.clear()
+        _staging[key] = st
+    side, bufs, ready, free = st["side"], st["bufs"], st["ready"], st["free"]
     side.wait_stream(main)
-    bufs = [torch.empty((Na, block_times, Nd, 4, Ns), dtype=torch.float64, device=dev) for _ in range(2)]
-    for t in bufs:
-        t.record_stream(side)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    free = [torch.cuda.Event() for _ in range(2)]
     blocks = [(t0, min(Nt, t0 + block_times)) for t0 in range(0, Nt, block_times)]
 
     def upload(b):
@@ -72,6 +96,10 @@ def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_t
     oob = torch.zeros(1, dtype=torch.int64, device=dev)
     oob_tot = torch.zeros(1, dtype=torch.int64, device=dev)
     grid = m_tci.grid()
+    if timings is not None:
+        torch.cuda.synchronize()
+        timings["setup_ms"] = (_time.time() - _t0) * 1e3
+        _t0 = _time.time()
     if blocks:
         upload(0)
     for b, (t0, t1) in enumerate(blocks):
@@ -80,7 +108,7 @@ def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_t
         main.wait_event(ready[b % 2])
         tb = t1 - t0
         # the 2-D copy packs the block densely, also the last, shorter one
-        rb = bufs[b % 2].reshape(-1)[:Na * tb * Nd * 4 * Ns].reshape(Na, tb, Nd, 4, Ns)
+        rb = bufs[b % 2][:Na * tb * Nd * 4 * Ns].reshape(Na, tb, Nd, 4, Ns)
         tec = tec_from_ne(rb, grid, ne, order=order, check_bounds=False)
         d = torch.empty_like(tec)
         _lib.call("iono_dtec_f64", _lib.ptr(tec), Na, tb, Nd, int(i0), _lib.ptr(d), _lib.stream_ptr())
@@ -90,6 +118,11 @@ def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_t
                   _lib.ORDERS[order], 0, _lib.ptr(acc), ctypes.c_void_p(oob.data_ptr()), _lib.stream_ptr())
         oob_tot += oob
         free[b % 2].record(main)
+    if timings is not None:
+        timings["enqueue_ms"] = (_time.time() - _t0) * 1e3
+        torch.cuda.synchronize()
+        timings["stream_ms"] = (_time.time() - _t0) * 1e3
+        _t0 = _time.time()
     if reduce_fn is not None:
         acc = reduce_fn(acc)
     from .gradient import misfit
@@ -99,4 +132,14 @@ def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_t
         raise ValueError("One of the requested xi is out of bounds (%d ray samples outside the grid)"
                          % int(oob_tot.item()))
     main.wait_stream(side)
-    return dtec.cpu().numpy(), float(S), acc.cpu().numpy()
+    dtec_h = _pinned_like("dtec", dtec.shape)
+    grad_h = _pinned_like("grad", acc.shape)
+    dtec_h.copy_(dtec, non_blocking=True)
+    grad_h.copy_(acc, non_blocking=True)
+    S = float(S)                                   # synchronises
+    torch.cuda.current_stream().synchronize()
+    if timings is not None:
+        timings["finish_ms"] = (_time.time() - _t0) * 1e3
+    if copy_results:   # private copies, so that the next call cannot overwrite them
+        return dtec_h.numpy().copy(), S, grad_h.numpy().copy()
+    return dtec_h.numpy(), S, grad_h.numpy()
