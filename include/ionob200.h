@@ -72,6 +72,16 @@ int iono_mul_f64(const double *a, const double *b, int64_t n, double *out, void 
 int iono_cast_rays_straight_f64(const double *origins, const double *directions, int64_t nrays,
                                 double tmax, int Ns, double *rays_out, void *stream);
 
+/* Frame-aware variant: ITRS inputs, the reference's Pointing frame applied per ray on the fly
+ * (astro/frames/pointing_frame.py:140-190 and the per-time loop of calc_rays, calc_rays.py:125-139):
+ *   origin[a,t,k]    = R[t] . (ants_itrs_m[a] - p0_itrs_m) / 1000   (km)
+ *   direction[a,t,k] = R[t] . dirs_itrs[t,k]
+ * R: (Nt,3,3) rows east, north, up of the pointing frame at each obstime (see
+ * ionotomo_b200.geometry.frames.pointing_rotation); dirs_itrs: (Nt,Nd,3) unit vectors. */
+int iono_cast_rays_frames_f64(const double *ants_itrs_m, const double *p0_itrs_m, const double *R,
+                              const double *dirs_itrs, int Na, int Nt, int Nd, double tmax_km, int Ns,
+                              double *rays_out, void *stream);
+
 /* ---- point-wise interpolation -------------------------------------------
  * TriCubic.interp / .extrapolate (geometry/tri_cubic.py:69-75) == SciPy
  * RegularGridInterpolator(method='linear').  M: (nx,ny,nz).  oob_count (device,

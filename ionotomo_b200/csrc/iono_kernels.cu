@@ -214,6 +214,83 @@ __global__ void __launch_bounds__(256) cast_rays_kernel(const double *__restrict
     }
 }
 
+// Same as cast_rays_kernel, with the model-frame origin and direction of every ray derived on the fly
+// from ITRS inputs by the per-time rotation of the reference's Pointing frame
+// (astro/frames/pointing_frame.py:151-183): origin = R_t (p_a - p0) / 1000 [km], direction = R_t d_{t,k}.
+__global__ void __launch_bounds__(256) cast_rays_frames_kernel(const double *__restrict__ ants_itrs_m,
+                                                                const double *__restrict__ p0_itrs_m,
+                                                                const double *__restrict__ R,
+                                                                const double *__restrict__ dirs_itrs, int Na, int Nt,
+                                                                int Nd, double tmax, int Ns,
+                                                                double *__restrict__ rays) {
+    __shared__ RayConst rc[CAST_RAYS_PER_CTA];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int64_t nrays = (int64_t)Na * Nt * Nd;
+    for (int64_t base = (int64_t)blockIdx.x * CAST_RAYS_PER_CTA; base < nrays;
+         base += (int64_t)gridDim.x * CAST_RAYS_PER_CTA) {
+        __syncthreads();
+        if (threadIdx.x < CAST_RAYS_PER_CTA && base + threadIdx.x < nrays) {
+            const int64_t ray = base + threadIdx.x;
+            const int a = (int)(ray / ((int64_t)Nt * Nd));
+            const int rem = (int)(ray - (int64_t)a * Nt * Nd);
+            const int t = rem / Nd, k = rem - t * Nd;
+            const double *Rt = R + (int64_t)t * 9;
+            const double dx = __dadd_rn(ants_itrs_m[a * 3 + 0], -p0_itrs_m[0]);
+            const double dy = __dadd_rn(ants_itrs_m[a * 3 + 1], -p0_itrs_m[1]);
+            const double dz = __dadd_rn(ants_itrs_m[a * 3 + 2], -p0_itrs_m[2]);
+            const double *d = dirs_itrs + ((int64_t)t * Nd + k) * 3;
+            double o[3], v[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {   // row r of R_t times the vector, left to right, no FMA contraction
+                o[r] = __dadd_rn(__dadd_rn(__dmul_rn(Rt[3 * r], dx), __dmul_rn(Rt[3 * r + 1], dy)),
+                                 __dmul_rn(Rt[3 * r + 2], dz));
+                v[r] = __dadd_rn(__dadd_rn(__dmul_rn(Rt[3 * r], d[0]), __dmul_rn(Rt[3 * r + 1], d[1])),
+                                 __dmul_rn(Rt[3 * r + 2], d[2]));
+                o[r] = __ddiv_rn(o[r], 1000.0);   // m -> km (calc_rays.py:132 `.to(au.km)`)
+            }
+            const double sdot = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(v[0], v[0]), __dmul_rn(v[1], v[1])),
+                                                     __dmul_rn(v[2], v[2])));
+            const double px = __ddiv_rn(v[0], sdot), py = __ddiv_rn(v[1], sdot), pz = __ddiv_rn(v[2], sdot);
+            RayConst c;
+            c.x0 = o[0]; c.y0 = o[1]; c.z0 = o[2];
+            c.kx = __ddiv_rn(px, pz);
+            c.ky = __ddiv_rn(py, pz);
+            c.pz = pz;
+            c.step = __ddiv_rn(__dadd_rn(tmax, -c.z0), (double)(Ns - 1));
+            rc[threadIdx.x] = c;
+        }
+        __syncthreads();
+        for (int r = warp; r < CAST_RAYS_PER_CTA && base + r < nrays; r += nwarp) {
+            const RayConst c = rc[r];
+            double *out = rays + (base + r) * 4 * (int64_t)Ns;
+            for (int i = lane; i < Ns; i += 32) {
+                double z = (i == Ns - 1 && Ns > 1) ? tmax : __dadd_rn(__dmul_rn((double)i, c.step), c.z0);
+                double dz = __dadd_rn(z, -c.z0);
+                __stcs(out + i, __dadd_rn(c.x0, __dmul_rn(c.kx, dz)));
+                __stcs(out + Ns + i, __dadd_rn(c.y0, __dmul_rn(c.ky, dz)));
+                __stcs(out + 2 * (int64_t)Ns + i, z);
+                __stcs(out + 3 * (int64_t)Ns + i, __ddiv_rn(dz, c.pz));
+            }
+        }
+    }
+}
+
+extern "C" int iono_cast_rays_frames_f64(const double *ants_itrs_m, const double *p0_itrs_m, const double *R,
+                                         const double *dirs_itrs, int Na, int Nt, int Nd, double tmax_km, int Ns,
+                                         double *rays_out, void *stream) {
+    const int64_t nrays = (int64_t)Na * Nt * Nd;
+    if (Na < 0 || Nt < 0 || Nd < 0 || Ns < 1) return fail(IONO_EBADARG, "iono_cast_rays_frames_f64: bad argument");
+    if (nrays == 0) return IONO_OK;
+    if (!ants_itrs_m || !p0_itrs_m || !R || !dirs_itrs || !rays_out)
+        return fail(IONO_EBADARG, "iono_cast_rays_frames_f64: NULL pointer");
+    int64_t ctas = (nrays + CAST_RAYS_PER_CTA - 1) / CAST_RAYS_PER_CTA;
+    int64_t cap = (int64_t)sm_count() * 8;
+    cast_rays_frames_kernel<<<(int)(ctas < cap ? ctas : cap), 256, 0, (cudaStream_t)stream>>>(
+        ants_itrs_m, p0_itrs_m, R, dirs_itrs, Na, Nt, Nd, tmax_km, Ns, rays_out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
 extern "C" int iono_cast_rays_straight_f64(const double *origins, const double *directions, int64_t nrays,
                                            double tmax, int Ns, double *rays_out, void *stream) {
     if (!origins || !directions || !rays_out || nrays < 0 || Ns < 1)

@@ -256,6 +256,36 @@ def cast_ray(origins, directions, tmax, N):
     return rays
 
 
+def pointing_rotation(lon_rad, ha_rad, dec_rad):
+    """R = [east; north; up] of the reference's Pointing frame
+    (astro/frames/pointing_frame.py:151-166): lonrad = lon - HA, latrad = dec."""
+    lonrad = lon_rad - ha_rad
+    sinlat, coslat = np.sin(dec_rad), np.cos(dec_rad)
+    sinlon, coslon = np.sin(lonrad), np.cos(lonrad)
+    north = [-sinlat * coslon, -sinlat * sinlon, coslat]
+    east = [-sinlon, coslon, 0.]
+    up = [coslat * coslon, coslat * sinlon, sinlat]
+    return np.array([east, north, up])
+
+
+def cast_ray_frames(ants_itrs_m, p0_itrs_m, R, dirs_itrs, tmax, N):
+    """calc_rays' per-time loop (geometry/calc_rays.py:125-139) with the Pointing transform
+    written out (pointing_frame.py:168-183): origins = R_t (p - p0) in km, directions = R_t d."""
+    ants = np.asarray(ants_itrs_m, dtype=np.float64)
+    Na, Nt, Nd = ants.shape[0], R.shape[0], dirs_itrs.shape[1]
+    origins = np.zeros((Na, Nt, Nd, 3))
+    directions = np.zeros((Na, Nt, Nd, 3))
+    diff = ants - np.asarray(p0_itrs_m, dtype=np.float64)
+    for j in range(Nt):
+        o = np.stack([R[j, r, 0] * diff[:, 0] + R[j, r, 1] * diff[:, 1] + R[j, r, 2] * diff[:, 2]
+                      for r in range(3)], -1) / 1000.0
+        d = np.stack([R[j, r, 0] * dirs_itrs[j, :, 0] + R[j, r, 1] * dirs_itrs[j, :, 1]
+                      + R[j, r, 2] * dirs_itrs[j, :, 2] for r in range(3)], -1)
+        origins[:, j, :, :] += o[:, None, :]
+        directions[:, j, :, :] += d[None]
+    return cast_ray(origins, directions, tmax, N)
+
+
 # --------------------------------------------------------------------------
 # TEC forward (generation A): inversion/forward_equation.py
 # --------------------------------------------------------------------------

@@ -95,6 +95,29 @@ def test_calc_rays_array_inputs(ib):
     np.testing.assert_array_equal(rays, O.cast_ray(P["origins"], P["directions"], 1000., tci.nz))
 
 
+def test_calc_rays_itrs_frames(ib):
+    """Frame-aware generator: ITRS antennas/directions + per-time Pointing rotation on the GPU."""
+    from ionotomo_b200.geometry import frames
+    rng = np.random.RandomState(8)
+    lon, lat = np.radians(6.87), np.radians(52.91)
+    p0 = 6364e3 * np.array([np.cos(lat) * np.cos(lon), np.cos(lat) * np.sin(lon), np.sin(lat)])
+    ants = p0 + rng.uniform(-3e4, 3e4, (7, 3))
+    Nt, Nd = 5, 9
+    jd = 2457700.5 + np.arange(Nt) * 8. / 86400.
+    ra0, dec0 = np.radians(210.), np.radians(54.)
+    ra, dec = ra0 + rng.uniform(-0.03, 0.03, Nd), dec0 + rng.uniform(-0.03, 0.03, Nd)
+    dirs = frames.icrs_to_itrs_simple(ra, dec, jd)
+    ha = frames.gmst_rad(jd) + lon - ra0
+    R = frames.pointing_rotation(lon, ha, dec0)
+    np.testing.assert_array_equal(R[2], O.pointing_rotation(lon, ha[2], dec0))
+    # the phase centre maps onto the frame's 'up' axis: directions come out near-vertical
+    rays = frames.calc_rays_itrs(ants, dirs, R, p0, 1000., 33)
+    ref = O.cast_ray_frames(ants, p0, R, dirs, 1000., 33)
+    assert rays.shape == (7, Nt, Nd, 4, 33)
+    np.testing.assert_allclose(rays, ref, rtol=1e-13, atol=1e-9)
+    assert np.all(rays[..., 2, -1] == 1000.) and np.all(np.abs(rays[..., 0, -1] - rays[..., 0, 0]) < 60.)
+
+
 # ---------------------------------------------------------------- forward
 @pytest.mark.parametrize("tag", ["odd", "even"])
 def test_forward_golden(ib, golden, tag):
