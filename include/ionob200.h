@@ -82,6 +82,16 @@ int iono_cast_rays_frames_f64(const double *ants_itrs_m, const double *p0_itrs_m
                               const double *dirs_itrs, int Na, int Nt, int Nd, double tmax_km, int Ns,
                               double *rays_out, void *stream);
 
+/* "Curved" mode as the reference ships it (Fermat(straight_line_approx=False), fermat.py:48-84: the
+ * index gradient is hard-coded to zero, so the geometry stays straight and only ds/dz = n/pz changes):
+ * n_out = sqrt(1 - 8.980^2 ne / nu^2) (Fermat.ne2n, fermat.py:36-46), and the s row of `rays`
+ * (nrays,4,Ns) is overwritten in place by the optical path int n dz / pz, integrated exactly over the
+ * trilinear interpolant (piecewise cubic along the ray) instead of LSODA. */
+int iono_ne_to_refractive_index_f64(const double *ne, int64_t nvox, double frequency_hz, double *n_out,
+                                    void *stream);
+int iono_optical_path_f64(iono_grid_t grid, const double *n_field, double *rays, int64_t nrays, int Ns,
+                          unsigned long long *oob_count, void *stream);
+
 /* ---- point-wise interpolation -------------------------------------------
  * TriCubic.interp / .extrapolate (geometry/tri_cubic.py:69-75) == SciPy
  * RegularGridInterpolator(method='linear').  M: (nx,ny,nz).  oob_count (device,

@@ -34,7 +34,22 @@ class Fermat(object):
         nrays = int(np.prod(lead)) if lead else 1
         rays = torch.empty(lead + (4, int(N)), dtype=torch.float64, device=o.device)
         _lib.call("iono_cast_rays_straight_f64", _lib.ptr(o), _lib.ptr(d), nrays, float(tmax), int(N),
-                                                   _lib.ptr(rays), _lib.stream_ptr())
+                  _lib.ptr(rays), _lib.stream_ptr())
+        if not self.straight_line_approx:
+            # the shipped "curved" mode: same geometry, s becomes the optical path int n dz/pz
+            # (euler_ode with grad n == 0, fermat.py:53-55,57-66)
+            import ctypes
+            assert self.ne_tci is not None, "straight_line_approx=False needs ne_tci"
+            ne = self.ne_tci.device_M()
+            n_field = torch.empty_like(ne)
+            _lib.call("iono_ne_to_refractive_index_f64", _lib.ptr(ne), ne.numel(), float(self.frequency),
+                      _lib.ptr(n_field), _lib.stream_ptr())
+            oob = torch.zeros(1, dtype=torch.int64, device=rays.device)
+            _lib.call("iono_optical_path_f64", self.ne_tci.grid().handle, _lib.ptr(n_field), _lib.ptr(rays), nrays,
+                      int(N), ctypes.c_void_p(oob.data_ptr()), _lib.stream_ptr())
+            if int(oob.item()) != 0:
+                raise ValueError("One of the requested xi is out of bounds (%d quadrature points outside the grid)"
+                                 % int(oob.item()))
         return rays.cpu().numpy() if want_numpy else rays
 
     def integrate_ray(self, origin, direction, tmax, N=100):

@@ -256,6 +256,45 @@ def cast_ray(origins, directions, tmax, N):
     return rays
 
 
+def ne2n(ne, frequency):
+    """Fermat.ne2n (inversion/fermat.py:36-46)."""
+    M = np.array(ne, dtype=np.float64, copy=True)
+    M *= -8.980 ** 2 / frequency ** 2
+    M += 1.
+    np.sqrt(M, out=M)
+    return M
+
+
+def optical_path(ray, xvec, yvec, zvec, n_field):
+    """s row of one ray (4, Ns) for ``straight_line_approx=False`` as shipped: the ODE
+    ``sdot = n/pz`` with straight geometry (inversion/fermat.py:48-84).  The reference integrates
+    with LSODA; here every sample interval is split at its grid-plane crossings and integrated
+    with 2-point Gauss-Legendre, exact for the (piecewise cubic) trilinear interpolant."""
+    Ns = ray.shape[1]
+    x, y, z = ray[0], ray[1], ray[2]
+    pz = (z[-1] - z[0]) / (ray[3, -1] - ray[3, 0])
+    gl = 0.5 / np.sqrt(3.)
+    s = np.zeros(Ns)
+    for i in range(Ns - 1):
+        za, zb = z[i], z[i + 1]
+        kx, ky = (x[i + 1] - x[i]) / (zb - za), (y[i + 1] - y[i]) / (zb - za)
+        cuts = [za, zb]
+        cuts += [g for g in zvec if za < g < zb]
+        for k, g0, vec in ((kx, x[i], xvec), (ky, y[i], yvec)):
+            if k != 0:
+                zc = za + (np.asarray(vec) - g0) / k
+                cuts += [c for c in zc if za < c < zb]
+        cuts = np.unique(cuts)
+        seg = 0.
+        for c0, c1 in zip(cuts[:-1], cuts[1:]):
+            h, zm = c1 - c0, 0.5 * (c0 + c1)
+            zq = np.array([zm - gl * h, zm + gl * h])
+            nq = rgi_linear(xvec, yvec, zvec, n_field, x[i] + kx * (zq - za), y[i] + ky * (zq - za), zq)
+            seg += 0.5 * h * nq.sum()
+        s[i + 1] = s[i] + seg
+    return s / pz
+
+
 def pointing_rotation(lon_rad, ha_rad, dec_rad):
     """R = [east; north; up] of the reference's Pointing frame
     (astro/frames/pointing_frame.py:151-166): lonrad = lon - HA, latrad = dec."""

@@ -257,6 +257,14 @@ def main():
              K_ne=K_ne, m0=m0, dobs=dobs, g=g, CdCt=CdCt, grad=grad, eps=eps, S=S, red=red,
              S0=S0, vx=vx, vy=vy, v1=np.array(v1), v2=np.array(v2))
 
+    # 7b. the shipped "curved" mode: Fermat(straight_line_approx=False) -> odeint with sdot = n/pz
+    xvec, yvec, zvec, ne, origins, directions, rng = small_problem(13, 2, 1, 3, 12, 12, 11, 10)
+    ne_tci = TriCubic(xvec, yvec, zvec, ne * 20.)
+    fermat_c = Fermat(ne_tci=ne_tci, frequency=40e6, type='z', straight_line_approx=False)
+    rays_c = cast_ray((origins, directions), fermat_c, 600., 12)       # tmax inside the grid: LSODA probes ahead
+    np.savez(os.path.join(OUT, "optical_path.npz"), xvec=xvec, yvec=yvec, zvec=zvec, ne=ne * 20., frequency=40e6,
+             origins=origins, directions=directions, rays=rays_c, tmax=600., Ns=12, n_field=fermat_c.n_tci.M)
+
     # 8. synthetic-input recipe (ionosphere/simulation.py:45-112, ionosphere/iri.py:20-68)
     xvec = np.linspace(-50., 50., 16)
     yvec = np.linspace(-40., 40., 12)

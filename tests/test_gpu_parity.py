@@ -95,6 +95,23 @@ def test_calc_rays_array_inputs(ib):
     np.testing.assert_array_equal(rays, O.cast_ray(P["origins"], P["directions"], 1000., tci.nz))
 
 
+def test_optical_path_mode(ib, golden):
+    """Fermat(straight_line_approx=False): the reference's shipped 'curved' mode (BASELINE config 5)."""
+    g = golden("optical_path")
+    tci = ib.TriCubic(g["xvec"], g["yvec"], g["zvec"], g["ne"])
+    fermat = ib.Fermat(ne_tci=tci, frequency=float(g["frequency"]), type='z', straight_line_approx=False)
+    rays = ib.cast_ray((g["origins"], g["directions"]), fermat, float(g["tmax"]), int(g["Ns"]))
+    np.testing.assert_allclose(rays[..., :3, :], g["rays"][..., :3, :], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(rays[..., 3, :], g["rays"][..., 3, :], rtol=0, atol=2e-4)    # vs LSODA
+    n_field = O.ne2n(g["ne"], float(g["frequency"]))
+    straight = O.cast_ray(g["origins"], g["directions"], float(g["tmax"]), int(g["Ns"]))
+    for idx in np.ndindex(*rays.shape[:3]):
+        s = O.optical_path(straight[idx], g["xvec"], g["yvec"], g["zvec"], n_field)
+        np.testing.assert_allclose(rays[idx][3], s, rtol=1e-12, atol=1e-10)                  # vs exact oracle
+    with pytest.raises(ValueError):
+        ib.cast_ray((g["origins"], g["directions"]), fermat, 1200., 8)
+
+
 def test_calc_rays_itrs_frames(ib):
     """Frame-aware generator: ITRS antennas/directions + per-time Pointing rotation on the GPU."""
     from ionotomo_b200.geometry import frames

@@ -188,3 +188,17 @@ def test_exact_adjoint_dot_product_and_fd(golden):
         fd = (O.misfit(O.forward_equation(rays, K_ne, xv, yv, zv, mp, i0), dobs, CdCt)
               - O.misfit(O.forward_equation(rays, K_ne, xv, yv, zv, mm, i0), dobs, CdCt)) / 2e-6
         assert abs(fd - grad[v]) <= 1e-5 * abs(grad[v]) + 1e-9 * abs(S0)
+
+
+def test_optical_path_matches_reference_odeint(golden):
+    """straight_line_approx=False as shipped: same geometry, s = int n dz / pz (LSODA in the reference)."""
+    g = golden("optical_path")
+    n_field = O.ne2n(g["ne"], float(g["frequency"]))
+    np.testing.assert_allclose(n_field, g["n_field"], rtol=1e-15)
+    straight = O.cast_ray(g["origins"], g["directions"], float(g["tmax"]), int(g["Ns"]))
+    np.testing.assert_allclose(straight[..., :3, :], g["rays"][..., :3, :], rtol=0, atol=1e-9)
+    for idx in np.ndindex(*g["rays"].shape[:3]):
+        s = O.optical_path(straight[idx], g["xvec"], g["yvec"], g["zvec"], n_field)
+        # LSODA runs at rtol = atol ~ 1.5e-8 on a path of ~800 km
+        np.testing.assert_allclose(s, g["rays"][idx][3], rtol=0, atol=2e-4)
+        assert np.all(s[1:] < straight[idx][3, 1:])      # n < 1: the optical path is shorter
