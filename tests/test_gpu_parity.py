@@ -452,3 +452,47 @@ def test_tricubic_inner_and_model_coordinates(ib):
     assert flat.M.shape == (9, 10, 11)
     with pytest.raises(AssertionError):
         ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], np.full(P["m"].shape, np.nan))
+
+
+# ---------------------------------------------------------------- BASELINE config 2 at full size
+def test_full_size_lofar_properties(ib):
+    """62 x 100 x 200 rays, 256x256x128 grid, Ns=128 (5 GB of rays): size-independent properties."""
+    import torch
+    from ionotomo_b200.ionosphere.synthetic import make_workload
+    from ionotomo_b200.inversion.forward_equation import tec_from_ne, _ne_from_m
+    from ionotomo_b200.inversion.gradient import backproject
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90e9:
+        pytest.skip("needs ~90 GB of free HBM")
+    w = make_workload()
+    tci = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_true"])
+    rays = ib.cast_ray((w["origins"], w["directions"]), ib.Fermat(tci), w["tmax"], w["Ns"])
+    assert tuple(rays.shape) == (62, 100, 200, 4, 128)
+    grid = tci.grid()
+    ne = _ne_from_m(tci.device_M(), w["K_ne"])
+    tec = tec_from_ne(rays, grid, ne)                    # also asserts every sample is inside the grid
+    assert bool(torch.isfinite(tec).all()) and float(tec.min()) > 0
+    # 1. a constant field integrates to the path length (Simpson is exact for constants)
+    length = tec_from_ne(rays, grid, torch.ones_like(ne))
+    assert float((length - rays[..., 3, -1]).abs().max()) < 1e-9
+    # 2. linearity
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    b = torch.rand(ne.shape, dtype=torch.float64, device="cuda", generator=gen)
+    tb = tec_from_ne(rays, grid, b)
+    tl = tec_from_ne(rays, grid, 0.5 * ne - 2.0 * b)
+    assert float((0.5 * tec - 2.0 * tb - tl).abs().max()) < 1e-11 * float(tl.abs().max())
+    # 3. both adjoints are the transpose of the forward: <G x, y> == <x, G^T y>
+    y = torch.randn(tec.shape, dtype=torch.float64, device="cuda", generator=gen)
+    lhs = float((tb * y).sum())
+    scat = backproject(rays, grid, y, tuple(ne.shape))
+    assert abs(lhs - float((b * scat).sum())) <= 1e-10 * abs(lhs)
+    bp = ib.BackProjector(rays, tci)
+    binned = bp.apply(y)
+    assert abs(lhs - float((b * binned).sum())) <= 1e-10 * abs(lhs)
+    assert float((binned - scat).abs().max()) <= 1e-10 * float(scat.abs().max())
+    assert torch.equal(binned, bp.apply(y))              # bit-reproducible
+    # 4. traversal order does not change the forward bits
+    assert torch.equal(tec, tec_from_ne(rays, grid, ne, order="natural"))
+    # 5. dTEC of the reference antenna is exactly zero
+    d = ib.forward_equation(rays, w["K_ne"], tci, 0)
+    assert float(d[0].abs().max()) == 0.0
