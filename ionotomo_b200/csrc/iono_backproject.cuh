@@ -26,8 +26,10 @@ struct iono_backprojector {
     long long *ptr;          // [n_rows+1] entry offsets of the non-empty rows
     unsigned int *row_voxel; // [n_rows] voxel index of each non-empty row
     long long n_rows;
-    int *long_rows;          // voxels whose entries span more than one segment
+    int *long_rows;          // rows whose entries span 2..8 segments (thread each in the combine step)
     int n_long;
+    int *vlong_rows;         // rows spanning more than 8 segments (warp each)
+    int n_vlong;
     double *partial;         // [2 * nseg] per-segment sums of the straddling rows
     int2 *items;             // [nseg] first and last row of every segment
     long long nnz;
@@ -164,11 +166,17 @@ __global__ void __launch_bounds__(256) segment_rows_kernel(const long long *__re
 // Build time: rows that span more than one segment.
 __global__ void __launch_bounds__(256) find_straddling_rows_kernel(const long long *__restrict__ ptr, long long V,
                                                                     int BP_SEG, int *__restrict__ rows, int *count,
-                                                                    int cap) {
+                                                                    int cap, int *__restrict__ vrows, int *vcount,
+                                                                    int vcap) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride) {
         const long long b = ptr[v], e = ptr[v + 1];
-        if (e > b && b / BP_SEG != (e - 1) / BP_SEG) {
+        if (e <= b) continue;
+        const long long span = (e - 1) / BP_SEG - b / BP_SEG;
+        if (span >= 8) {
+            const int k = atomicAdd(vcount, 1);
+            if (k < vcap) vrows[k] = (int)v;
+        } else if (span >= 1) {
             const int k = atomicAdd(count, 1);
             if (k < cap) rows[k] = (int)v;
         }
@@ -275,9 +283,135 @@ __global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *_
     }
 }
 
+// Warp-private variant: every WARP owns segments of BP_WSEG entries (static stride over all warps of
+// the grid), with its own 2-deep TMA ring and mbarriers -- no __syncthreads in the loop, so a warp
+// that waits for its gathers or sums a long row never stalls the other warps of the CTA.
+// Rows of a segment are summed one after the other by the whole warp (lanes stride, shuffle
+// reduction); lane q remembers the total of row q and the lanes store their rows together.
+constexpr int BP_WSEG = 256;
+
+__global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *__restrict__ seg_rows,
+                                                                     const long long *__restrict__ ptr,
+                                                                     const unsigned int *__restrict__ row_voxel,
+                                                                     const unsigned int *__restrict__ ray_idx,
+                                                                     const double *__restrict__ weight,
+                                                                     const double *__restrict__ coef,
+                                                                     const double *__restrict__ scale, long long nnz,
+                                                                     double *__restrict__ out,
+                                                                     double *__restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char bp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    constexpr int STAGE = BP_WSEG * 12;                       // weights then ray indices
+    unsigned char *mine = bp_smem + (size_t)warp * (2 * STAGE);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(bp_smem + (size_t)nwarp * 2 * STAGE) + warp * 2;
+    const long long nseg = (nnz + BP_WSEG - 1) / BP_WSEG;
+    const long long gw = (long long)blockIdx.x * nwarp + warp, gstride = (long long)gridDim.x * nwarp;
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+    auto issue = [&](long long seg, int buf) {
+        if (lane == 0) {
+            mbar_expect_tx(&bar[buf], STAGE);
+            bulk_g2s(mine + buf * STAGE, weight + seg * BP_WSEG, BP_WSEG * 8, &bar[buf], pol);
+            bulk_g2s(mine + buf * STAGE + BP_WSEG * 8, ray_idx + seg * BP_WSEG, BP_WSEG * 4, &bar[buf], pol);
+        }
+    };
+    if (gw < nseg) issue(gw, 0);
+    unsigned int phase = 0;
+    int buf = 0;
+    constexpr int PER = BP_WSEG / 32;
+    for (long long seg = gw; seg < nseg; seg += gstride, buf ^= 1) {
+        const long long k0 = seg * BP_WSEG, k1 = min(k0 + (long long)BP_WSEG, nnz);
+        const int2 rr = __ldg(seg_rows + seg);
+        if (seg + gstride < nseg) issue(seg + gstride, buf ^ 1);
+        const int n_rows = rr.y - rr.x + 1;
+        // row table of the first 31 rows: lane q holds ptr[rr.x + q]; lanes < n_rows also voxel and scale
+        long long myptr = 0;
+        unsigned int myvox = 0;
+        double myscale = 1.0;
+        if (lane <= min(n_rows, 31)) myptr = __ldg(ptr + rr.x + lane);
+        if (lane < min(n_rows, 31)) {
+            myvox = __ldg(row_voxel + rr.x + lane);
+            if (scale) myscale = __ldg(scale + myvox);
+        }
+        mbar_wait(&bar[buf], (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        double *prod = reinterpret_cast<double *>(mine + buf * STAGE);
+        const unsigned int *rs = reinterpret_cast<const unsigned int *>(mine + buf * STAGE + BP_WSEG * 8);
+        double c[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) c[u] = __ldg(coef + rs[lane + u * 32]);
+        if (n_rows == 1) {
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) s = fma(prod[lane + u * 32], c[u], s);   // padding has weight 0
+            s = warp_sum(s);
+            const long long b = __shfl_sync(0xffffffffu, myptr, 0), e = __shfl_sync(0xffffffffu, myptr, 1);
+            if (lane == 0) {
+                if (b >= k0 && e <= k1) out[myvox] = s * myscale;
+                else partial[2 * seg + (b > k0 ? 1 : 0)] = s;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < PER; ++u) prod[lane + u * 32] *= c[u];
+            __syncwarp();
+            int r0 = 0;   // first row of the current batch (relative to rr.x)
+            while (true) {
+                const int nb = min(n_rows - r0, 31);
+                double mysum = 0.0;
+                for (int q = 0; q < nb; ++q) {
+                    const long long b = __shfl_sync(0xffffffffu, myptr, q), e = __shfl_sync(0xffffffffu, myptr, q + 1);
+                    const int lo = (int)(max(b, k0) - k0), hi = (int)(min(e, k1) - k0);
+                    double s = 0.0;
+                    for (int j = lo + lane; j < hi; j += 32) s += prod[j];
+                    s = warp_sum(s);
+                    if (lane == q) mysum = s;
+                }
+                const long long mye = __shfl_down_sync(0xffffffffu, myptr, 1);
+                if (lane < nb) {
+                    if (myptr >= k0 && mye <= k1) out[myvox] = mysum * myscale;
+                    else partial[2 * seg + (myptr > k0 ? 1 : 0)] = mysum;
+                }
+                r0 += nb;
+                if (r0 >= n_rows) break;
+                // next batch of rows (segments made of many tiny rows)
+                myptr = 0; myvox = 0; myscale = 1.0;
+                if (lane <= min(n_rows - r0, 31)) myptr = __ldg(ptr + rr.x + r0 + lane);
+                if (lane < min(n_rows - r0, 31)) {
+                    myvox = __ldg(row_voxel + rr.x + r0 + lane);
+                    if (scale) myscale = __ldg(scale + myvox);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// One THREAD per straddling row whose partials lie in at most 8 segments (the common case).
+__global__ void __launch_bounds__(256) backproject_combine_short_kernel(const int *__restrict__ rows, int n_rows,
+                                                                         int seg, const long long *__restrict__ ptr,
+                                                                         const unsigned int *__restrict__ row_voxel,
+                                                                         const double *__restrict__ partial,
+                                                                         const double *__restrict__ scale,
+                                                                         double *__restrict__ out) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const long long row = rows[r];
+        const long long b = ptr[row], e = ptr[row + 1];
+        const long long s_first = b / seg, s_last = (e - 1) / seg;
+        double s = 0.0;
+        for (long long sg = s_first; sg <= s_last; ++sg)
+            s += partial[2 * sg + ((sg == s_first && b > sg * seg) ? 1 : 0)];
+        const long long v = row_voxel[row];
+        out[v] = scale ? s * scale[v] : s;
+    }
+}
+
 // One warp per straddling row: add its partials in segment order.
 __global__ void __launch_bounds__(256) backproject_combine_kernel(const int *__restrict__ rows, int n_rows,
-                                                                   int BP_SEG, const long long *__restrict__ ptr,
+                                                                   int BP_SEG,
+                                                                   const long long *__restrict__ ptr,
                                                                    const unsigned int *__restrict__ row_voxel,
                                                                    const double *__restrict__ partial,
                                                                    const double *__restrict__ scale,
@@ -307,6 +441,7 @@ extern "C" int iono_backprojector_destroy(iono_backprojector_t h) {
     cudaFree(h->ptr);
     cudaFree(h->row_voxel);
     cudaFree(h->long_rows);
+    cudaFree(h->vlong_rows);
     cudaFree(h->partial);
     cudaFree(h->items);
     cudaFree(h->coef_perm);
@@ -331,10 +466,10 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
     CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
 
     iono_backprojector *h = new iono_backprojector();
-    h->seg = BP_SEG_DEFAULT;
-    if (const char *es = getenv("IONO_BP_SEG")) h->seg = (atoi(es) == 2048) ? 2048 : 1024;
+    h->seg = BP_WSEG;   // warp-private segments (default); IONO_BP_SEG=1024|2048 selects the CTA-segment kernel
+    if (const char *es = getenv("IONO_BP_SEG")) h->seg = (atoi(es) == 2048) ? 2048 : (atoi(es) == 1024 ? 1024 : BP_WSEG);
     const int BP_SEG = h->seg;
-    h->ray_idx = nullptr; h->weight = nullptr; h->ptr = nullptr; h->row_voxel = nullptr; h->n_rows = 0; h->long_rows = nullptr; h->n_long = 0; h->partial = nullptr; h->items = nullptr;
+    h->ray_idx = nullptr; h->weight = nullptr; h->ptr = nullptr; h->row_voxel = nullptr; h->n_rows = 0; h->long_rows = nullptr; h->n_long = 0; h->vlong_rows = nullptr; h->n_vlong = 0; h->partial = nullptr; h->items = nullptr;
     h->nnz = 0; h->V = V; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->coef_perm = nullptr;
     cudaGetDevice(&h->device);
     unsigned long long *k0 = nullptr, *k1 = nullptr, *uk = nullptr;
@@ -439,15 +574,18 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
         BP_TRY(cudaMalloc(&h->partial, (size_t)(2 * nseg + 2) * sizeof(double)));
         BP_TRY(cudaMalloc(&h->items, (size_t)(nseg + 1) * sizeof(int2)));
         BP_TRY(cudaMalloc(&h->long_rows, (size_t)(nseg + 1) * sizeof(int)));   // <= one straddler per boundary
-        BP_TRY(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+        BP_TRY(cudaMalloc(&h->vlong_rows, (size_t)(nseg / 8 + 2) * sizeof(int)));
+        BP_TRY(cudaMemsetAsync(d_count, 0, 2 * sizeof(int), st));
         if (nseg > 0) {
             segment_rows_kernel<<<ew_grid(nseg), 256, 0, st>>>(h->ptr, h->n_rows, M, BP_SEG, h->items);
             BP_TRY(cudaGetLastError());
             find_straddling_rows_kernel<<<ew_grid(h->n_rows), 256, 0, st>>>(h->ptr, h->n_rows, BP_SEG, h->long_rows, d_count,
-                                                                          (int)nseg + 1);
+                                                                          (int)nseg + 1, h->vlong_rows, d_count + 1,
+                                                                          (int)(nseg / 8 + 2));
             BP_TRY(cudaGetLastError());
         }
         BP_TRY(cudaMemcpyAsync(&h->n_long, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BP_TRY(cudaMemcpyAsync(&h->n_vlong, d_count + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         BP_TRY(cudaStreamSynchronize(st));
     }
 #undef BP_TRY
@@ -455,6 +593,16 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
     h->nnz = M;
     *out = h;
     return IONO_OK;
+}
+
+static cudaError_t bp_combine(iono_backprojector_t h, const double *scale, double *out, cudaStream_t st) {
+    if (h->n_long > 0)
+        backproject_combine_short_kernel<<<ew_grid(h->n_long), 256, 0, st>>>(h->long_rows, h->n_long, h->seg, h->ptr,
+                                                                           h->row_voxel, h->partial, scale, out);
+    if (h->n_vlong > 0)
+        backproject_combine_kernel<<<(h->n_vlong + 7) / 8, 256, 0, st>>>(h->vlong_rows, h->n_vlong, h->seg, h->ptr,
+                                                                         h->row_voxel, h->partial, scale, out);
+    return cudaGetLastError();
 }
 
 extern "C" int iono_backprojector_apply_f64(iono_backprojector_t h, const double *coef, const double *scale,
@@ -468,6 +616,20 @@ extern "C" int iono_backprojector_apply_f64(iono_backprojector_t h, const double
     CU_CHECK(cudaGetLastError());
     const int BP_SEG = h->seg;
     const long long nseg = (h->nnz + BP_SEG - 1) / BP_SEG;
+    if (BP_SEG == BP_WSEG) {
+        int warps = 8, per_sm = 4;
+        if (const char *ew = getenv("IONO_BP_WARPS")) warps = atoi(ew);
+        if (const char *ec = getenv("IONO_BP_CTAS")) per_sm = atoi(ec);
+        const int smem = warps * 2 * BP_WSEG * 12 + warps * 16 + 64;
+        const long long cap = (long long)sm_count() * per_sm;
+        const long long want = (nseg + warps - 1) / warps;
+        CU_CHECK(cudaFuncSetAttribute(backproject_wsegments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        backproject_wsegments_kernel<<<(int)(want < cap ? want : cap), warps * 32, smem, st>>>(
+            h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, out, h->partial);
+        CU_CHECK(cudaGetLastError());
+        CU_CHECK(bp_combine(h, scale, out, st));
+        return IONO_OK;
+    }
     const int bp_smem_bytes = 2 * BP_SEG * 12 + 16 + 64 + 16;
     int per_sm = (227 * 1024) / (bp_smem_bytes + 1024);
     if (per_sm > 8) per_sm = 8;
@@ -486,10 +648,6 @@ extern "C" int iono_backprojector_apply_f64(iono_backprojector_t h, const double
             h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, out, h->partial);
     }
     CU_CHECK(cudaGetLastError());
-    if (h->n_long > 0) {
-        backproject_combine_kernel<<<(h->n_long + 7) / 8, 256, 0, st>>>(h->long_rows, h->n_long, BP_SEG, h->ptr,
-                                                                        h->row_voxel, h->partial, scale, out);
-        CU_CHECK(cudaGetLastError());
-    }
+    CU_CHECK(bp_combine(h, scale, out, st));
     return IONO_OK;
 }
