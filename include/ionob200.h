@@ -170,6 +170,13 @@ int64_t iono_misfit_scratch_elems(void);
 int iono_misfit_f64(const double *g, const double *dobs, const double *CdCt, int64_t n,
                     double *scratch, double *out, void *stream);
 
+/* ---- model-covariance smoothing ------------------------------------------------------
+ * out = scipy.ndimage.convolve(phi, stencil, mode='nearest') for an (m,m,m) stencil, m odd:
+ * Covariance.smooth (ionosphere/covariance.py:383-385), the Cm . (G^T r) step after the adjoint.
+ * phi, out: (nx,ny,nz), must not alias. */
+int iono_convolve3d_nearest_f64(const double *phi, int nx, int ny, int nz, const double *stencil, int m,
+                                double *out, void *stream);
+
 /* ---- host <-> device staging ---------------------------------------------------
  * Strided block copy of `height` rows of `width_bytes` from pinned or pageable HOST memory
  * to DEVICE memory (cudaMemcpy2DAsync).  Used to stream time blocks rays[:, t0:t1] of a

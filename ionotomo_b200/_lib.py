@@ -41,6 +41,7 @@ SIGNATURES = {
     "iono_tec_adjoint_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "iono_misfit_scratch_elems": (_i64, []),
     "iono_misfit_f64": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "iono_convolve3d_nearest_f64": (_i, [_vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "iono_copy2d_h2d": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "iono_chord_adjoint_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "iono_phase_integrals_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
@@ -56,7 +57,7 @@ SIGNATURES = {
 KERNEL_LAUNCHES = {
     "iono_ne_from_m_f64": 1, "iono_mul_f64": 1, "iono_cast_rays_straight_f64": 1, "iono_cast_rays_frames_f64": 1, "iono_ne_to_refractive_index_f64": 1, "iono_optical_path_f64": 1, "iono_tci_interp_f64": 1,
     "iono_tec_forward_f64": 1, "iono_dtec_f64": 1, "iono_adjoint_coef_f64": 1, "iono_tec_adjoint_f64": 1,
-    "iono_misfit_f64": 2, "iono_phase_integrals_f64": 1, "iono_chord_adjoint_f64": 1, "iono_phase_assemble_f64": 1, "iono_backprojector_apply_f64": 4,
+    "iono_misfit_f64": 2, "iono_convolve3d_nearest_f64": 1, "iono_phase_integrals_f64": 1, "iono_chord_adjoint_f64": 1, "iono_phase_assemble_f64": 1, "iono_backprojector_apply_f64": 4,
 }
 launch_count = 0
 

@@ -494,3 +494,54 @@ extern "C" int iono_copy2d_h2d(void *dst, int64_t dpitch, const void *src, int64
                                cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return IONO_OK;
 }
+
+// ---------------------------------------------------------------------------
+// model-covariance smoothing: Covariance.smooth == scipy.ndimage.convolve(phi, stencil, mode='nearest')
+// (ionosphere/covariance.py:383-385) -- the Cm . (G^T r) step that follows the adjoint in the
+// reference's solvers.  out[i,j,k] = sum_{a,b,c} w[a,b,c] * phi[clamp(i + h - a), clamp(j + h - b),
+// clamp(k + h - c)], h = m/2 (convolution flips the stencil).  One thread per voxel, z fastest; the
+// stencil sits in shared memory, the input is read through L1 (each value is reused m^3 times).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) convolve3d_nearest_kernel(const double *__restrict__ phi, int nx, int ny,
+                                                                  int nz, const double *__restrict__ w, int m,
+                                                                  double *__restrict__ out) {
+    extern __shared__ double w_s[];
+    for (int i = threadIdx.x; i < m * m * m; i += blockDim.x) w_s[i] = w[i];
+    __syncthreads();
+    const int h = m / 2;
+    const long long n = (long long)nx * ny * nz;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const int k = (int)(v % nz);
+        const int j = (int)((v / nz) % ny);
+        const int i = (int)(v / ((long long)nz * ny));
+        double acc = 0.0;
+        for (int a = 0; a < m; ++a) {
+            const int ii = min(max(i + h - a, 0), nx - 1);
+            for (int b = 0; b < m; ++b) {
+                const int jj = min(max(j + h - b, 0), ny - 1);
+                const double *row = phi + ((long long)ii * ny + jj) * nz;
+                const double *wr = w_s + (a * m + b) * m;
+                for (int c = 0; c < m; ++c) {
+                    const int kk = min(max(k + h - c, 0), nz - 1);
+                    acc = fma(wr[c], __ldg(row + kk), acc);
+                }
+            }
+        }
+        out[v] = acc;
+    }
+}
+
+extern "C" int iono_convolve3d_nearest_f64(const double *phi, int nx, int ny, int nz, const double *stencil, int m,
+                                           double *out, void *stream) {
+    if (nx < 0 || ny < 0 || nz < 0 || m < 1 || (m & 1) == 0 || m > 31)
+        return fail(IONO_EBADARG, "iono_convolve3d_nearest_f64: bad argument (odd stencil size 1..31)");
+    const long long n = (long long)nx * ny * nz;
+    if (n == 0) return IONO_OK;
+    if (!phi || !stencil || !out || phi == out) return fail(IONO_EBADARG, "iono_convolve3d_nearest_f64: bad pointer");
+    const size_t smem = (size_t)m * m * m * sizeof(double);
+    CU_CHECK(cudaFuncSetAttribute(convolve3d_nearest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    convolve3d_nearest_kernel<<<ew_grid(n), 256, smem, (cudaStream_t)stream>>>(phi, nx, ny, nz, stencil, m, out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}

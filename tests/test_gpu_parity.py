@@ -496,3 +496,20 @@ def test_full_size_lofar_properties(ib):
     # 5. dTEC of the reference antenna is exactly zero
     d = ib.forward_equation(rays, w["K_ne"], tci, 0)
     assert float(d[0].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------- model covariance (Cm . phi)
+def test_covariance_smooth_vs_scipy(ib):
+    from scipy.ndimage import convolve
+    from ionotomo_b200.ionosphere.covariance import Covariance, exponential_sep_stencil
+    rng = np.random.RandomState(12)
+    phi = rng.normal(size=(19, 14, 23))
+    for m in (3, 5, 7):
+        st = rng.uniform(size=(m, m, m))          # deliberately asymmetric: convolution flips it
+        out = Covariance(c_stencil=st).smooth(phi)
+        np.testing.assert_allclose(out, convolve(phi, st, mode='nearest'), rtol=1e-12, atol=1e-12)
+    cov = Covariance(dx=5., dy=5., dz=8.)
+    assert cov.c_stencil.shape[0] % 2 == 1 and cov.c_stencil.min() / cov.c_stencil.max() <= 0.05
+    assert np.array_equal(cov.c_stencil, exponential_sep_stencil(5., 5., 8.))
+    out = cov.smooth(phi)
+    np.testing.assert_allclose(out, convolve(phi, cov.c_stencil, mode='nearest'), rtol=1e-12, atol=1e-12)
