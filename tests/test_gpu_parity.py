@@ -513,3 +513,28 @@ def test_covariance_smooth_vs_scipy(ib):
     assert np.array_equal(cov.c_stencil, exponential_sep_stencil(5., 5., 8.))
     out = cov.smooth(phi)
     np.testing.assert_allclose(out, convolve(phi, cov.c_stencil, mode='nearest'), rtol=1e-12, atol=1e-12)
+
+
+# ---------------------------------------------------------------- linear-operator view (generation C)
+def test_rayop_linear_operator(ib):
+    import torch
+    from ionotomo_b200.tomography.linear_operators import TECForwardEquation
+    P = small_problem(17, 4, 2, 3, 21, 12, 11, 13)
+    rays4 = O.cast_ray(P["origins"], P["directions"], P["tmax"], 21)
+    rays3 = np.ascontiguousarray(rays4[..., :3, :])
+    grid = (P["xvec"], P["yvec"], P["zvec"])
+    M = P["ne"] / 1e13
+    op = TECForwardEquation(1, grid, M, rays3)
+    x = P["rng"].normal(size=M.shape)
+    h = op.matmul(x)
+    # reference semantics: interp(M*x), arclength from point distances, simps, minus [i0]
+    seg = np.sqrt(((rays3[..., 1:] - rays3[..., :-1]) ** 2).sum(-2))
+    s = np.concatenate([np.zeros_like(seg[..., :1]), np.cumsum(seg, -1)], -1)
+    vals = O.rgi_linear(P["xvec"], P["yvec"], P["zvec"], M * x, rays3[..., 0, :], rays3[..., 1, :], rays3[..., 2, :])
+    ref = O.simps_avg(vals, s)
+    ref = ref - ref[1:2]
+    assert h.shape == ref.shape == (4, 2, 3)
+    assert np.abs(h - ref).max() < 1e-11 * np.abs(ref).max() + 1e-9 * np.abs(O.simps_avg(vals, s)).max() * 1e-3
+    y = P["rng"].normal(size=h.shape)
+    g = op.matmul(y, adjoint=True)
+    assert abs((h * y).sum() - (x * g).sum()) <= 1e-10 * abs((h * y).sum())
