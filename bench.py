@@ -272,7 +272,18 @@ def main():
     m_true = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_true"])
     m_tci = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_prior"])      # model being fitted
     grid = m_tci.grid()
-    rays = ib.cast_ray((w["origins"], w["directions"]), ib.Fermat(m_tci), w["tmax"], w["Ns"])
+    fermat = ib.Fermat(m_tci)
+    rays = ib.cast_ray((w["origins"], w["directions"]), fermat, w["tmax"], w["Ns"])
+    # ray generation, timed for the record (write-only kernel; not part of the steps)
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    _lib.call("iono_cast_rays_straight_f64", _lib.ptr(w["origins"]), _lib.ptr(w["directions"]),
+              rays.shape[0] * rays.shape[1] * rays.shape[2], float(w["tmax"]), int(w["Ns"]), _lib.ptr(rays),
+              _lib.stream_ptr())
+    c1.record()
+    torch.cuda.synchronize()
+    cast_ms = c0.elapsed_time(c1)
     del w["origins"], w["directions"]
     Na, Nt, Nd, _, Ns = rays.shape
     R, V = Na * Nt * Nd, NX * NY * NZ
@@ -416,6 +427,10 @@ def main():
                               "achieved_gbs": bytes_fwd / fwd_ms / 1e6, "frac": bytes_fwd / fwd_ms / 1e6 / hbm,
                               "rays_per_s": R / fwd_ms * 1e3},
     }
+    bytes_cast = R * 4 * Ns * 8
+    kernels["cast_rays"] = {"ms": cast_ms, "algorithmic_bytes": bytes_cast, "achieved_gbs": bytes_cast / cast_ms / 1e6,
+                            "frac": bytes_cast / cast_ms / 1e6 / hbm, "rays_per_s": R / cast_ms * 1e3,
+                            "in_step": False}
     adj_name = "binned_adjoint" if bp is not None else "ray_sweep_adjoint_scatter"
     kernels[adj_name] = {"ms": adj_ms, "algorithmic_bytes": bytes_adj, "achieved_gbs": bytes_adj / adj_ms / 1e6,
                          "frac": bytes_adj / adj_ms / 1e6 / hbm, "rays_per_s": R / adj_ms * 1e3}
