@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--order", default=os.environ.get("IONO_BENCH_ORDER", "time"))
+    ap.add_argument("--overlap", type=int, default=0, choices=[0, 1, 2, 4, 8, 16],
+                    help="EXPERIMENTAL: chunks of the binned apply whose allreduce overlaps the next chunk "
+                         "(0 = one NCCL allreduce after the apply, the validated path)")
     ap.add_argument("--adjoint", default="binned", choices=["binned", "scatter"],
                     help="binned: pre-assembled voxel-binned gather (default); scatter: stateless fp64 atomics")
     return ap.parse_args()
@@ -318,7 +321,12 @@ def main():
         coef = adjoint_coefficients(g, dobs, CdCt, i0)
         e2, e3 = ev(), ev()
         e2.record()
-        if bp is not None:
+        if bp is not None and world > 1 and args.overlap:
+            # chunked apply; the allreduce of each finished voxel slice overlaps the next chunk
+            bp.apply_overlapped(coef, scale=ne, out=acc, n_chunks=args.overlap,
+                                reduce_slice=sharding.allreduce_sum_async)
+            e3.record()
+        elif bp is not None:
             bp.apply(coef, scale=ne, out=acc)            # ne[v] * sum_ray A[v,ray] coef[ray]
             e3.record()
             sharding.allreduce_sum_(acc)
@@ -456,7 +464,8 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload_config(world, nt), dx_km=w["dx_km"], dy_km=w["dy_km"], dz_km=w["dz_km"],
-                       ray_order=args.order, adjoint=args.adjoint),
+                       ray_order=args.order, adjoint=args.adjoint,
+                       allreduce_overlap_chunks=(args.overlap if world > 1 else 0)),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": hbm,
                      "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src},
         "kernels": kernels,

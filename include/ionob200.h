@@ -158,6 +158,12 @@ int iono_backprojector_create(iono_grid_t grid, const double *rays, int Na, int 
                               iono_backprojector_t *bp_out, unsigned long long *oob_count, void *stream);
 int iono_backprojector_apply_f64(iono_backprojector_t bp, const double *coef, const double *scale,
                                  double *out, void *stream);
+/* The apply in sixteenths of the operator, for overlapping the cross-GPU sum with the computation:
+ * chunks [c0,c1) (issue them in increasing order on one stream, starting at 0); afterwards
+ * out[chunk_voxels(c0) : chunk_voxels(c1)) is final and may be all-reduced while later chunks run. */
+int iono_backprojector_apply_chunks_f64(iono_backprojector_t bp, const double *coef, const double *scale,
+                                        double *out, int c0, int c1, void *stream);
+long long iono_backprojector_chunk_voxels(iono_backprojector_t bp, int c);
 long long iono_backprojector_nnz(iono_backprojector_t bp);
 long long iono_backprojector_bytes(iono_backprojector_t bp);
 int iono_backprojector_destroy(iono_backprojector_t bp);

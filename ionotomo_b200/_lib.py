@@ -48,6 +48,8 @@ SIGNATURES = {
     "iono_phase_assemble_f64": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "iono_backprojector_create": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp, _vp]),
     "iono_backprojector_apply_f64": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "iono_backprojector_apply_chunks_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "iono_backprojector_chunk_voxels": (ctypes.c_longlong, [_vp, _i]),
     "iono_backprojector_nnz": (ctypes.c_longlong, [_vp]),
     "iono_backprojector_bytes": (ctypes.c_longlong, [_vp]),
     "iono_backprojector_destroy": (_i, [_vp]),
@@ -57,7 +59,7 @@ SIGNATURES = {
 KERNEL_LAUNCHES = {
     "iono_ne_from_m_f64": 1, "iono_mul_f64": 1, "iono_cast_rays_straight_f64": 1, "iono_cast_rays_frames_f64": 1, "iono_ne_to_refractive_index_f64": 1, "iono_optical_path_f64": 1, "iono_tci_interp_f64": 1,
     "iono_tec_forward_f64": 1, "iono_dtec_f64": 1, "iono_adjoint_coef_f64": 1, "iono_tec_adjoint_f64": 1,
-    "iono_misfit_f64": 2, "iono_convolve3d_nearest_f64": 1, "iono_phase_integrals_f64": 1, "iono_chord_adjoint_f64": 1, "iono_phase_assemble_f64": 1, "iono_backprojector_apply_f64": 4,
+    "iono_misfit_f64": 2, "iono_convolve3d_nearest_f64": 1, "iono_phase_integrals_f64": 1, "iono_chord_adjoint_f64": 1, "iono_phase_assemble_f64": 1, "iono_backprojector_apply_f64": 4, "iono_backprojector_apply_chunks_f64": 3,
 }
 launch_count = 0
 

@@ -37,6 +37,10 @@ struct iono_backprojector {
     long long R;
     int Na, Nt, Nd;
     int seg;                 // entries per segment
+    // 16 equal chunks of the segment range (for overlapping the cross-GPU sum with the apply):
+    // chunk c completes rows [chunk_row[c], chunk_row[c+1]) = voxels [chunk_vox[c], chunk_vox[c+1])
+    long long chunk_seg[17], chunk_row[17], chunk_vox[17];
+    int chunk_short[17], chunk_vlong[17];   // index ranges in the (sorted) straddler lists
     double *coef_perm;       // [R] coefficients in the internal ray order (a, d, t)
     int device;
 };
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *_
                                                                     const double *__restrict__ weight,
                                                                     const double *__restrict__ coef,
                                                                     const double *__restrict__ scale, long long nnz,
+                                                                    long long seg_begin, long long seg_end,
                                                                     double *__restrict__ out,
                                                                     double *__restrict__ partial) {
     // double-buffered segment of the entry stream, filled by TMA bulk copies
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *_
     double *part = reinterpret_cast<double *>(bp_smem + 2 * BP_SEG * 12 + 16);   // [8]
     int *next_row = reinterpret_cast<int *>(bp_smem + 2 * BP_SEG * 12 + 16 + 64);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long nseg = (nnz + BP_SEG - 1) / BP_SEG;
+    const long long nseg = seg_end;
     if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -211,11 +216,11 @@ __global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *_
         bulk_g2s(w_s[buf], weight + seg * BP_SEG, BP_SEG * 8, &bar[buf], pol);
         bulk_g2s(r_s[buf], ray_idx + seg * BP_SEG, BP_SEG * 4, &bar[buf], pol);
     };
-    if (threadIdx.x == 0 && (long long)blockIdx.x < nseg) issue(blockIdx.x, 0);
+    if (threadIdx.x == 0 && seg_begin + (long long)blockIdx.x < nseg) issue(seg_begin + blockIdx.x, 0);
     unsigned int phase = 0;
     int buf = 0;
     constexpr int PER = BP_SEG / 256;
-    for (long long seg = blockIdx.x; seg < nseg; seg += gridDim.x, buf ^= 1) {
+    for (long long seg = seg_begin + blockIdx.x; seg < nseg; seg += gridDim.x, buf ^= 1) {
         const long long k0 = seg * BP_SEG, k1 = min(k0 + (long long)BP_SEG, nnz);
         const int2 rr = seg_rows[seg];
         if (threadIdx.x == 0) {
@@ -297,6 +302,7 @@ __global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *
                                                                      const double *__restrict__ weight,
                                                                      const double *__restrict__ coef,
                                                                      const double *__restrict__ scale, long long nnz,
+                                                                     long long seg_begin, long long seg_end,
                                                                      double *__restrict__ out,
                                                                      double *__restrict__ partial) {
     extern __shared__ __align__(128) unsigned char bp_smem[];
@@ -304,8 +310,8 @@ __global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *
     constexpr int STAGE = BP_WSEG * 12;                       // weights then ray indices
     unsigned char *mine = bp_smem + (size_t)warp * (2 * STAGE);
     uint64_t *bar = reinterpret_cast<uint64_t *>(bp_smem + (size_t)nwarp * 2 * STAGE) + warp * 2;
-    const long long nseg = (nnz + BP_WSEG - 1) / BP_WSEG;
-    const long long gw = (long long)blockIdx.x * nwarp + warp, gstride = (long long)gridDim.x * nwarp;
+    const long long nseg = seg_end;
+    const long long gw = seg_begin + (long long)blockIdx.x * nwarp + warp, gstride = (long long)gridDim.x * nwarp;
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
@@ -434,6 +440,35 @@ __global__ void __launch_bounds__(256) backproject_combine_kernel(const int *__r
     }
 }
 
+// Build time: boundaries of 16 equal chunks of the segment range.  Chunk c owns the rows whose LAST
+// entry lies in its segments, i.e. rows [row(c), row(c+1)) with row(c) = #rows ending at or before
+// the chunk's first entry; voxels likewise (rows are sorted by voxel).
+__global__ void chunk_table_kernel(const long long *__restrict__ ptr, const unsigned int *__restrict__ row_voxel,
+                                   long long n_rows, long long nseg, int seg, long long V,
+                                   const int *__restrict__ short_rows, int n_short, const int *__restrict__ vlong_rows,
+                                   int n_vlong, long long *__restrict__ tab) {
+    const int c = threadIdx.x;
+    if (c > 16) return;
+    const long long sb = (c == 16) ? nseg : nseg * c / 16;
+    const long long first_entry = sb * seg;
+    // number of rows with ptr[r+1] <= first_entry
+    long long lo = 0, hi = n_rows;
+    while (lo < hi) {
+        const long long mid = (lo + hi) >> 1;
+        if (ptr[mid + 1] <= first_entry) lo = mid + 1; else hi = mid;
+    }
+    const long long row = (c == 16) ? n_rows : lo;
+    long long vox = (c == 0) ? 0 : ((row < n_rows) ? (long long)row_voxel[row] : V);
+    if (c == 16) vox = V;
+    auto lower = [&](const int *list, int n) {
+        int a = 0, b = n;
+        while (a < b) { const int m = (a + b) >> 1; if ((long long)list[m] < row) a = m + 1; else b = m; }
+        return (long long)a;
+    };
+    tab[c * 5 + 0] = sb; tab[c * 5 + 1] = row; tab[c * 5 + 2] = vox;
+    tab[c * 5 + 3] = lower(short_rows, n_short); tab[c * 5 + 4] = lower(vlong_rows, n_vlong);
+}
+
 extern "C" int iono_backprojector_destroy(iono_backprojector_t h) {
     if (!h) return IONO_OK;
     cudaFree(h->ray_idx);
@@ -466,6 +501,7 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
     CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
 
     iono_backprojector *h = new iono_backprojector();
+    for (int c = 0; c <= 16; ++c) { h->chunk_seg[c] = 0; h->chunk_row[c] = 0; h->chunk_vox[c] = (c == 16) ? V : 0; h->chunk_short[c] = 0; h->chunk_vlong[c] = 0; }
     h->seg = BP_WSEG;   // warp-private segments (default); IONO_BP_SEG=1024|2048 selects the CTA-segment kernel
     if (const char *es = getenv("IONO_BP_SEG")) h->seg = (atoi(es) == 2048) ? 2048 : (atoi(es) == 1024 ? 1024 : BP_WSEG);
     const int BP_SEG = h->seg;
@@ -574,19 +610,54 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
         BP_TRY(cudaMalloc(&h->partial, (size_t)(2 * nseg + 2) * sizeof(double)));
         BP_TRY(cudaMalloc(&h->items, (size_t)(nseg + 1) * sizeof(int2)));
         BP_TRY(cudaMalloc(&h->long_rows, (size_t)(nseg + 1) * sizeof(int)));   // <= one straddler per boundary
-        BP_TRY(cudaMalloc(&h->vlong_rows, (size_t)(nseg / 8 + 2) * sizeof(int)));
+        BP_TRY(cudaMalloc(&h->vlong_rows, (size_t)(nseg / 7 + 2) * sizeof(int)));
         BP_TRY(cudaMemsetAsync(d_count, 0, 2 * sizeof(int), st));
         if (nseg > 0) {
             segment_rows_kernel<<<ew_grid(nseg), 256, 0, st>>>(h->ptr, h->n_rows, M, BP_SEG, h->items);
             BP_TRY(cudaGetLastError());
             find_straddling_rows_kernel<<<ew_grid(h->n_rows), 256, 0, st>>>(h->ptr, h->n_rows, BP_SEG, h->long_rows, d_count,
                                                                           (int)nseg + 1, h->vlong_rows, d_count + 1,
-                                                                          (int)(nseg / 8 + 2));
+                                                                          (int)(nseg / 7 + 2));
             BP_TRY(cudaGetLastError());
         }
         BP_TRY(cudaMemcpyAsync(&h->n_long, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
         BP_TRY(cudaMemcpyAsync(&h->n_vlong, d_count + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         BP_TRY(cudaStreamSynchronize(st));
+        if (h->n_long > (int)nseg + 1) h->n_long = (int)nseg + 1;            // cannot happen (one straddler per boundary)
+        if (h->n_vlong > (int)(nseg / 7 + 2)) h->n_vlong = (int)(nseg / 7 + 2);
+        // sort the straddler lists by row and cut everything into 16 chunks of segments
+        {
+            int *lists[2] = {h->long_rows, h->vlong_rows};
+            const int counts[2] = {h->n_long, h->n_vlong};
+            for (int li = 0; li < 2; ++li) {
+                if (counts[li] < 2) continue;
+                int *alt = nullptr;
+                BP_TRY(cudaMalloc(&alt, (size_t)counts[li] * sizeof(int)));
+                tmp_bytes = 0;
+                e = cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, lists[li], alt, counts[li], 0, 32, st);
+                if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes);
+                if (e == cudaSuccess) e = cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, lists[li], alt, counts[li], 0, 32, st);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(lists[li], alt, (size_t)counts[li] * sizeof(int), cudaMemcpyDeviceToDevice, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                cudaFree(tmp); tmp = nullptr;
+                cudaFree(alt);
+                if (e != cudaSuccess) { cleanup(); iono_backprojector_destroy(h); return fail(IONO_ECUDA, "iono_backprojector_create: sort: %s", cudaGetErrorString(e)); }
+            }
+            long long *d_tab = nullptr;
+            BP_TRY(cudaMalloc(&d_tab, 17 * 5 * sizeof(long long)));
+            chunk_table_kernel<<<1, 32, 0, st>>>(h->ptr, h->row_voxel, h->n_rows, nseg, BP_SEG, V, h->long_rows, h->n_long,
+                                                 h->vlong_rows, h->n_vlong, d_tab);
+            long long tab[17 * 5];
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(tab, d_tab, sizeof(tab), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            cudaFree(d_tab);
+            if (e != cudaSuccess) { cleanup(); iono_backprojector_destroy(h); return fail(IONO_ECUDA, "iono_backprojector_create: chunk table: %s", cudaGetErrorString(e)); }
+            for (int c = 0; c <= 16; ++c) {
+                h->chunk_seg[c] = tab[c * 5 + 0]; h->chunk_row[c] = tab[c * 5 + 1]; h->chunk_vox[c] = tab[c * 5 + 2];
+                h->chunk_short[c] = (int)tab[c * 5 + 3]; h->chunk_vlong[c] = (int)tab[c * 5 + 4];
+            }
+        }
     }
 #undef BP_TRY
     cleanup();
@@ -595,59 +666,85 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
     return IONO_OK;
 }
 
-static cudaError_t bp_combine(iono_backprojector_t h, const double *scale, double *out, cudaStream_t st) {
-    if (h->n_long > 0)
-        backproject_combine_short_kernel<<<ew_grid(h->n_long), 256, 0, st>>>(h->long_rows, h->n_long, h->seg, h->ptr,
-                                                                           h->row_voxel, h->partial, scale, out);
-    if (h->n_vlong > 0)
-        backproject_combine_kernel<<<(h->n_vlong + 7) / 8, 256, 0, st>>>(h->vlong_rows, h->n_vlong, h->seg, h->ptr,
-                                                                         h->row_voxel, h->partial, scale, out);
+// combine the straddling rows completed in chunks [c0, c1)
+static cudaError_t bp_combine(iono_backprojector_t h, const double *scale, double *out, int c0, int c1,
+                              cudaStream_t st) {
+    const int ns = h->chunk_short[c1] - h->chunk_short[c0], nv = h->chunk_vlong[c1] - h->chunk_vlong[c0];
+    if (ns > 0)
+        backproject_combine_short_kernel<<<ew_grid(ns), 256, 0, st>>>(h->long_rows + h->chunk_short[c0], ns, h->seg,
+                                                                    h->ptr, h->row_voxel, h->partial, scale, out);
+    if (nv > 0)
+        backproject_combine_kernel<<<(nv + 7) / 8, 256, 0, st>>>(h->vlong_rows + h->chunk_vlong[c0], nv, h->seg, h->ptr,
+                                                                 h->row_voxel, h->partial, scale, out);
     return cudaGetLastError();
+}
+
+// Chunks c0..c1-1 (sixteenths of the entry stream).  Chunk 0 also clears `out` and permutes the
+// coefficients, so the chunks of one apply must be issued in increasing order on one stream.  After the
+// call, out[chunk_voxels(c0) : chunk_voxels(c1)) is final -- the caller may start summing that
+// slice across GPUs while the next chunks are computed.
+extern "C" int iono_backprojector_apply_chunks_f64(iono_backprojector_t h, const double *coef, const double *scale,
+                                                   double *out, int c0, int c1, void *stream) {
+    if (!h || !out || (h->R > 0 && !coef) || c0 < 0 || c1 > 16 || c0 >= c1)
+        return fail(IONO_EBADARG, "iono_backprojector_apply_chunks_f64: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ctas = sm_count() * 8;
+    if (c0 == 0) {
+        CU_CHECK(cudaMemsetAsync(out, 0, (size_t)h->V * sizeof(double), st));   // voxels no ray touches
+        if (h->nnz == 0) return IONO_OK;
+        permute_coef_kernel<<<ctas, 256, 0, st>>>(coef, h->Na, h->Nt, h->Nd, h->coef_perm);
+        CU_CHECK(cudaGetLastError());
+    }
+    if (h->nnz == 0) return IONO_OK;
+    const int BP_SEG = h->seg;
+    const long long sb = h->chunk_seg[c0], se = h->chunk_seg[c1];
+    const long long nseg = se - sb;
+    if (nseg > 0) {
+        if (BP_SEG == BP_WSEG) {
+            int warps = 8, per_sm = 4;
+            if (const char *ew = getenv("IONO_BP_WARPS")) warps = atoi(ew);
+            if (const char *ec = getenv("IONO_BP_CTAS")) per_sm = atoi(ec);
+            if (warps < 1 || warps > 8) warps = 8;
+            const int smem = warps * 2 * BP_WSEG * 12 + warps * 16 + 64;
+            const long long cap = (long long)sm_count() * per_sm;
+            const long long want = (nseg + warps - 1) / warps;
+            CU_CHECK(cudaFuncSetAttribute(backproject_wsegments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            backproject_wsegments_kernel<<<(int)(want < cap ? want : cap), warps * 32, smem, st>>>(
+                h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, sb, se, out,
+                h->partial);
+        } else {
+            const int bp_smem_bytes = 2 * BP_SEG * 12 + 16 + 64 + 16;
+            int per_sm = (227 * 1024) / (bp_smem_bytes + 1024);
+            if (per_sm > 8) per_sm = 8;
+            if (const char *ec = getenv("IONO_BP_CTAS")) per_sm = atoi(ec);
+            const long long cap = (long long)sm_count() * per_sm;
+            const int ctas_seg = (int)(nseg < cap ? nseg : cap);
+            if (BP_SEG == 2048) {
+                CU_CHECK(cudaFuncSetAttribute(backproject_segments_kernel<2048>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, bp_smem_bytes));
+                backproject_segments_kernel<2048><<<ctas_seg, 256, bp_smem_bytes, st>>>(
+                    h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, sb, se, out,
+                    h->partial);
+            } else {
+                CU_CHECK(cudaFuncSetAttribute(backproject_segments_kernel<1024>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, bp_smem_bytes));
+                backproject_segments_kernel<1024><<<ctas_seg, 256, bp_smem_bytes, st>>>(
+                    h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, sb, se, out,
+                    h->partial);
+            }
+        }
+        CU_CHECK(cudaGetLastError());
+    }
+    CU_CHECK(bp_combine(h, scale, out, c0, c1, st));
+    return IONO_OK;
+}
+
+extern "C" long long iono_backprojector_chunk_voxels(iono_backprojector_t h, int c) {
+    return (h && c >= 0 && c <= 16) ? h->chunk_vox[c] : -1;
 }
 
 extern "C" int iono_backprojector_apply_f64(iono_backprojector_t h, const double *coef, const double *scale,
                                             double *out, void *stream) {
     if (!h || !out || (h->R > 0 && !coef)) return fail(IONO_EBADARG, "iono_backprojector_apply_f64: bad argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int ctas = sm_count() * 8;
-    CU_CHECK(cudaMemsetAsync(out, 0, (size_t)h->V * sizeof(double), st));   // voxels no ray touches
-    if (h->nnz == 0) return IONO_OK;
-    permute_coef_kernel<<<ctas, 256, 0, st>>>(coef, h->Na, h->Nt, h->Nd, h->coef_perm);
-    CU_CHECK(cudaGetLastError());
-    const int BP_SEG = h->seg;
-    const long long nseg = (h->nnz + BP_SEG - 1) / BP_SEG;
-    if (BP_SEG == BP_WSEG) {
-        int warps = 8, per_sm = 4;
-        if (const char *ew = getenv("IONO_BP_WARPS")) warps = atoi(ew);
-        if (const char *ec = getenv("IONO_BP_CTAS")) per_sm = atoi(ec);
-        const int smem = warps * 2 * BP_WSEG * 12 + warps * 16 + 64;
-        const long long cap = (long long)sm_count() * per_sm;
-        const long long want = (nseg + warps - 1) / warps;
-        CU_CHECK(cudaFuncSetAttribute(backproject_wsegments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        backproject_wsegments_kernel<<<(int)(want < cap ? want : cap), warps * 32, smem, st>>>(
-            h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, out, h->partial);
-        CU_CHECK(cudaGetLastError());
-        CU_CHECK(bp_combine(h, scale, out, st));
-        return IONO_OK;
-    }
-    const int bp_smem_bytes = 2 * BP_SEG * 12 + 16 + 64 + 16;
-    int per_sm = (227 * 1024) / (bp_smem_bytes + 1024);
-    if (per_sm > 8) per_sm = 8;
-    if (const char *ec = getenv("IONO_BP_CTAS")) per_sm = atoi(ec);
-    const long long cap = (long long)sm_count() * per_sm;
-    const int ctas_seg = (int)(nseg < cap ? nseg : cap);
-    if (BP_SEG == 2048) {
-        CU_CHECK(cudaFuncSetAttribute(backproject_segments_kernel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      bp_smem_bytes));
-        backproject_segments_kernel<2048><<<ctas_seg, 256, bp_smem_bytes, st>>>(
-            h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, out, h->partial);
-    } else {
-        CU_CHECK(cudaFuncSetAttribute(backproject_segments_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      bp_smem_bytes));
-        backproject_segments_kernel<1024><<<ctas_seg, 256, bp_smem_bytes, st>>>(
-            h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, out, h->partial);
-    }
-    CU_CHECK(cudaGetLastError());
-    CU_CHECK(bp_combine(h, scale, out, st));
-    return IONO_OK;
+    return iono_backprojector_apply_chunks_f64(h, coef, scale, out, 0, 16, stream);
 }

@@ -35,3 +35,10 @@ def sharded_misfit(S_local, group=None):
     s = S_local.detach().clone().reshape(1)
     allreduce_sum_(s, group)
     return float(s[0])
+
+
+def allreduce_sum_async(t, group=None):
+    """Start an in-place sum over ranks and return the work handle (``None`` for one process)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    return None

@@ -41,6 +41,20 @@ def _worker(rank, world, port, out):
                                    reduce_fn=sharding.allreduce_sum_, backprojector=bp)
         ref = O.gradient_exact(rays, g, dobs, i0, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], CdCt)
         ok = ok and np.abs(grad.cpu().numpy() - ref).max() < 1e-10 * np.abs(ref).max()
+    if os.environ.get("IONO_TEST_OVERLAP") != "1":     # experimental path, opt-in (see apply_overlapped)
+        if rank == 0:
+            out.put(bool(ok))
+        dist.destroy_process_group()
+        return
+    # overlapped variant: chunked apply + asynchronous all_reduce of the finished slices
+    bp = ib.BackProjector(rs, tci)
+    from ionotomo_b200.inversion.gradient import adjoint_coefficients
+    from ionotomo_b200.inversion.forward_equation import _ne_from_m
+    coef = adjoint_coefficients(torch.as_tensor(g_loc).cuda(), torch.as_tensor(np.ascontiguousarray(dobs[:, t0:t1])).cuda(),
+                                torch.as_tensor(np.ascontiguousarray(CdCt[:, t0:t1])).cuda(), i0)
+    ne = _ne_from_m(tci.device_M(), P["K_ne"])
+    grad2 = bp.apply_overlapped(coef, scale=ne, n_chunks=4, reduce_slice=sharding.allreduce_sum_async)
+    ok = ok and np.abs(grad2.cpu().numpy() - ref).max() < 1e-10 * np.abs(ref).max()
     if rank == 0:
         out.put(bool(ok))
     dist.destroy_process_group()

@@ -297,6 +297,31 @@ def test_binned_backprojector_vs_oracle(ib, Ns):
         ib.BackProjector(O.cast_ray(P["origins"], P["directions"], 1300., 8), tci)
 
 
+@pytest.mark.parametrize("seg", ["256", "1024"])
+def test_binned_backprojector_chunked_apply(ib, seg, monkeypatch):
+    import torch
+    monkeypatch.setenv("IONO_BP_SEG", seg)
+    P = small_problem(79, 20, 3, 16, 64, 40, 36, 64)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    rays = ib.cast_ray((torch.as_tensor(P["origins"]).cuda(), torch.as_tensor(P["directions"]).cuda()),
+                       ib.Fermat(tci), 1000., 64)
+    y = torch.randn(rays.shape[:3], dtype=torch.float64, device="cuda")
+    scale = torch.rand(P["m"].shape, dtype=torch.float64, device="cuda")
+    bp = ib.BackProjector(rays, tci)
+    ref = bp.apply(y, scale=scale)
+    V = ref.numel()
+    for n_chunks in (1, 2, 4, 8, 16):
+        seen = []
+        out = torch.full_like(ref, float("nan"))
+        got = bp.apply_overlapped(y, scale=scale, out=out, n_chunks=n_chunks,
+                                  reduce_slice=lambda sl: seen.append((sl.data_ptr(), sl.numel())))
+        assert torch.equal(got, ref)
+        # the slices handed to the reducer are the n_chunks equal parts of the grid, in order
+        base = out.data_ptr()
+        bounds = [V * j // n_chunks for j in range(n_chunks + 1)]
+        assert seen == [(base + 8 * a, b - a) for a, b in zip(bounds[:-1], bounds[1:])]
+
+
 def test_binned_backprojector_matches_scatter_lofar_slice(ib):
     import torch
     from ionotomo_b200.inversion.gradient import backproject

@@ -69,3 +69,18 @@ def test_sharded_gradient_gloo_world2():
         p.join(180)
         assert p.exitcode == 0
     assert out.get(timeout=5) is True
+
+
+def test_released_slices_are_rank_independent():
+    """The overlapped apply hands the reducer the same equal slices in the same order on every rank,
+    whatever the rank's own chunk boundaries are (a collective must match in size and order)."""
+    from ionotomo_b200.inversion.gradient import released_slices
+    V, K = 1000, 4
+    bounds = [V * j // K for j in range(K + 1)]
+    for progress in ([100, 300, 620, 1000], [250, 500, 750, 1000], [999, 999, 1000], [1000]):
+        nxt, got = 0, []
+        for done in progress:
+            rel = released_slices(bounds, nxt, done)
+            got += rel
+            nxt += len(rel)
+        assert got == list(zip(bounds[:-1], bounds[1:]))
