@@ -84,3 +84,49 @@ def test_released_slices_are_rank_independent():
             got += rel
             nxt += len(rel)
         assert got == list(zip(bounds[:-1], bounds[1:]))
+
+
+def test_apply_overlapped_host_logic_with_fake_library(monkeypatch):
+    """BackProjector.apply_overlapped without a GPU: the C entry points are replaced by fakes that
+    record the chunk calls; checks chunk order, the released slices and the waits."""
+    from ionotomo_b200 import _lib
+    from ionotomo_b200.inversion import gradient as G
+    V = 6 * 5 * 4
+    chunk_vox = [0, 3, 9, 20, 20, 31, 40, 47, 55, 60, 71, 80, 88, 97, 105, 111, V]   # this rank's progress table
+    calls = []
+
+    class FakeLib(object):
+        def iono_backprojector_chunk_voxels(self, handle, c):
+            return chunk_vox[c]
+
+    monkeypatch.setattr(_lib, "load", lambda: FakeLib())
+    monkeypatch.setattr(_lib, "to_device", lambda a, device=None: a)
+    monkeypatch.setattr(_lib, "ptr", lambda t: None)
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
+    monkeypatch.setattr(_lib, "call", lambda name, *args: calls.append((name, args[4], args[5])))
+    bp = object.__new__(G.BackProjector)
+    bp.handle, bp.shape = None, (6, 5, 4)
+
+    class Handle(object):
+        waited = 0
+
+        def wait(self):
+            Handle.waited += 1
+
+    for n_chunks in (1, 2, 4, 8, 16):
+        del calls[:]
+        Handle.waited = 0
+        seen = []
+        out = torch.zeros(6, 5, 4, dtype=torch.float64)
+        coef = torch.zeros(2, 2, 2, dtype=torch.float64)
+
+        def reducer(sl):
+            seen.append((sl.data_ptr() - out.data_ptr(), sl.numel()))
+            return Handle()
+        got = bp.apply_overlapped(coef, out=out, n_chunks=n_chunks, reduce_slice=reducer)
+        assert got is out
+        step = 16 // n_chunks
+        assert calls == [("iono_backprojector_apply_chunks_f64", c, c + step) for c in range(0, 16, step)]
+        bounds = [V * j // n_chunks for j in range(n_chunks + 1)]
+        assert seen == [(8 * a, b - a) for a, b in zip(bounds[:-1], bounds[1:])]
+        assert Handle.waited == n_chunks
