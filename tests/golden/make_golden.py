@@ -265,6 +265,18 @@ def main():
     np.savez(os.path.join(OUT, "optical_path.npz"), xvec=xvec, yvec=yvec, zvec=zvec, ne=ne * 20., frequency=40e6,
              origins=origins, directions=directions, rays=rays_c, tmax=600., Ns=12, n_field=fermat_c.n_tci.M)
 
+    # 7c. BASELINE.json configs[0]: 10 antennas x 20 directions x 1 time, 50x50x30 grid, Ns = nz = 30
+    xvec, yvec, zvec, ne, origins, directions, rng = small_problem(1, 10, 1, 20, 30, 50, 50, 30)
+    ne_tci = TriCubic(xvec, yvec, zvec, ne)
+    fermat = Fermat(ne_tci=ne_tci, frequency=120e6, type='z', straight_line_approx=True)
+    rays = cast_ray((origins, directions), fermat, 1000., ne_tci.nz)
+    K_ne = np.median(ne)
+    m_tci = ne_tci.copy()
+    m_tci.M = np.log(m_tci.M / K_ne)
+    dtec = forward_equation(rays, K_ne, m_tci, 0)
+    np.savez_compressed(os.path.join(OUT, "config1.npz"), xvec=xvec, yvec=yvec, zvec=zvec, m=m_tci.M, K_ne=K_ne,
+                        origins=origins[:, 0, 0, :], directions=directions[0], rays=rays, dtec=dtec)
+
     # 8. synthetic-input recipe (ionosphere/simulation.py:45-112, ionosphere/iri.py:20-68)
     xvec = np.linspace(-50., 50., 16)
     yvec = np.linspace(-40., 40., 12)

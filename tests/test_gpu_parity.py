@@ -297,31 +297,6 @@ def test_binned_backprojector_vs_oracle(ib, Ns):
         ib.BackProjector(O.cast_ray(P["origins"], P["directions"], 1300., 8), tci)
 
 
-@pytest.mark.parametrize("seg", ["256", "1024"])
-def test_binned_backprojector_chunked_apply(ib, seg, monkeypatch):
-    import torch
-    monkeypatch.setenv("IONO_BP_SEG", seg)
-    P = small_problem(79, 20, 3, 16, 64, 40, 36, 64)
-    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
-    rays = ib.cast_ray((torch.as_tensor(P["origins"]).cuda(), torch.as_tensor(P["directions"]).cuda()),
-                       ib.Fermat(tci), 1000., 64)
-    y = torch.randn(rays.shape[:3], dtype=torch.float64, device="cuda")
-    scale = torch.rand(P["m"].shape, dtype=torch.float64, device="cuda")
-    bp = ib.BackProjector(rays, tci)
-    ref = bp.apply(y, scale=scale)
-    V = ref.numel()
-    for n_chunks in (1, 2, 4, 8, 16):
-        seen = []
-        out = torch.full_like(ref, float("nan"))
-        got = bp.apply_overlapped(y, scale=scale, out=out, n_chunks=n_chunks,
-                                  reduce_slice=lambda sl: seen.append((sl.data_ptr(), sl.numel())))
-        assert torch.equal(got, ref)
-        # the slices handed to the reducer are the n_chunks equal parts of the grid, in order
-        base = out.data_ptr()
-        bounds = [V * j // n_chunks for j in range(n_chunks + 1)]
-        assert seen == [(base + 8 * a, b - a) for a, b in zip(bounds[:-1], bounds[1:])]
-
-
 def test_binned_backprojector_matches_scatter_lofar_slice(ib):
     import torch
     from ionotomo_b200.inversion.gradient import backproject
@@ -563,3 +538,44 @@ def test_rayop_linear_operator(ib):
     y = P["rng"].normal(size=h.shape)
     g = op.matmul(y, adjoint=True)
     assert abs((h * y).sum() - (x * g).sum()) <= 1e-10 * abs((h * y).sum())
+
+
+# ---------------------------------------------------------------- added after the last GPU run of round 1
+# (kept last so that a surprise here cannot hide the rest of the suite under `pytest -x`)
+def test_config1_golden(ib, golden):
+    """BASELINE.json configs[0] against the reference's own output (rays by odeint, dTEC by its
+    forward_equation): 10 antennas x 20 directions x 1 time, 50x50x30 grid, Ns = nz = 30."""
+    g = golden("config1")
+    m_tci = ib.TriCubic(g["xvec"], g["yvec"], g["zvec"], g["m"])
+    rays = ib.calc_rays(g["origins"], g["directions"], [0], None, None, None, m_tci, 120e6, True, 1000., None)
+    assert rays.shape == (10, 1, 20, 4, 30)
+    np.testing.assert_allclose(rays, g["rays"], rtol=0, atol=1e-9)
+    dtec = ib.forward_equation(rays, float(g["K_ne"]), m_tci, 0)
+    np.testing.assert_allclose(dtec, g["dtec"], rtol=0, atol=1e-10 * np.abs(g["dtec"]).max())
+    dtec_ref_rays = ib.forward_equation(g["rays"], float(g["K_ne"]), m_tci, 0)
+    np.testing.assert_allclose(dtec_ref_rays, g["dtec"], rtol=0, atol=1e-10 * np.abs(g["dtec"]).max())
+
+
+@pytest.mark.parametrize("seg", ["256", "1024"])
+def test_binned_backprojector_chunked_apply(ib, seg, monkeypatch):
+    import torch
+    monkeypatch.setenv("IONO_BP_SEG", seg)
+    P = small_problem(79, 20, 3, 16, 64, 40, 36, 64)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    rays = ib.cast_ray((torch.as_tensor(P["origins"]).cuda(), torch.as_tensor(P["directions"]).cuda()),
+                       ib.Fermat(tci), 1000., 64)
+    y = torch.randn(rays.shape[:3], dtype=torch.float64, device="cuda")
+    scale = torch.rand(P["m"].shape, dtype=torch.float64, device="cuda")
+    bp = ib.BackProjector(rays, tci)
+    ref = bp.apply(y, scale=scale)
+    V = ref.numel()
+    for n_chunks in (1, 2, 4, 8, 16):
+        seen = []
+        out = torch.full_like(ref, float("nan"))
+        got = bp.apply_overlapped(y, scale=scale, out=out, n_chunks=n_chunks,
+                                  reduce_slice=lambda sl: seen.append((sl.data_ptr(), sl.numel())))
+        assert torch.equal(got, ref)
+        # the slices handed to the reducer are the n_chunks equal parts of the grid, in order
+        base = out.data_ptr()
+        bounds = [V * j // n_chunks for j in range(n_chunks + 1)]
+        assert seen == [(base + 8 * a, b - a) for a, b in zip(bounds[:-1], bounds[1:])]

@@ -202,3 +202,54 @@ def test_optical_path_matches_reference_odeint(golden):
         # LSODA runs at rtol = atol ~ 1.5e-8 on a path of ~800 km
         np.testing.assert_allclose(s, g["rays"][idx][3], rtol=0, atol=2e-4)
         assert np.all(s[1:] < straight[idx][3, 1:])      # n < 1: the optical path is shorter
+
+
+def test_config1_matches_reference(golden):
+    """BASELINE.json configs[0] (10 antennas x 20 directions x 1 time, 50x50x30 grid, Ns = 30), produced
+    end to end by the reference's cast_ray (odeint per ray) and forward_equation."""
+    g = golden("config1")
+    o = np.broadcast_to(g["origins"][:, None, None, :], (10, 1, 20, 3))
+    d = np.broadcast_to(g["directions"][None], (10, 1, 20, 3))
+    rays = O.cast_ray(o, d, 1000., 30)
+    np.testing.assert_allclose(rays, g["rays"], rtol=0, atol=1e-9)
+    dtec = O.forward_equation(rays, float(g["K_ne"]), g["xvec"], g["yvec"], g["zvec"], g["m"], 0)
+    np.testing.assert_allclose(dtec, g["dtec"], rtol=0, atol=1e-12 * np.abs(g["dtec"]).max() + 1e-13)
+
+
+def test_synthetic_generators_match_reference(golden):
+    """The benchmark's input recipes (torch versions in the package) against the reference's generators."""
+    from ionotomo_b200.ionosphere import synthetic as S
+    g = golden("synthetic")
+    dm = S.matern52_field(g["xvec"], g["yvec"], g["zvec"], np.log(2.), 20., 1234).numpy()
+    np.testing.assert_allclose(dm, g["dm"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(S.chapman_profile(g["h"], 45.), g["chap45"], rtol=1e-13)
+    np.testing.assert_allclose(S.chapman_profile(g["h"], 80., thin_f=True), g["chap80"], rtol=1e-13)
+    ants = S.lofar_stations_enu_km()
+    assert ants.shape == (62, 3) and abs(ants.mean(0)).max() < 1e-6      # ENU about the centroid
+    assert -48 < ants[:, 0].min() < -47 and 9 < ants[:, 0].max() < 10     # extents quoted in SURVEY.md (d)
+    d = S.directions_in_fov(200, 4., 1234)
+    assert np.allclose(np.linalg.norm(d, axis=1), 1.) and np.degrees(np.arccos(d[:, 2])).max() <= 2.0 + 1e-9
+    dt = S.track_directions(d, 100)
+    assert np.array_equal(dt[50], d) and np.allclose(np.linalg.norm(dt, axis=-1), 1.)
+    # 8 s of Earth rotation = 2 arcmin on the sky at most
+    assert np.degrees(np.arccos(np.clip((dt[51] * dt[50]).sum(-1), -1, 1))).max() <= 8 * 15 / 3600. + 1e-9
+    w = S.make_workload(Na=10, Nt=3, Nd=20, nx=50, ny=50, nz=30, device="cpu")
+    assert tuple(w["origins"].shape) == (10, 3, 20, 3) and w["Ns"] == 30
+    # every ray of the case stays inside the tight box, with the 20-cell padding
+    ends_x = w["origins"][..., 0] + w["directions"][..., 0] / w["directions"][..., 2] * (1000. - w["origins"][..., 2])
+    assert float(ends_x.min()) - w["xvec"][0] >= 19.9 * w["dx_km"] and w["xvec"][-1] - float(ends_x.max()) >= 19.9 * w["dx_km"]
+
+
+def test_frames_helpers():
+    from ionotomo_b200.geometry import frames
+    lon, dec = np.radians(6.87), np.radians(54.)
+    ha = np.radians(np.array([-20., 0., 35.]))
+    R = frames.pointing_rotation(lon, ha, dec)
+    for j in range(3):
+        np.testing.assert_array_equal(R[j], O.pointing_rotation(lon, ha[j], dec))
+        np.testing.assert_allclose(R[j] @ R[j].T, np.eye(3), atol=1e-15)
+    # GMST advances by one sidereal day per 0.99727 solar days
+    g0, g1 = frames.gmst_rad(2457700.5), frames.gmst_rad(2457700.5 + 0.9972695663)
+    assert abs(((g1 - g0 + np.pi) % (2 * np.pi)) - np.pi) < 1e-6
+    d = frames.icrs_to_itrs_simple(np.array([1.0, 2.0]), np.array([0.3, -0.2]), np.array([2457700.5, 2457700.6]))
+    assert d.shape == (2, 2, 3) and np.allclose(np.linalg.norm(d, axis=-1), 1.)
