@@ -305,7 +305,13 @@ def main():
     # outside the timed steps, and report its build time and size.
     torch.cuda.synchronize()
     t_b = time.time()
-    bp = None if args.adjoint == "scatter" else BackProjector(rays, m_tci)
+    bp, bp_note = None, None
+    if args.adjoint != "scatter":
+        try:
+            bp = BackProjector(rays, m_tci)
+        except _lib.IonoError as exc:       # e.g. not enough free HBM for the assembly: stay on the GPU, use atomics
+            bp_note = "binned adjoint unavailable (%s); scatter adjoint used" % str(exc)[:200]
+            args.adjoint = "scatter"
     torch.cuda.synchronize()
     bp_build_s = time.time() - t_b
 
@@ -473,6 +479,8 @@ def main():
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "misfit": float(S),
     }
+    if bp_note:
+        line["note"] = bp_note
     print(json.dumps(line), flush=True)
     if sampler:
         sampler.stop()
