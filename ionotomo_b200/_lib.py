@@ -57,9 +57,12 @@ SIGNATURES = {
 
 # kernels launched per C call (for bench.py's ``gpu_launches``; memsets are not counted)
 KERNEL_LAUNCHES = {
-    "iono_ne_from_m_f64": 1, "iono_mul_f64": 1, "iono_cast_rays_straight_f64": 1, "iono_cast_rays_frames_f64": 1, "iono_ne_to_refractive_index_f64": 1, "iono_optical_path_f64": 1, "iono_tci_interp_f64": 1,
-    "iono_tec_forward_f64": 1, "iono_dtec_f64": 1, "iono_adjoint_coef_f64": 1, "iono_tec_adjoint_f64": 1,
-    "iono_misfit_f64": 2, "iono_convolve3d_nearest_f64": 1, "iono_phase_integrals_f64": 1, "iono_chord_adjoint_f64": 1, "iono_phase_assemble_f64": 1, "iono_backprojector_apply_f64": 4, "iono_backprojector_apply_chunks_f64": 3,
+    "iono_ne_from_m_f64": 1, "iono_mul_f64": 1, "iono_cast_rays_straight_f64": 1,
+    "iono_cast_rays_frames_f64": 1, "iono_ne_to_refractive_index_f64": 1, "iono_optical_path_f64": 1,
+    "iono_tci_interp_f64": 1, "iono_tec_forward_f64": 1, "iono_dtec_f64": 1, "iono_adjoint_coef_f64": 1,
+    "iono_tec_adjoint_f64": 1, "iono_misfit_f64": 2, "iono_convolve3d_nearest_f64": 1,
+    "iono_phase_integrals_f64": 1, "iono_phase_assemble_f64": 1, "iono_chord_adjoint_f64": 1,
+    "iono_backprojector_apply_f64": 4, "iono_backprojector_apply_chunks_f64": 3,
 }
 launch_count = 0
 

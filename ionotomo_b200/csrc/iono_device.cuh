@@ -148,11 +148,6 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ uint64_t policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
 // bytes must be a multiple of 16; src and dst 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
                                          uint64_t *bar, uint64_t policy) {
@@ -163,12 +158,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
-// grid gather: read-only path, keep in L1, prefer to keep in L2
-__device__ __forceinline__ double ld_grid(const double *p, uint64_t policy) {
-    double v;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
-    return v;
-}
 // streaming read (ray data without the bulk path): do not allocate in L1, evict first from L2
 __device__ __forceinline__ double ld_stream(const double *p, uint64_t policy) {
     double v;

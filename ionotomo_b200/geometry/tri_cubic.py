@@ -33,7 +33,7 @@ class _GridHandle(object):
         self.device = torch.cuda.current_device()
         h = ctypes.c_void_p()
         _lib.call("iono_grid_create", self.xvec.ctypes.data, self.yvec.ctypes.data, self.zvec.ctypes.data,
-                                        self.xvec.size, self.yvec.size, self.zvec.size, ctypes.byref(h))
+                  self.xvec.size, self.yvec.size, self.zvec.size, ctypes.byref(h))
         self.handle = h
         self.uniform = bool(lib.iono_grid_is_uniform(h))
 
@@ -150,8 +150,8 @@ class TriCubic(object):
         oob = torch.zeros(1, dtype=torch.int64, device=xd.device)
         Md = self.device_M()
         _lib.call("iono_tci_interp_f64", self.grid().handle, _lib.ptr(Md), _lib.ptr(xd), _lib.ptr(yd),
-                                           _lib.ptr(zd), xd.numel(), int(extrapolate), _lib.ptr(out),
-                                           ctypes.c_void_p(oob.data_ptr()), _lib.stream_ptr())
+                  _lib.ptr(zd), xd.numel(), int(extrapolate), _lib.ptr(out),
+                  ctypes.c_void_p(oob.data_ptr()), _lib.stream_ptr())
         if not extrapolate and int(oob.item()) != 0:
             # scipy RegularGridInterpolator(bounds_error=True) behaviour (tri_cubic.py:22)
             raise ValueError("One of the requested xi is out of bounds (%d points)" % int(oob.item()))

@@ -17,7 +17,7 @@ def _ne_from_m(m_dev, K_ne):
     lib = _lib.load()
     ne = torch.empty_like(m_dev)
     _lib.call("iono_ne_from_m_f64", _lib.ptr(m_dev), m_dev.numel(), float(K_ne) / TECU, _lib.ptr(ne),
-                                      _lib.stream_ptr())
+              _lib.stream_ptr())
     return ne
 
 
@@ -31,8 +31,8 @@ def tec_from_ne(rays_dev, grid, ne_dev, order="time", check_bounds=True):
     tec = torch.empty((Na, Nt, Nd), dtype=torch.float64, device=rays_dev.device)
     oob = torch.zeros(1, dtype=torch.int64, device=rays_dev.device)
     _lib.call("iono_tec_forward_f64", grid.handle, _lib.ptr(ne_dev), _lib.ptr(rays_dev), Na, Nt, Nd, Ns,
-                                        _lib.ORDERS[order], _lib.ptr(tec), ctypes.c_void_p(oob.data_ptr()),
-                                        _lib.stream_ptr())
+              _lib.ORDERS[order], _lib.ptr(tec), ctypes.c_void_p(oob.data_ptr()),
+              _lib.stream_ptr())
     if check_bounds and int(oob.item()) != 0:
         raise ValueError("One of the requested xi is out of bounds (%d ray samples outside the grid)"
                          % int(oob.item()))

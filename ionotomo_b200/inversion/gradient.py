@@ -26,7 +26,7 @@ def adjoint_coefficients(g, dobs, CdCt, i0):
     Na, Nt, Nd = g.shape
     coef = torch.empty_like(g)
     _lib.call("iono_adjoint_coef_f64", _lib.ptr(g), _lib.ptr(dobs), _lib.ptr(CdCt), Na, Nt, Nd, int(i0),
-                                         _lib.ptr(coef), _lib.stream_ptr())
+              _lib.ptr(coef), _lib.stream_ptr())
     return coef
 
 
@@ -38,8 +38,8 @@ def backproject(rays_dev, grid, coef, shape, order="time", check_bounds=True, ou
     acc = out if out is not None else torch.empty(shape, dtype=torch.float64, device=rays_dev.device)
     oob = torch.zeros(1, dtype=torch.int64, device=rays_dev.device)
     _lib.call("iono_tec_adjoint_f64", grid.handle, _lib.ptr(rays_dev), Na, Nt, Nd, Ns, _lib.ptr(coef),
-                                        _lib.ORDERS[order], 1, _lib.ptr(acc), ctypes.c_void_p(oob.data_ptr()),
-                                        _lib.stream_ptr())
+              _lib.ORDERS[order], 1, _lib.ptr(acc), ctypes.c_void_p(oob.data_ptr()),
+              _lib.stream_ptr())
     if check_bounds and int(oob.item()) != 0:
         raise ValueError("One of the requested xi is out of bounds (%d ray samples outside the grid)"
                          % int(oob.item()))
@@ -201,5 +201,5 @@ def misfit(g, dobs, CdCt):
     scratch = torch.empty(int(lib.iono_misfit_scratch_elems()), dtype=torch.float64, device=g_d.device)
     out = torch.empty(1, dtype=torch.float64, device=g_d.device)
     _lib.call("iono_misfit_f64", _lib.ptr(g_d), _lib.ptr(dobs_d), _lib.ptr(C_d), g_d.numel(),
-                                   _lib.ptr(scratch), _lib.ptr(out), _lib.stream_ptr())
+              _lib.ptr(scratch), _lib.ptr(out), _lib.stream_ptr())
     return out[0]
