@@ -373,9 +373,13 @@ static int launch_sweep(SweepParams p, iono_grid_t grid, cudaStream_t st) {
     SweepConfig cfg = sweep_config(MODE, p.Ns);
     p.stages = cfg.stages;
     const size_t stage_bytes = cfg.chunk == 64 ? StageLayout<64>::BYTES : StageLayout<128>::BYTES;
-    size_t smem = (((size_t)(grid->nx + grid->ny + grid->nz) * sizeof(double2)) + 127) / 128 * 128;
-    smem += (((size_t)cfg.warps * cfg.stages * sizeof(uint64_t)) + 127) / 128 * 128;
-    smem += (size_t)cfg.warps * cfg.stages * stage_bytes;
+    const size_t table_bytes = (((size_t)(grid->nx + grid->ny + grid->nz) * sizeof(double2)) + 127) / 128 * 128;
+    auto smem_for = [&](int warps) {
+        return table_bytes + (((size_t)warps * cfg.stages * sizeof(uint64_t)) + 127) / 128 * 128 +
+               (size_t)warps * cfg.stages * stage_bytes;
+    };
+    while (cfg.warps > 4 && smem_for(cfg.warps) > 227 * 1024) cfg.warps -= 4;   // very large axis tables: fewer warps
+    const size_t smem = smem_for(cfg.warps);
     if (smem > 227 * 1024) return fail(IONO_EBADARG, "ray sweep: shared-memory configuration exceeds 227 KB");
     // TMA bulk copies need 16-byte aligned rows: even Ns and a 16-byte aligned base
     const bool bulk = (p.Ns % 2 == 0) && (((uintptr_t)p.rays & 15) == 0) && !getenv("IONO_SWEEP_NO_BULK");
