@@ -130,3 +130,62 @@ def test_apply_overlapped_host_logic_with_fake_library(monkeypatch):
         bounds = [V * j // n_chunks for j in range(n_chunks + 1)]
         assert seen == [(8 * a, b - a) for a, b in zip(bounds[:-1], bounds[1:])]
         assert Handle.waited == n_chunks
+
+
+def _overlap_worker(rank, world, port, out):
+    """Two ranks with DIFFERENT chunk-progress tables run apply_overlapped with a real asynchronous
+    all_reduce (gloo): the collectives must match in order and size, or this dead-locks."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ionotomo_b200 import _lib, sharding
+    from ionotomo_b200.inversion import gradient as G
+    shape = (8, 7, 9)
+    V = shape[0] * shape[1] * shape[2]
+    rng = np.random.RandomState(100 + rank)
+    cuts = np.sort(rng.randint(0, V + 1, size=15))
+    chunk_vox = [0] + [int(c) for c in cuts] + [V]          # this rank's own voxel boundaries per sixteenth
+
+    class FakeLib(object):
+        def iono_backprojector_chunk_voxels(self, handle, c):
+            return chunk_vox[c]
+
+    def fake_call(name, handle, coef, scale, acc, c0, c1, stream):
+        assert name == "iono_backprojector_apply_chunks_f64"
+        flat = acc.reshape(-1)
+        if c0 == 0:
+            flat.zero_()
+        flat[chunk_vox[c0]:chunk_vox[c1]] = float(rank + 1)      # "final" values of this rank's finished voxels
+
+    _lib.load = lambda: FakeLib()
+    _lib.to_device = lambda a, device=None: a
+    _lib.ptr = lambda t: t
+    _lib.stream_ptr = lambda: None
+    _lib.call = fake_call
+    bp = object.__new__(G.BackProjector)
+    bp.handle, bp.shape = None, shape
+    ok = True
+    for n_chunks in (1, 2, 4, 8, 16):
+        acc = torch.full(shape, -1.0, dtype=torch.float64)
+        got = bp.apply_overlapped(torch.zeros(1, dtype=torch.float64), out=acc, n_chunks=n_chunks,
+                                  reduce_slice=sharding.allreduce_sum_async)
+        ok = ok and bool(torch.all(got == float(sum(range(1, world + 1)))))
+    if rank == 0:
+        out.put(ok)
+    dist.destroy_process_group()
+
+
+def test_overlapped_apply_collectives_match_across_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29700 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        if p.is_alive():
+            p.terminate()
+            raise AssertionError("overlapped apply dead-locked")
+        assert p.exitcode == 0
+    assert out.get(timeout=5) is True
