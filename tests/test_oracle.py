@@ -79,6 +79,22 @@ def test_simps_even_is_avg_rule():
     assert abs(O.simps_avg(y, x) - scipy.integrate.simpson(y, x=x)) > 1e-8
 
 
+def test_simps_even_known_answers_from_old_scipy_docstring():
+    """Published known answers for an EVEN number of samples: the docstring example of
+    ``scipy.integrate.simps`` (SciPy <= 1.10) -- ``x = np.arange(0, 10); y = x**3`` gives
+    ``simps(y, x) == 1642.5`` with the default ``even='avg'`` and ``1644.5`` with ``even='first'``
+    (exact integral 1640.25); ``simps(x, x) == 40.5``.  Modern ``simpson`` returns 1640.5 instead."""
+    x = np.arange(0, 10.)
+    y = np.power(x, 3)
+    assert O.simps_avg(x, x) == 40.5
+    assert O.simps_avg(y, x) == 1642.5
+    first = O._basic_simps(y, 0, 10 - 3, x) + 0.5 * (x[-1] - x[-2]) * (y[-1] + y[-2])
+    assert first == 1644.5
+    assert scipy.integrate.simpson(y, x=x) == 1640.5          # the rule the reference did NOT run
+    w = O.simps_weights_fast(x)
+    np.testing.assert_allclose((w * y).sum(), 1642.5, rtol=1e-14)
+
+
 def test_simps_weights():
     rng = np.random.RandomState(3)
     for N in (3, 4, 5, 9, 10, 31, 64):
