@@ -20,8 +20,10 @@ Parity pinning (see ``tests/golden/make_golden.py`` and ``tests/test_oracle.py``
 the oracle is checked against outputs of the *reference's own modules* executed
 in the build container (with stub modules for the absent astropy/h5py/dask and a
 NumPy shim of the TF1 ops used by ``tomography/integrate.py``), committed as
-``tests/golden/*.npz``, and against the installed SciPy where the algorithm is
-still shipped (RGI; ``simpson`` for odd N).
+``tests/golden/*.npz``, against the installed SciPy where the algorithm is still
+shipped (RGI; ``simpson`` for odd N; ``ndimage.convolve``), and -- for the even-N
+``'avg'`` rule, which no installed library implements any more -- against the known
+answers published in old SciPy's own ``simps`` docstring (1642.5 / 1644.5 / 40.5).
 """
 from __future__ import annotations
 
