@@ -131,6 +131,17 @@ int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, i
 int iono_chord_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
                            const double *dd, int zero_first, double *acc, void *stream);
 
+/* ---- Gaussian-covariance adjoint ("adjoint B", Cm.G^t.dd) -------------------------
+ * acc[v] (+)= sum_ray dd[ray] * simps(sigma_m^2 exp(-|x_v-r(s)|^2/(2 L_m^2)) ne_rays[ray,s], s)
+ * over the samples idx_min..idx_max of the ray whose +-Nkernel-cell boxes hold voxel v; the last
+ * node of every axis receives nothing (inner loops of inversion/gradient_and_adjoint.py:12-103,
+ * `do_adjoint`).  ne_rays: (Na,Nt,Nd,Ns) = K_ne exp(interp(m))/1e13 at the ray samples (:37), made
+ * by the caller with iono_tci_interp_f64 + iono_ne_from_m_f64.  L_m = Nkernel*size_cell (:14).
+ * dd: (Na,Nt,Nd) weighted residuals.  Compatibility kernel, fp64 atomics. */
+int iono_gaussian_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
+                              const double *ne_rays, const double *dd, double sigma_m, double L_m,
+                              int Nkernel, int zero_first, double *acc, void *stream);
+
 /* ---- phase-domain ray integrals (reference generation B) -------------------------
  * out[ray,f] = simps(g_f(ne(x_s)), s), n_f = sqrt(1 - ne/(1.2404e-2 nu_f^2)):
  *   dmu == NULL : g_f = 1 - n_f                (forward_equation, iterative_newton.py:108-119)

@@ -564,6 +564,74 @@ def gradient_chord(rays, g, dobs, i0, K_ne, xvec, yvec, zvec, m, CdCt,
 
 
 # --------------------------------------------------------------------------
+# adjoint B (row A9): Cm.G^t.dd with a Gaussian model covariance,
+# inversion/gradient_and_adjoint.py:12-167
+# --------------------------------------------------------------------------
+def gaussian_adjoint_ray(ray, ne_ray, xvec, yvec, zvec, sigma_m, L_m, Nkernel):
+    """Contribution of ONE ray with unit residual, as a sparse dict
+    ``{(xi,yi,zi): value}`` (gradient_and_adjoint.py:32-53 builds the per-voxel sample
+    range, :67-93 integrates it).
+
+    A voxel belongs to the box of sample ``idx`` when it lies in the slices
+    ``max(0,c-Nk) : min(n-1, c+Nk+1)`` around the sample's ``bisection`` cell ``c`` on
+    every axis (:42-44; the upper bound ``n-1`` is exclusive, so the last node of an axis
+    never receives anything).  ``idx_min``/``idx_max`` are the first and last sample whose
+    box holds the voxel; the integrand ``sigma_m^2 exp(-r^2/(2 L_m^2)) ne(s)`` is
+    integrated with ``simps`` over ALL samples idx_min..idx_max (:80-92)."""
+    x, y, z, s = ray
+    Ns = x.shape[0]
+    nx, ny, nz = len(xvec), len(yvec), len(zvec)
+    idx_min = np.full((nx, ny, nz), Ns, dtype=np.int64)
+    idx_max = np.full((nx, ny, nz), -1, dtype=np.int64)
+    for idx in range(Ns):
+        xi, yi, zi = bisection(xvec, x[idx]), bisection(yvec, y[idx]), bisection(zvec, z[idx])
+        box = (slice(max(0, xi - Nkernel), min(nx - 1, xi + Nkernel + 1)),
+               slice(max(0, yi - Nkernel), min(ny - 1, yi + Nkernel + 1)),
+               slice(max(0, zi - Nkernel), min(nz - 1, zi + Nkernel + 1)))
+        idx_max[box] = np.maximum(idx_max[box], idx)
+        idx_min[box] = np.minimum(idx_min[box], idx)
+    out = {}
+    for xi, yi, zi in zip(*np.nonzero(idx_max >= 0)):
+        seg = slice(idx_min[xi, yi, zi], idx_max[xi, yi, zi] + 1)
+        Cm = (xvec[xi] - x[seg]) ** 2 + (yvec[yi] - y[seg]) ** 2 + (zvec[zi] - z[seg]) ** 2
+        Cm = np.exp(Cm / (-2. * L_m ** 2)) * sigma_m ** 2 * ne_ray[seg]
+        out[(int(xi), int(yi), int(zi))] = float(simps_avg(Cm, s[seg]))
+    return out
+
+
+def gaussian_adjoint(rays, dd, i0, K_ne, xvec, yvec, zvec, m, sigma_m, Nkernel, size_cell,
+                     bug_compat=False):
+    """``sum_d do_adjoint(rays[:,:,d], dd[:,:,d], ...)`` (gradient_and_adjoint.py:12-103,
+    162-163).  ``ne`` along the ray is ``K_ne*exp(interp(m))/1e13`` (:37: the LOG model is
+    interpolated, then exponentiated -- unlike the forward, which interpolates ne).
+    ``bug_compat`` applies ``grad -= grad[i0,:,:]`` (:102: antenna index used on grid-x)."""
+    L_m = Nkernel * size_cell
+    Na, Nt, Nd = rays.shape[:3]
+    grad = np.zeros((len(xvec), len(yvec), len(zvec)))
+    for i in range(Na):
+        for j in range(Nt):
+            for k in range(Nd):
+                ray = rays[i, j, k]
+                ne_ray = K_ne * np.exp(rgi_linear(xvec, yvec, zvec, m, ray[0], ray[1], ray[2])) / 1e13
+                for v, c in gaussian_adjoint_ray(ray, ne_ray, xvec, yvec, zvec, sigma_m, L_m,
+                                                 Nkernel).items():
+                    grad[v] += c * dd[i, j, k]
+    if bug_compat:
+        grad = grad - grad[i0, :, :]
+    return grad
+
+
+def compute_adjoint(rays, g, dobs, i0, K_ne, xvec, yvec, zvec, m, m_prior, CdCt, sigma_m,
+                    Nkernel, size_cell, bug_compat=True):
+    """``compute_adjoint`` (gradient_and_adjoint.py:137-167):
+    ``Cm.G^t.Cd^-1.(g - dobs) + (m - m_prior)``."""
+    dd = weighted_residual(g, dobs, CdCt)
+    grad = gaussian_adjoint(rays, dd, i0, K_ne, xvec, yvec, zvec, m, sigma_m, Nkernel, size_cell,
+                            bug_compat=bug_compat)
+    return grad + m - m_prior
+
+
+# --------------------------------------------------------------------------
 # line search: inversion/line_search.py
 # --------------------------------------------------------------------------
 def vertex(x1, x2, x3, y1, y2, y3):

@@ -14,7 +14,8 @@ SciPy >= 1.14), so this script
   (``geometry/tri_cubic.py``, ``inversion/fermat.py``, ``geometry/calc_rays.py``,
   ``inversion/forward_equation.py``, ``inversion/iterative_newton.py``,
   ``geometry/ray_dirac.py``, ``geometry/slab_method.py``, ``inversion/gradient.py``,
-  ``inversion/line_search.py``, ``ionosphere/simulation.py``, ``ionosphere/iri.py``)
+  ``inversion/line_search.py``, ``inversion/gradient_and_adjoint.py``,
+  ``ionosphere/simulation.py``, ``ionosphere/iri.py``)
   are executed UNMODIFIED from where they lie;
 * satisfies their imports of absent third-party packages with inert stub
   modules (none of the stubs is reached by the functions called below);
@@ -130,8 +131,46 @@ def small_problem(seed, Na, Nt, Nd, Ns, nx, ny, nz):
     return xvec, yvec, zvec, ne, origins, directions, rng
 
 
+def golden_gauss():
+    """9. adjoint B (gradient_and_adjoint.py:12-167): Gaussian model covariance along the rays."""
+    from ionotomo.geometry.tri_cubic import TriCubic
+    from ionotomo.inversion.fermat import Fermat
+    from ionotomo.geometry.calc_rays import cast_ray
+    from ionotomo.inversion.forward_equation import forward_equation
+    from ionotomo.inversion.gradient_and_adjoint import do_adjoint, compute_adjoint
+    Ns = 14
+    xvec, yvec, zvec, ne, origins, directions, rng = small_problem(21, 3, 2, 2, Ns, 10, 9, 12)
+    origins[0, ..., 0] = 38.          # boxes clipped at the upper x edge
+    origins[2, ..., 0] = -38.         # and at the lower one
+    origins[2, ..., 1] = 43.          # upper y edge
+    ne_tci = TriCubic(xvec, yvec, zvec, ne)
+    fermat = Fermat(ne_tci=ne_tci, frequency=120e6, type='z', straight_line_approx=True)
+    rays = cast_ray((origins, directions), fermat, 1000., Ns)
+    K_ne = np.median(ne)
+    m_tci = ne_tci.copy()
+    m_tci.M = np.log(m_tci.M / K_ne)
+    i0 = 1
+    g = forward_equation(rays, K_ne, m_tci, i0)
+    dobs = g + 0.05 * rng.normal(size=g.shape)
+    CdCt = (0.01 + 0.01 * rng.uniform(size=g.shape)) ** 2
+    m_prior = m_tci.M + 0.1 * rng.normal(size=m_tci.M.shape)
+    sigma_m, Nkernel, size_cell = 0.7, 2, 20.
+    dd = (g - dobs) / (CdCt + 1e-15)
+    slice0 = do_adjoint(rays[:, :, 0], dd[:, :, 0], K_ne, m_tci, sigma_m, Nkernel, size_cell, i0)
+    adj = compute_adjoint(rays, g.copy(), dobs, i0, K_ne, m_tci, m_prior, CdCt, sigma_m, Nkernel, size_cell)
+    # a second kernel size whose boxes reach both ends of every axis
+    adj_wide = compute_adjoint(rays[:2, :1], g[:2, :1].copy(), dobs[:2, :1], 0, K_ne, m_tci, m_prior,
+                               CdCt[:2, :1], 1.3, 5, 7.)
+    np.savez(os.path.join(OUT, "adjoint_gauss.npz"), xvec=xvec, yvec=yvec, zvec=zvec, m=m_tci.M, K_ne=K_ne,
+             rays=rays, g=g, dobs=dobs, CdCt=CdCt, m_prior=m_prior, i0=i0, sigma_m=sigma_m, Nkernel=Nkernel,
+             size_cell=size_cell, slice0=slice0, adj=adj, adj_wide=adj_wide)
+
+
 def main():
     install()
+    if "--only-gauss" in sys.argv:
+        golden_gauss()
+        return
     from ionotomo.geometry.tri_cubic import TriCubic, bisection
     from ionotomo.inversion.fermat import Fermat
     from ionotomo.geometry.calc_rays import cast_ray
@@ -288,6 +327,7 @@ def main():
     chap80 = a_priori_model_(h, 80., thin_f=True)
     np.savez(os.path.join(OUT, "synthetic.npz"), xvec=xvec, yvec=yvec, zvec=zvec, dm=dm, h=h,
              chap45=chap45, chap80=chap80)
+    golden_gauss()
     print("golden vectors written to", OUT)
 
 

@@ -4,6 +4,8 @@ oracle and the reference-generated golden vectors.  Needs a B200: ``pytest -m gp
 Tolerances: the north star asks for rel 1e-6 in fp64; the kernels differ from the oracle
 only by floating-point reassociation, so the tests assert 1e-11 or tighter (bit-exact where
 the arithmetic order is reproduced: ray generation, point-wise interpolation)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -579,3 +581,49 @@ def test_binned_backprojector_chunked_apply(ib, seg, monkeypatch):
         base = out.data_ptr()
         bounds = [V * j // n_chunks for j in range(n_chunks + 1)]
         assert seen == [(base + 8 * a, b - a) for a, b in zip(bounds[:-1], bounds[1:])]
+
+
+# ---------------------------------------------------------------- kernels that have not run on a GPU yet
+# Written after round 1's GPU budget was spent: compiled for sm_100a, index logic checked on the CPU by
+# tests/test_kernel_models.py, but never launched.  Opt-in until `tools/validate_unrun.sh` has passed once.
+unrun = pytest.mark.skipif(os.environ.get("IONO_TEST_UNRUN") != "1",
+                           reason="kernel not yet validated on a GPU; set IONO_TEST_UNRUN=1")
+
+
+@unrun
+def test_gaussian_adjoint_golden(ib, golden):
+    """Adjoint B against the reference's own compute_adjoint (gradient_and_adjoint.py:137-167)."""
+    from ionotomo_b200.inversion.gradient_and_adjoint import compute_adjoint
+    g = golden("adjoint_gauss")
+    tci = ib.TriCubic(g["xvec"], g["yvec"], g["zvec"], g["m"])
+    K, sig, Nk, cell = float(g["K_ne"]), float(g["sigma_m"]), int(g["Nkernel"]), float(g["size_cell"])
+    adj = compute_adjoint(g["rays"], g["g"], g["dobs"], int(g["i0"]), K, tci, g["m_prior"], g["CdCt"], sig, Nk,
+                          cell, bug_compat=True)
+    np.testing.assert_allclose(adj, g["adj"], rtol=0, atol=1e-10 * np.abs(g["adj"]).max())
+    wide = compute_adjoint(g["rays"][:2, :1], g["g"][:2, :1], g["dobs"][:2, :1], 0, K, tci, g["m_prior"],
+                           g["CdCt"][:2, :1], 1.3, 5, 7., bug_compat=True)
+    np.testing.assert_allclose(wide, g["adj_wide"], rtol=0, atol=1e-10 * np.abs(g["adj_wide"]).max())
+    with pytest.raises(ValueError):                       # m_tci.interp at gradient_and_adjoint.py:37
+        bad = g["rays"].copy()
+        bad[0, 0, 0, 0, 3] = 1e4
+        compute_adjoint(bad, g["g"], g["dobs"], 0, K, tci, g["m_prior"], g["CdCt"], sig, Nk, cell)
+
+
+@unrun
+@pytest.mark.parametrize("Ns,Nk", [(9, 1), (40, 2), (33, 3)])
+def test_gaussian_adjoint_vs_oracle(ib, Ns, Nk):
+    """Seeded problems incl. several samples per cell (long segments) and a non-uniform z axis."""
+    from ionotomo_b200.inversion.gradient_and_adjoint import compute_adjoint
+    P = small_problem(100 + Ns, 3, 2, 3, Ns, 9, 8, 11)
+    zvec = P["zvec"].copy()
+    zvec[1:-1] += 0.2 * (zvec[1] - zvec[0]) * P["rng"].uniform(-1, 1, zvec.size - 2)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], Ns)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], zvec, P["m"])
+    g = P["rng"].normal(size=rays.shape[:3])
+    dobs = P["rng"].normal(size=rays.shape[:3])
+    CdCt = P["rng"].uniform(0.5, 2., size=rays.shape[:3])
+    m_prior = P["m"] + 0.1
+    ref = O.compute_adjoint(rays, g, dobs, 1, P["K_ne"], P["xvec"], P["yvec"], zvec, P["m"], m_prior, CdCt, 0.8, Nk,
+                            15., bug_compat=False)
+    got = compute_adjoint(rays, g, dobs, 1, P["K_ne"], tci, m_prior, CdCt, 0.8, Nk, 15.)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-10 * np.abs(ref).max())

@@ -1,0 +1,140 @@
+"""Host models of device-side index logic, checked against the oracle on the CPU.
+
+These are line-by-line Python restatements of the enumeration a CUDA kernel performs (which
+thread owns which (ray, voxel) pair, which samples it integrates over, which quadrature weight each
+sample gets).  They are test infrastructure: they let the no-GPU suite catch a wrong ownership rule
+or weight formula before the kernel ever runs; the kernel itself is compared with the oracle in
+tests/test_gpu_parity.py."""
+import numpy as np
+
+from oracle import ionotomo_oracle as O
+
+
+def simpson_weight_model(i, N, s):
+    """``simpson_weight`` of csrc/iono_device.cuh with its neighbour clamping, exact division."""
+    c = lambda k: s[min(max(k, 0), N - 1)]
+    sm2, sm1, s0, sp1, sp2 = c(i - 2), c(i - 1), c(i), c(i + 1), c(i + 2)
+    n_odd = N % 2 == 1
+    hm, hp = s0 - sm1, sp1 - s0
+    if i < 1:
+        hm = hp
+    if i > N - 2:
+        hp = hm
+    h0 = sm1 - sm2 if i >= 2 else hm
+    h3 = sp2 - sp1 if i <= N - 3 else hp
+    par = i & 1
+    trap = 0.0
+    if n_odd:
+        cm = 1.0 if par else 0.0
+        cr = 0.0 if (par or i < 2) else 1.0
+        cl = 0.0 if (par or i > N - 3) else 1.0
+    else:
+        cm = 0.5 if ((i <= N - 3) if par else (i >= 2)) else 0.0
+        cr = 0.5 if i >= 2 + par else 0.0
+        cl = 0.5 if i <= N - 4 + par else 0.0
+        if i < 2 or i > N - 3:
+            trap = 0.25 * (hp * ((i == 0) + (i == N - 2)) + hm * ((i == 1) + (i == N - 1)))
+    A = hm + hp
+    num = cm * A * A * A + cr * (h0 + hm) * (2.0 * hm - h0) * hp + cl * (hp + h3) * (2.0 * hp - h3) * hm
+    return num / (6.0 * hm * hp) + trap
+
+
+def test_simpson_weight_model_small_segments():
+    """Every segment length the Gaussian adjoint can meet, 2 upwards, non-uniform abscissae."""
+    rng = np.random.RandomState(0)
+    for N in range(2, 12):
+        s = np.cumsum(rng.uniform(0.5, 1.5, N))
+        w = np.array([simpson_weight_model(i, N, s) for i in range(N)])
+        np.testing.assert_allclose(w, O.simps_weights(s), rtol=1e-12, atol=1e-14)
+        y = rng.normal(size=N)
+        np.testing.assert_allclose(w @ y, O.simps_avg(y, s), rtol=1e-11, atol=1e-13)
+
+
+def gaussian_adjoint_kernel_model(ray, ne_ray, xvec, yvec, zvec, sigma_m, L_m, Nk):
+    """gaussian_adjoint_kernel (csrc/iono_gaussian.cuh), one ray, lanes run one after another."""
+    x, y, z, s = ray
+    Ns = len(x)
+    nx, ny, nz = len(xvec), len(yvec), len(zvec)
+    cx = [O.bisection(xvec, v) for v in x]
+    cy = [O.bisection(yvec, v) for v in y]
+    cz = [O.bisection(zvec, v) for v in z]
+    mono = all(cz[q] >= cz[q - 1] for q in range(1, Ns))
+
+    def member(q, xi, yi, zi):
+        return abs(cx[q] - xi) <= Nk and abs(cy[q] - yi) <= Nk and abs(cz[q] - zi) <= Nk
+
+    out = {}
+    for zi in range(0, nz - 1):
+        s_lo, s_hi = 0, Ns
+        if mono:
+            lo, hi = 0, Ns
+            while lo < hi:
+                m = (lo + hi) >> 1
+                if cz[m] < zi - Nk:
+                    lo = m + 1
+                else:
+                    hi = m
+            s_lo = lo
+            hi = Ns
+            while lo < hi:
+                m = (lo + hi) >> 1
+                if cz[m] <= zi + Nk:
+                    lo = m + 1
+                else:
+                    hi = m
+            s_hi = lo
+        for q0 in range(s_lo, s_hi):
+            if abs(cz[q0] - zi) > Nk:
+                continue
+            for xi in range(max(0, cx[q0] - Nk), min(nx - 2, cx[q0] + Nk) + 1):
+                for yi in range(max(0, cy[q0] - Nk), min(ny - 2, cy[q0] + Nk) + 1):
+                    if any(member(q, xi, yi, zi) for q in range(s_lo, q0)):
+                        continue
+                    b = q0
+                    for q in range(q0 + 1, s_hi):
+                        if member(q, xi, yi, zi):
+                            b = q
+                    n = b - q0 + 1
+                    if n < 2:
+                        continue
+                    total = 0.0
+                    for i in range(n):
+                        q = q0 + i
+                        r2 = (xvec[xi] - x[q]) ** 2 + (yvec[yi] - y[q]) ** 2 + (zvec[zi] - z[q]) ** 2
+                        f = np.exp(r2 / (-2.0 * L_m * L_m)) * sigma_m ** 2 * ne_ray[q]
+                        total += simpson_weight_model(i, n, s[q0:b + 1]) * f
+                    assert (xi, yi, zi) not in out          # each (ray, voxel) pair has exactly one owner
+                    out[(xi, yi, zi)] = total
+    return out
+
+
+def _compare(ray, ne_ray, xv, yv, zv, sigma_m, L_m, Nk):
+    ref = O.gaussian_adjoint_ray(ray, ne_ray, xv, yv, zv, sigma_m, L_m, Nk)
+    got = gaussian_adjoint_kernel_model(ray, ne_ray, xv, yv, zv, sigma_m, L_m, Nk)
+    scale = max(abs(v) for v in ref.values())
+    for v, c in ref.items():                                   # the oracle also lists one-sample segments (= 0)
+        assert abs(got.get(v, 0.0) - c) <= 1e-11 * scale, (v, got.get(v), c)
+    assert set(got) <= set(ref)
+    return len(got)
+
+
+def test_gaussian_adjoint_kernel_model_on_reference_rays(golden):
+    g = golden("adjoint_gauss")
+    xv, yv, zv = g["xvec"], g["yvec"], g["zvec"]
+    rng = np.random.RandomState(1)
+    n = 0
+    for (i, j, k), Nk in (((0, 0, 0), 2), ((2, 1, 1), 2), ((1, 0, 1), 1), ((2, 0, 0), 5), ((0, 1, 0), 0)):
+        ray = g["rays"][i, j, k]
+        n += _compare(ray, rng.uniform(0.5, 2., ray.shape[1]), xv, yv, zv, 0.7, 20. * max(Nk, 1), Nk)
+    assert n > 500
+
+
+def test_gaussian_adjoint_kernel_model_non_monotone_ray(golden):
+    """A ray that turns back in z: first/last-sample hull semantics, all samples scanned."""
+    g = golden("adjoint_gauss")
+    xv, yv, zv = g["xvec"], g["yvec"], g["zvec"]
+    t = np.linspace(0., 1., 17)
+    ray = np.stack([-30. + 70. * t, 20. * np.sin(5. * t), 500. + 450. * np.sin(7. * t),
+                    np.cumsum(np.full(17, 60.)) + 3. * np.cos(11. * t)])
+    assert np.any(np.diff(ray[2]) < 0)
+    assert _compare(ray, np.linspace(1., 2., 17), xv, yv, zv, 1.1, 35., 2) > 100

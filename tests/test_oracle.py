@@ -269,3 +269,24 @@ def test_frames_helpers():
     assert abs(((g1 - g0 + np.pi) % (2 * np.pi)) - np.pi) < 1e-6
     d = frames.icrs_to_itrs_simple(np.array([1.0, 2.0]), np.array([0.3, -0.2]), np.array([2457700.5, 2457700.6]))
     assert d.shape == (2, 2, 3) and np.allclose(np.linalg.norm(d, axis=-1), 1.)
+
+
+def test_gaussian_adjoint_matches_reference(golden):
+    """Adjoint B against the reference's own do_adjoint / compute_adjoint (gradient_and_adjoint.py:12-167)."""
+    g = golden("adjoint_gauss")
+    xv, yv, zv, i0 = g["xvec"], g["yvec"], g["zvec"], int(g["i0"])
+    K, sig, Nk, cell = float(g["K_ne"]), float(g["sigma_m"]), int(g["Nkernel"]), float(g["size_cell"])
+    dd = O.weighted_residual(g["g"], g["dobs"], g["CdCt"])
+    s0 = O.gaussian_adjoint(g["rays"][:, :, :1], dd[:, :, :1], i0, K, xv, yv, zv, g["m"], sig, Nk, cell,
+                            bug_compat=True)
+    np.testing.assert_allclose(s0, g["slice0"], rtol=RTOL, atol=RTOL * np.abs(g["slice0"]).max())
+    adj = O.compute_adjoint(g["rays"], g["g"], g["dobs"], i0, K, xv, yv, zv, g["m"], g["m_prior"], g["CdCt"],
+                            sig, Nk, cell)
+    np.testing.assert_allclose(adj, g["adj"], rtol=RTOL, atol=RTOL * np.abs(g["adj"]).max())
+    wide = O.compute_adjoint(g["rays"][:2, :1], g["g"][:2, :1], g["dobs"][:2, :1], 0, K, xv, yv, zv, g["m"],
+                             g["m_prior"], g["CdCt"][:2, :1], 1.3, 5, 7.)
+    np.testing.assert_allclose(wide, g["adj_wide"], rtol=RTOL, atol=RTOL * np.abs(g["adj_wide"]).max())
+    # the exclusive upper slice bound: the last node of every axis receives nothing
+    raw = O.gaussian_adjoint(g["rays"], dd, i0, K, xv, yv, zv, g["m"], sig, Nk, cell)
+    assert np.all(raw[-1] == 0) and np.all(raw[:, -1] == 0) and np.all(raw[:, :, -1] == 0)
+    assert np.abs(raw).max() > 0
