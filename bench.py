@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--overlap", type=int, default=0, choices=[0, 1, 2, 4, 8, 16],
                     help="EXPERIMENTAL: chunks of the binned apply whose allreduce overlaps the next chunk "
                          "(0 = one NCCL allreduce after the apply, the validated path)")
+    ap.add_argument("--forward", default="sweep", choices=["sweep", "prepared"],
+                    help="sweep: stateless ray sweep; prepared: per-geometry forward projector (36 B/sample "
+                         "records assembled once, outside the timed steps, like the binned adjoint)")
     ap.add_argument("--adjoint", default="binned", choices=["binned", "scatter"],
                     help="binned: pre-assembled voxel-binned gather (default); scatter: stateless fp64 atomics")
     return ap.parse_args()
@@ -265,7 +268,7 @@ def main():
     import ionotomo_b200 as ib
     from ionotomo_b200 import _lib, sharding
     from ionotomo_b200.ionosphere.synthetic import make_workload
-    from ionotomo_b200.inversion.forward_equation import _ne_from_m, tec_from_ne
+    from ionotomo_b200.inversion.forward_equation import ForwardProjector, _ne_from_m, tec_from_ne
     from ionotomo_b200.inversion.gradient import BackProjector, adjoint_coefficients, backproject, misfit
     from ionotomo_b200.inversion.host_stream import misfit_and_gradient
 
@@ -314,12 +317,21 @@ def main():
             args.adjoint = "scatter"
     torch.cuda.synchronize()
     bp_build_s = time.time() - t_b
+    fp, fp_build_s = None, None
+    if args.forward == "prepared":
+        t_b = time.time()
+        fp = ForwardProjector(rays, m_tci)
+        torch.cuda.synchronize()
+        fp_build_s = time.time() - t_b
 
     def step(timed):
         ne = _ne_from_m(m_dev, K_ne)
         e0, e1 = ev(), ev()
         e0.record()
-        tec = tec_from_ne(rays, grid, ne, order=args.order, check_bounds=False)
+        if fp is not None:
+            tec = fp.tec(ne)
+        else:
+            tec = tec_from_ne(rays, grid, ne, order=args.order, check_bounds=False)
         e1.record()
         g = torch.empty_like(tec)
         _lib.call("iono_dtec_f64", _lib.ptr(tec), Na, Nt, Nd, i0, _lib.ptr(g), _lib.stream_ptr())
@@ -389,6 +401,20 @@ def main():
             ts.append(a.elapsed_time(b))
         scat_ms = float(np.mean(ts[1:]))
         del tmp
+    # likewise the stateless forward sweep when the prepared projector is the one in the steps
+    sweep_ms = None
+    if fp is not None:
+        ne_s = _ne_from_m(m_dev, K_ne)
+        ts = []
+        for i in range(3):
+            a, b = ev(), ev()
+            a.record()
+            tec_s = tec_from_ne(rays, grid, ne_s, order=args.order, check_bounds=False)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        sweep_ms = float(np.mean(ts[1:]))
+        assert torch.equal(tec_s, fp.tec(ne_s)), "prepared forward differs from the stateless sweep"
     clocks = None
     if sampler:
         clocks = sampler.window(t_wall0, t_wall1)
@@ -436,11 +462,19 @@ def main():
     hbm, peak_src = peaks()
     bytes_fwd = R * (4 * Ns * 8 + 8) + V * 8
     bytes_adj = R * (4 * Ns * 8 + 8) + 2 * V * 8
+    fwd_name = "prepared_forward" if fp is not None else "ray_sweep_forward"
     kernels = {
-        "ray_sweep_forward": {"ms": fwd_ms, "algorithmic_bytes": bytes_fwd,
-                              "achieved_gbs": bytes_fwd / fwd_ms / 1e6, "frac": bytes_fwd / fwd_ms / 1e6 / hbm,
-                              "rays_per_s": R / fwd_ms * 1e3},
+        fwd_name: {"ms": fwd_ms, "algorithmic_bytes": bytes_fwd,
+                   "achieved_gbs": bytes_fwd / fwd_ms / 1e6, "frac": bytes_fwd / fwd_ms / 1e6 / hbm,
+                   "rays_per_s": R / fwd_ms * 1e3},
     }
+    if fp is not None:
+        kernels[fwd_name].update({"build_s_once_per_geometry": fp_build_s, "operator_bytes": fp.nbytes,
+                                  "streamed_gbs": (fp.nbytes + V * 8 + R * 8) / fwd_ms / 1e6})
+        kernels["ray_sweep_forward"] = {"ms": sweep_ms, "algorithmic_bytes": bytes_fwd,
+                                        "achieved_gbs": bytes_fwd / sweep_ms / 1e6,
+                                        "frac": bytes_fwd / sweep_ms / 1e6 / hbm, "rays_per_s": R / sweep_ms * 1e3,
+                                        "in_step": False}
     bytes_cast = R * 4 * Ns * 8
     kernels["cast_rays"] = {"ms": cast_ms, "algorithmic_bytes": bytes_cast, "achieved_gbs": bytes_cast / cast_ms / 1e6,
                             "frac": bytes_cast / cast_ms / 1e6 / hbm, "rays_per_s": R / cast_ms * 1e3,
@@ -457,7 +491,7 @@ def main():
                                                 "achieved_gbs": bytes_adj / scat_ms / 1e6,
                                                 "frac": bytes_adj / scat_ms / 1e6 / hbm,
                                                 "rays_per_s": R / scat_ms * 1e3, "in_step": False}
-    dom = adj_name if adj_ms >= fwd_ms else "ray_sweep_forward"
+    dom = adj_name if adj_ms >= fwd_ms else fwd_name
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -470,7 +504,7 @@ def main():
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload_config(world, nt), dx_km=w["dx_km"], dy_km=w["dy_km"], dz_km=w["dz_km"],
-                       ray_order=args.order, adjoint=args.adjoint,
+                       ray_order=args.order, forward=args.forward, adjoint=args.adjoint,
                        allreduce_overlap_chunks=(args.overlap if world > 1 else 0)),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": hbm,
                      "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src},

@@ -123,6 +123,23 @@ int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, i
                          const double *coef, int order, int zero_first, double *acc,
                          unsigned long long *oob_count, void *stream);
 
+/* ---- prepared forward sweep (forward projector) -------------------------------------
+ * For a ray geometry that is reused across iterations (the reference's drivers call
+ * forward_equation with the same rays every iteration: bfgs_dask.py:207-340,
+ * iterative_newton.py:954-1017): per sample the cell index, the in-cell fractions and the
+ * Simpson weight are computed once (create) and streamed by apply, 36 B per sample, HBM owned
+ * by the handle.  apply writes tec_out[a,t,d] = simps(interp(ne; ray), s), bit-identical to
+ * iono_tec_forward_f64 (same device functions, same summation order).  create counts samples
+ * outside the grid in *oob_count (device) -- the caller raises like the forward does. */
+typedef struct iono_forwardprojector *iono_forwardprojector_t;
+int iono_forwardprojector_create(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
+                                 iono_forwardprojector_t *out, unsigned long long *oob_count,
+                                 void *stream);
+int iono_forwardprojector_apply_f64(iono_forwardprojector_t fp, const double *ne, double *tec_out,
+                                    void *stream);
+long long iono_forwardprojector_bytes(iono_forwardprojector_t fp);
+int iono_forwardprojector_destroy(iono_forwardprojector_t fp);
+
 /* ---- chord-length adjoint (the reference's generation-A gradient) ----------------
  * acc[v] (+)= sum_ray dd[ray] * l(ray,v): l = chord of the line first->last sample through the
  * box centred on node v, for the voxels within +-1 cell of any sample (geometry/ray_dirac.py:5-34,

@@ -8,10 +8,10 @@ underneath, Python holds PyTorch tensors as buffers and calls the C ABI of
 from .geometry.tri_cubic import TriCubic, bisection
 from .geometry.calc_rays import calc_rays, cast_ray
 from .inversion.fermat import Fermat
-from .inversion.forward_equation import forward_equation, forward_equation_dask
+from .inversion.forward_equation import ForwardProjector, forward_equation, forward_equation_dask
 from .inversion.gradient import BackProjector, compute_gradient, compute_gradient_dask, misfit
 from .inversion.line_search import line_search, vertex
 
 __all__ = ["TriCubic", "bisection", "calc_rays", "cast_ray", "Fermat", "forward_equation",
-           "forward_equation_dask", "BackProjector", "compute_gradient", "compute_gradient_dask", "misfit",
+           "forward_equation_dask", "ForwardProjector", "BackProjector", "compute_gradient", "compute_gradient_dask", "misfit",
            "line_search", "vertex"]

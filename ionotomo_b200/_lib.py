@@ -54,6 +54,10 @@ SIGNATURES = {
     "iono_backprojector_nnz": (ctypes.c_longlong, [_vp]),
     "iono_backprojector_bytes": (ctypes.c_longlong, [_vp]),
     "iono_backprojector_destroy": (_i, [_vp]),
+    "iono_forwardprojector_create": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp, _vp]),
+    "iono_forwardprojector_apply_f64": (_i, [_vp, _vp, _vp, _vp]),
+    "iono_forwardprojector_bytes": (ctypes.c_longlong, [_vp]),
+    "iono_forwardprojector_destroy": (_i, [_vp]),
 }
 
 # kernels launched per C call (for bench.py's ``gpu_launches``; memsets are not counted)
@@ -65,6 +69,7 @@ KERNEL_LAUNCHES = {
     "iono_phase_integrals_f64": 1, "iono_phase_assemble_f64": 1, "iono_chord_adjoint_f64": 1,
     "iono_gaussian_adjoint_f64": 1,
     "iono_backprojector_apply_f64": 4, "iono_backprojector_apply_chunks_f64": 3,
+    "iono_forwardprojector_create": 1, "iono_forwardprojector_apply_f64": 1,
 }
 launch_count = 0
 

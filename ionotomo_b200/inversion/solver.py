@@ -13,7 +13,7 @@ import torch
 
 from .. import _lib
 from ..geometry.tri_cubic import TriCubic
-from .forward_equation import forward_equation
+from .forward_equation import ForwardProjector, forward_equation
 from .gradient import BackProjector, adjoint_coefficients, backproject, misfit, _ne_from_m
 
 
@@ -21,7 +21,7 @@ class InversionProblem(object):
     """Fixed geometry + data; evaluates misfit and gradient for a model array on the device."""
 
     def __init__(self, rays, K_ne, m_tci, i0, dobs, CdCt, order="time", binned=True, reduce_fn=None,
-                 reduce_scalar=None):
+                 reduce_scalar=None, prepared=False):
         self.rays = _lib.to_device(rays)
         self.K_ne = float(K_ne)
         self.i0 = int(i0)
@@ -33,6 +33,7 @@ class InversionProblem(object):
         self.reduce_fn = reduce_fn
         self.reduce_scalar = reduce_scalar
         self.bp = BackProjector(self.rays, m_tci) if binned else None
+        self.fp = ForwardProjector(self.rays, m_tci) if prepared else None
         self.n_forward = 0
         self.n_gradient = 0
 
@@ -46,7 +47,8 @@ class InversionProblem(object):
 
     def forward(self, m):
         self.n_forward += 1
-        return forward_equation(self.rays, self.K_ne, self._tci(m), self.i0, order=self.order, check_bounds=False)
+        return forward_equation(self.rays, self.K_ne, self._tci(m), self.i0, order=self.order, check_bounds=False,
+                                projector=self.fp)
 
     def misfit(self, g):
         S = misfit(g, self.dobs, self.CdCt)

@@ -627,3 +627,67 @@ def test_gaussian_adjoint_vs_oracle(ib, Ns, Nk):
                             15., bug_compat=False)
     got = compute_adjoint(rays, g, dobs, 1, P["K_ne"], tci, m_prior, CdCt, 0.8, Nk, 15.)
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-10 * np.abs(ref).max())
+
+
+@unrun
+@pytest.mark.parametrize("Ns", [2, 3, 4, 5, 30, 31, 64, 65, 66, 127, 128, 130, 200, 257])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_forward_projector_bit_identical_to_sweep(ib, Ns, uniform):
+    """The prepared forward derives cell, fractions and weights with the sweep's own device functions and
+    sums in the same order: TEC must be bit-identical, for every Ns (padding to 4), both grid kinds."""
+    import torch
+    P = small_problem(300 + Ns, 5, 3, 4, Ns, 14, 12, 16, uniform=uniform)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], Ns)
+    rays[..., 3, :] = rays[..., 3, :] + 0.3 * np.sin(rays[..., 3, :] / 50.)
+    m_tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    rays_d = torch.as_tensor(rays).cuda()
+    fp = ib.ForwardProjector(rays_d, m_tci)
+    assert fp.nbytes == rays_d.shape[0] * rays_d.shape[1] * rays_d.shape[2] * ((Ns + 3) // 4 * 4) * 36
+    dtec0, tec0 = ib.forward_equation(rays_d, P["K_ne"], m_tci, 2, return_tec=True)
+    dtec1, tec1 = ib.forward_equation(rays_d, P["K_ne"], m_tci, 2, return_tec=True, projector=fp)
+    assert torch.equal(tec0, tec1) and torch.equal(dtec0, dtec1)
+    ref_tec = O.tec(rays, P["xvec"], P["yvec"], P["zvec"], O.ne_from_m(P["m"], P["K_ne"]))
+    assert relerr(tec1.cpu().numpy(), ref_tec) < TOL
+
+
+@unrun
+@pytest.mark.parametrize("env", [{"IONO_SWEEP_NO_BULK": "1"}, {"IONO_PREP_CHUNK": "64"}, {"IONO_PREP_WARPS": "32"},
+                                 {"IONO_PREP_WARPS": "5", "IONO_PREP_STAGES": "3"}])
+def test_forward_projector_launch_variants(ib, env, monkeypatch):
+    import torch
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    P = small_problem(401, 7, 5, 9, 130, 20, 18, 40)
+    rays = torch.as_tensor(O.cast_ray(P["origins"], P["directions"], P["tmax"], 130)).cuda()
+    m_tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    fp = ib.ForwardProjector(rays, m_tci)
+    a = ib.forward_equation(rays, P["K_ne"], m_tci, 0, projector=fp)
+    for k in env:
+        monkeypatch.delenv(k)
+    b = ib.forward_equation(rays, P["K_ne"], m_tci, 0)
+    assert torch.equal(a, b)
+
+
+@unrun
+def test_forward_projector_edges(ib):
+    import torch
+    P = small_problem(9, 3, 1, 4, 16, 10, 10, 10)
+    m_tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    bad = O.cast_ray(P["origins"], P["directions"], 1200., 16)        # tmax above the grid top
+    with pytest.raises(ValueError):
+        ib.ForwardProjector(bad, m_tci)
+    empty = torch.empty((0, 2, 3, 4, 16), dtype=torch.float64, device="cuda")
+    fp = ib.ForwardProjector(empty, m_tci)
+    ones = torch.ones(m_tci.nx, m_tci.ny, m_tci.nz, dtype=torch.float64, device="cuda")
+    assert fp.tec(ones).shape == (0, 2, 3)
+    one_sample = torch.zeros((2, 1, 2, 4, 1), dtype=torch.float64, device="cuda")      # simps of one sample is 0
+    assert float(ib.ForwardProjector(one_sample, m_tci).tec(ones).abs().max()) == 0.0
+    # the device-resident driver with both prepared operators
+    from ionotomo_b200.inversion.solver import InversionProblem
+    rays = torch.as_tensor(O.cast_ray(P["origins"], P["directions"], 1000., 16)).cuda()
+    dobs = torch.zeros(3, 1, 4, dtype=torch.float64, device="cuda")
+    C = torch.ones_like(dobs)
+    m = torch.as_tensor(P["m"]).cuda()
+    pa = InversionProblem(rays, P["K_ne"], m_tci, 0, dobs, C, prepared=True)
+    pb = InversionProblem(rays, P["K_ne"], m_tci, 0, dobs, C, prepared=False)
+    assert torch.equal(pa.forward(m), pb.forward(m))

@@ -1,11 +1,26 @@
 #!/usr/bin/env bash
 # Round-2 first 1-GPU call: launch the kernels that were written after round 1's GPU budget was spent
 # (tests marked `unrun` in tests/test_gpu_parity.py), each under `timeout`.
-#   gpurun --timeout 900 -- 'bash tools/validate_unrun.sh'
-# When this passes, drop the `unrun` marker from those tests.
+#   gpurun --timeout 1200 -- 'bash tools/validate_unrun.sh'
+# When this passes, drop the `unrun` marker from those tests (and, if the prepared forward is faster,
+# make it bench.py's default --forward).
 set -u
 mkdir -p gpurun_out
 echo "== validated suite"
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 echo "== not-yet-run kernels"
-IONO_TEST_UNRUN=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "gaussian" 2>&1 | tail -15
+IONO_TEST_UNRUN=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q \
+    -k "gaussian or forward_projector" 2>&1 | tail -15
+for fwd in sweep prepared; do
+  echo "== bench --forward $fwd"
+  timeout 240 python bench.py --forward $fwd --no-e2e --no-cpu-baseline --steps 30 --warmup 5 \
+      > gpurun_out/unrun_bench_$fwd.json 2> gpurun_out/unrun_bench_$fwd.err
+  echo "rc=$?"; python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/unrun_bench_$fwd.json"))
+    print({k: round(v["ms"], 3) for k, v in d["kernels"].items()}, "ms/step", round(d["ms_per_step"], 3))
+except Exception as e:
+    print("no bench line:", e)
+PY
+done
