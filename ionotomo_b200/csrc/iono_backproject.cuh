@@ -43,6 +43,12 @@ struct iono_backprojector {
     int chunk_short[17], chunk_vlong[17];   // index ranges in the (sorted) straddler lists
     double *coef_perm;       // [R] coefficients in the internal ray order (a, d, t)
     int device;
+    // optional run-compressed ray indices (IONO_BP_RUNS=1 at create time, warp-private segments only):
+    // per segment a 256-bit mask of run heads + the ray index of every head, see backproject_wruns_kernel
+    unsigned char *runs;           // records, 16-byte units
+    unsigned long long *run_ptr;   // [nseg+1] record offsets in 16-byte units
+    long long run_bytes;
+    int use_runs;
 };
 
 // Internal ray numbering of the back-projector: time fastest, (a*Nd + d)*Nt + t.  Rays of one
@@ -394,6 +400,174 @@ __global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Run-compressed ray indices (experimental, IONO_BP_RUNS=1).  In the internal ray order (time
+// fastest) a voxel's sorted entry list consists of RUNS of consecutive ray numbers -- the rays of
+// one (antenna, direction) at successive times cross the same voxels; measured on the LOFAR-like
+// geometry: 8.6 entries per run -- so 4 bytes of index per entry are mostly redundant.  Per segment
+// of BP_WSEG entries the index array is replaced by a record
+//     [8 x u32 mask: bit b of word u set <=> entry 32u+b starts a run][u32 ray index of every head]
+// (entry 0 always starts a run; the record is padded to 16 bytes for the bulk copy).  The ray of
+// entry j is  head[rank(j) - 1] + (j - pos(j))  with rank = number of heads at positions <= j and pos
+// the position of the last of them: one popc and one clz on the mask word of the entry, the counts
+// of the earlier words carried along the unrolled loop.  ~9 bytes per entry instead of 12.
+// ---------------------------------------------------------------------------------------------
+constexpr int BP_RUNREC_MAX = 32 + BP_WSEG * 4;   // mask + a head for every entry
+
+// head flags of segment `seg` as ballot words: lane b, word u <-> entry 32u+b
+__device__ __forceinline__ unsigned int run_head_word(const unsigned int *__restrict__ ray_idx, long long k0, int u,
+                                                      int lane) {
+    const int j = 32 * u + lane;
+    const bool head = (j == 0) || (ray_idx[k0 + j] != ray_idx[k0 + j - 1] + 1u);
+    return __ballot_sync(0xffffffffu, head);
+}
+
+// Build time, pass 1: record size of every segment in 16-byte units (warp per segment).
+__global__ void __launch_bounds__(256) run_record_units_kernel(const unsigned int *__restrict__ ray_idx, long long nseg,
+                                                                unsigned long long *__restrict__ units) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long seg = warp_global; seg < nseg; seg += n_warps) {
+        int nh = 0;
+        for (int u = 0; u < BP_WSEG / 32; ++u) nh += __popc(run_head_word(ray_idx, seg * BP_WSEG, u, lane));
+        if (lane == 0) units[seg] = (unsigned long long)((32 + 4 * nh + 15) / 16);
+    }
+    if (warp_global == 0 && lane == 0) units[nseg] = 0;
+}
+
+// Build time, pass 2: write the records.
+__global__ void __launch_bounds__(256) run_record_fill_kernel(const unsigned int *__restrict__ ray_idx, long long nseg,
+                                                               const unsigned long long *__restrict__ run_ptr,
+                                                               unsigned char *__restrict__ runs) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long seg = warp_global; seg < nseg; seg += n_warps) {
+        unsigned int *rec = reinterpret_cast<unsigned int *>(runs + run_ptr[seg] * 16ull);
+        unsigned int *heads = rec + 8;
+        const long long k0 = seg * BP_WSEG;
+        int cum = 0;
+        for (int u = 0; u < BP_WSEG / 32; ++u) {
+            const unsigned int m = run_head_word(ray_idx, k0, u, lane);
+            if (lane == 0) rec[u] = m;
+            if ((m >> lane) & 1u) heads[cum + __popc(m & ((1u << lane) - 1u))] = ray_idx[k0 + 32 * u + lane];
+            cum += __popc(m);
+        }
+    }
+}
+
+// backproject_wsegments_kernel with the ray indices reconstructed from the run records.
+__global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__restrict__ seg_rows,
+                                                                 const long long *__restrict__ ptr,
+                                                                 const unsigned int *__restrict__ row_voxel,
+                                                                 const unsigned char *__restrict__ runs,
+                                                                 const unsigned long long *__restrict__ run_ptr,
+                                                                 const double *__restrict__ weight,
+                                                                 const double *__restrict__ coef,
+                                                                 const double *__restrict__ scale, long long nnz,
+                                                                 long long seg_begin, long long seg_end,
+                                                                 double *__restrict__ out,
+                                                                 double *__restrict__ partial) {
+    extern __shared__ __align__(128) unsigned char bp_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    constexpr int STAGE = BP_WSEG * 8 + BP_RUNREC_MAX;         // weights then the run record
+    unsigned char *mine = bp_smem + (size_t)warp * (2 * STAGE);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(bp_smem + (size_t)nwarp * 2 * STAGE) + warp * 2;
+    const long long nseg = seg_end;
+    const long long gw = seg_begin + (long long)blockIdx.x * nwarp + warp, gstride = (long long)gridDim.x * nwarp;
+    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const uint64_t pol = policy_evict_first();
+    auto issue = [&](long long seg, int buf) {
+        if (lane == 0) {
+            const unsigned long long u0 = __ldg(run_ptr + seg), u1 = __ldg(run_ptr + seg + 1);
+            const unsigned int rec_bytes = (unsigned int)(u1 - u0) * 16u;
+            mbar_expect_tx(&bar[buf], BP_WSEG * 8 + rec_bytes);
+            bulk_g2s(mine + buf * STAGE, weight + seg * BP_WSEG, BP_WSEG * 8, &bar[buf], pol);
+            bulk_g2s(mine + buf * STAGE + BP_WSEG * 8, runs + u0 * 16ull, rec_bytes, &bar[buf], pol);
+        }
+    };
+    if (gw < nseg) issue(gw, 0);
+    unsigned int phase = 0;
+    int buf = 0;
+    constexpr int PER = BP_WSEG / 32;
+    for (long long seg = gw; seg < nseg; seg += gstride, buf ^= 1) {
+        const long long k0 = seg * BP_WSEG, k1 = min(k0 + (long long)BP_WSEG, nnz);
+        const int2 rr = __ldg(seg_rows + seg);
+        if (seg + gstride < nseg) issue(seg + gstride, buf ^ 1);
+        const int n_rows = rr.y - rr.x + 1;
+        long long myptr = 0;
+        unsigned int myvox = 0;
+        double myscale = 1.0;
+        if (lane <= min(n_rows, 31)) myptr = __ldg(ptr + rr.x + lane);
+        if (lane < min(n_rows, 31)) {
+            myvox = __ldg(row_voxel + rr.x + lane);
+            if (scale) myscale = __ldg(scale + myvox);
+        }
+        mbar_wait(&bar[buf], (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        double *prod = reinterpret_cast<double *>(mine + buf * STAGE);
+        const unsigned int *mk = reinterpret_cast<const unsigned int *>(mine + buf * STAGE + BP_WSEG * 8);
+        const unsigned int *heads = mk + 8;
+        double c[PER];
+        int cum = 0, lastpos = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const unsigned int m = mk[u];
+            const unsigned int mle = m & (0xffffffffu >> (31 - lane));   // heads at positions <= mine in this word
+            const int rank = cum + __popc(mle);
+            const int pos = mle ? (32 * u + 31 - __clz(mle)) : lastpos;
+            c[u] = __ldg(coef + (heads[rank - 1] + (unsigned int)(32 * u + lane - pos)));
+            cum += __popc(m);
+            if (m) lastpos = 32 * u + 31 - __clz(m);
+        }
+        if (n_rows == 1) {
+            double s = 0.0;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) s = fma(prod[lane + u * 32], c[u], s);   // padding has weight 0
+            s = warp_sum(s);
+            const long long b = __shfl_sync(0xffffffffu, myptr, 0), e = __shfl_sync(0xffffffffu, myptr, 1);
+            if (lane == 0) {
+                if (b >= k0 && e <= k1) out[myvox] = s * myscale;
+                else partial[2 * seg + (b > k0 ? 1 : 0)] = s;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < PER; ++u) prod[lane + u * 32] *= c[u];
+            __syncwarp();
+            int r0 = 0;
+            while (true) {
+                const int nb = min(n_rows - r0, 31);
+                double mysum = 0.0;
+                for (int q = 0; q < nb; ++q) {
+                    const long long b = __shfl_sync(0xffffffffu, myptr, q), e = __shfl_sync(0xffffffffu, myptr, q + 1);
+                    const int lo = (int)(max(b, k0) - k0), hi = (int)(min(e, k1) - k0);
+                    double s = 0.0;
+                    for (int j = lo + lane; j < hi; j += 32) s += prod[j];
+                    s = warp_sum(s);
+                    if (lane == q) mysum = s;
+                }
+                const long long mye = __shfl_down_sync(0xffffffffu, myptr, 1);
+                if (lane < nb) {
+                    if (myptr >= k0 && mye <= k1) out[myvox] = mysum * myscale;
+                    else partial[2 * seg + (myptr > k0 ? 1 : 0)] = mysum;
+                }
+                r0 += nb;
+                if (r0 >= n_rows) break;
+                myptr = 0; myvox = 0; myscale = 1.0;
+                if (lane <= min(n_rows - r0, 31)) myptr = __ldg(ptr + rr.x + r0 + lane);
+                if (lane < min(n_rows - r0, 31)) {
+                    myvox = __ldg(row_voxel + rr.x + r0 + lane);
+                    if (scale) myscale = __ldg(scale + myvox);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // One THREAD per straddling row whose partials lie in at most 8 segments (the common case).
 __global__ void __launch_bounds__(256) backproject_combine_short_kernel(const int *__restrict__ rows, int n_rows,
                                                                          int seg, const long long *__restrict__ ptr,
@@ -480,13 +654,17 @@ extern "C" int iono_backprojector_destroy(iono_backprojector_t h) {
     cudaFree(h->partial);
     cudaFree(h->items);
     cudaFree(h->coef_perm);
+    cudaFree(h->runs);
+    cudaFree(h->run_ptr);
     delete h;
     return IONO_OK;
 }
 
 extern "C" long long iono_backprojector_nnz(iono_backprojector_t h) { return h ? h->nnz : 0; }
 extern "C" long long iono_backprojector_bytes(iono_backprojector_t h) {
-    return h ? h->nnz * 12 + (h->n_rows + 1) * 12 : 0;
+    if (!h) return 0;
+    if (h->use_runs) return h->nnz * 8 + h->run_bytes + ((h->nnz + BP_WSEG - 1) / BP_WSEG + 1) * 8 + (h->n_rows + 1) * 12;
+    return h->nnz * 12 + (h->n_rows + 1) * 12;
 }
 
 extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
@@ -507,6 +685,7 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
     const int BP_SEG = h->seg;
     h->ray_idx = nullptr; h->weight = nullptr; h->ptr = nullptr; h->row_voxel = nullptr; h->n_rows = 0; h->long_rows = nullptr; h->n_long = 0; h->vlong_rows = nullptr; h->n_vlong = 0; h->partial = nullptr; h->items = nullptr;
     h->nnz = 0; h->V = V; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->coef_perm = nullptr;
+    h->runs = nullptr; h->run_ptr = nullptr; h->run_bytes = 0; h->use_runs = 0;
     cudaGetDevice(&h->device);
     unsigned long long *k0 = nullptr, *k1 = nullptr, *uk = nullptr;
     double *v0 = nullptr, *v1 = nullptr;
@@ -658,6 +837,29 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
                 h->chunk_short[c] = (int)tab[c * 5 + 3]; h->chunk_vlong[c] = (int)tab[c * 5 + 4];
             }
         }
+        // optional: run-compressed ray indices for the warp-private apply
+        const char *er = getenv("IONO_BP_RUNS");
+        if (er && atoi(er) == 1 && BP_SEG == BP_WSEG && nseg > 0) {
+            BP_TRY(cudaMalloc(&h->run_ptr, (size_t)(nseg + 1) * sizeof(unsigned long long)));
+            run_record_units_kernel<<<ew_grid(nseg * 32), 256, 0, st>>>(h->ray_idx, nseg, h->run_ptr);
+            BP_TRY(cudaGetLastError());
+            tmp_bytes = 0;
+            BP_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->run_ptr, h->run_ptr, nseg + 1, st));
+            BP_TRY(cudaMalloc(&tmp, tmp_bytes));
+            BP_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, h->run_ptr, h->run_ptr, nseg + 1, st));
+            unsigned long long total_units = 0;
+            BP_TRY(cudaMemcpyAsync(&total_units, h->run_ptr + nseg, sizeof(total_units), cudaMemcpyDeviceToHost, st));
+            BP_TRY(cudaStreamSynchronize(st));
+            cudaFree(tmp); tmp = nullptr;
+            h->run_bytes = (long long)total_units * 16;
+            BP_TRY(cudaMalloc(&h->runs, (size_t)h->run_bytes + 16));
+            BP_TRY(cudaMemsetAsync(h->runs, 0, (size_t)h->run_bytes + 16, st));
+            run_record_fill_kernel<<<ew_grid(nseg * 32), 256, 0, st>>>(h->ray_idx, nseg, h->run_ptr, h->runs);
+            BP_TRY(cudaGetLastError());
+            BP_TRY(cudaStreamSynchronize(st));
+            cudaFree(h->ray_idx); h->ray_idx = nullptr;   // not read again in this mode
+            h->use_runs = 1;
+        }
     }
 #undef BP_TRY
     cleanup();
@@ -708,6 +910,16 @@ extern "C" int iono_backprojector_apply_chunks_f64(iono_backprojector_t h, const
             const int smem = warps * 2 * BP_WSEG * 12 + warps * 16 + 64;
             const long long cap = (long long)sm_count() * per_sm;
             const long long want = (nseg + warps - 1) / warps;
+            if (h->use_runs) {
+                const int smem_r = warps * 2 * (BP_WSEG * 8 + BP_RUNREC_MAX) + warps * 16 + 64;
+                CU_CHECK(cudaFuncSetAttribute(backproject_wruns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
+                backproject_wruns_kernel<<<(int)(want < cap ? want : cap), warps * 32, smem_r, st>>>(
+                    h->items, h->ptr, h->row_voxel, h->runs, h->run_ptr, h->weight, h->coef_perm, scale, h->nnz, sb, se,
+                    out, h->partial);
+                CU_CHECK(cudaGetLastError());
+                CU_CHECK(bp_combine(h, scale, out, c0, c1, st));
+                return IONO_OK;
+            }
             CU_CHECK(cudaFuncSetAttribute(backproject_wsegments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             backproject_wsegments_kernel<<<(int)(want < cap ? want : cap), warps * 32, smem, st>>>(
                 h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, sb, se, out,

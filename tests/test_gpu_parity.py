@@ -691,3 +691,27 @@ def test_forward_projector_edges(ib):
     pa = InversionProblem(rays, P["K_ne"], m_tci, 0, dobs, C, prepared=True)
     pb = InversionProblem(rays, P["K_ne"], m_tci, 0, dobs, C, prepared=False)
     assert torch.equal(pa.forward(m), pb.forward(m))
+
+
+@unrun
+@pytest.mark.parametrize("shape", [(20, 3, 16, 64, 40, 36, 64), (6, 40, 5, 30, 24, 20, 30), (3, 1, 2, 9, 10, 9, 11)])
+def test_binned_backprojector_run_compressed(ib, shape, monkeypatch):
+    """IONO_BP_RUNS=1 replaces the per-entry ray index by per-segment run records; products and sums are
+    formed in the same order, so the result must be bit-identical to the plain warp-private apply."""
+    import torch
+    Na, Nt, Nd, Ns, nx, ny, nz = shape
+    P = small_problem(500 + Nt, Na, Nt, Nd, Ns, nx, ny, nz)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    rays = ib.cast_ray((torch.as_tensor(P["origins"]).cuda(), torch.as_tensor(P["directions"]).cuda()),
+                       ib.Fermat(tci), 1000., Ns)
+    y = torch.randn(rays.shape[:3], dtype=torch.float64, device="cuda")
+    scale = torch.rand(P["m"].shape, dtype=torch.float64, device="cuda")
+    ref_bp = ib.BackProjector(rays, tci)
+    monkeypatch.setenv("IONO_BP_RUNS", "1")
+    run_bp = ib.BackProjector(rays, tci)
+    monkeypatch.delenv("IONO_BP_RUNS")
+    assert run_bp.nnz == ref_bp.nnz and run_bp.nbytes < ref_bp.nbytes
+    assert torch.equal(run_bp.apply(y, scale=scale), ref_bp.apply(y, scale=scale))
+    assert torch.equal(run_bp.apply(y), ref_bp.apply(y))
+    out = torch.empty_like(scale)
+    assert torch.equal(run_bp.apply_overlapped(y, scale=scale, out=out, n_chunks=4), ref_bp.apply(y, scale=scale))

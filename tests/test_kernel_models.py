@@ -138,3 +138,63 @@ def test_gaussian_adjoint_kernel_model_non_monotone_ray(golden):
                     np.cumsum(np.full(17, 60.)) + 3. * np.cos(11. * t)])
     assert np.any(np.diff(ray[2]) < 0)
     assert _compare(ray, np.linspace(1., 2., 17), xv, yv, zv, 1.1, 35., 2) > 100
+
+
+# ---------------------------------------------------------------- run-compressed ray indices
+def run_records_model(idx, seg=256):
+    """run_record_units_kernel / run_record_fill_kernel (csrc/iono_backproject.cuh): per segment of `seg`
+    entries the 8 mask words (bit b of word u <-> entry 32u+b starts a run) and the ray index of every head."""
+    recs = []
+    for k0 in range(0, len(idx), seg):
+        words, heads = [], []
+        for u in range(seg // 32):
+            m = 0
+            for lane in range(32):
+                j = 32 * u + lane
+                if j == 0 or idx[k0 + j] != (idx[k0 + j - 1] + 1) & 0xffffffff:
+                    m |= 1 << lane
+                    heads.append(int(idx[k0 + j]))
+            words.append(m)
+        recs.append((words, heads))
+    return recs
+
+
+def run_index_model(words, heads, u, lane):
+    """Ray index of entry 32u+lane as backproject_wruns_kernel reconstructs it."""
+    cum, lastpos = 0, 0
+    for w in range(u):                       # what the unrolled loop has carried along so far
+        m = words[w]
+        cum += bin(m).count("1")
+        if m:
+            lastpos = 32 * w + m.bit_length() - 1          # 31 - clz(m)
+    mle = words[u] & (0xffffffff >> (31 - lane))
+    rank = cum + bin(mle).count("1")
+    pos = 32 * u + mle.bit_length() - 1 if mle else lastpos
+    return heads[rank - 1] + (32 * u + lane - pos)
+
+
+def test_run_compressed_indices_model():
+    rng = np.random.RandomState(3)
+    # rows of a voxel-sorted operator: runs of consecutive rays (lengths 1..40), restarting at every row,
+    # plus the zero padding of the last segment and a run that crosses a segment boundary
+    idx = []
+    while len(idx) < 5 * 256 - 37:
+        start = rng.randint(0, 1_000_000)
+        for _ in range(rng.randint(1, 12)):
+            n = rng.randint(1, 41)
+            idx.extend(range(start, start + n))
+            start += n + rng.randint(1, 50_000)
+    idx = np.array(idx[:5 * 256 - 37] + [0] * 37, dtype=np.uint32)
+    recs = run_records_model(idx)
+    assert len(recs) == 5
+    n_heads = 0
+    for g, (words, heads) in enumerate(recs):
+        assert words[0] & 1                                  # entry 0 of a segment always starts a run
+        assert len(heads) == sum(bin(m).count("1") for m in words) <= 256
+        n_heads += len(heads)
+        for u in range(8):
+            for lane in range(32):
+                assert run_index_model(words, heads, u, lane) == idx[g * 256 + 32 * u + lane]
+    assert n_heads < len(idx) / 4                            # the point of the format
+    # record size in 16-byte units as the build computes it
+    assert all((32 + 4 * len(h) + 15) // 16 * 16 <= 32 + 256 * 4 for _, h in recs)

@@ -10,10 +10,11 @@ echo "== validated suite"
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 echo "== not-yet-run kernels"
 IONO_TEST_UNRUN=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q \
-    -k "gaussian or forward_projector" 2>&1 | tail -15
-for fwd in sweep prepared; do
-  echo "== bench --forward $fwd"
-  timeout 240 python bench.py --forward $fwd --no-e2e --no-cpu-baseline --steps 30 --warmup 5 \
+    -k "gaussian or forward_projector or run_compressed" 2>&1 | tail -15
+for fwd in sweep prepared runs; do
+  echo "== bench variant $fwd (runs = prepared forward + run-compressed binned adjoint)"
+  if [ $fwd = runs ]; then export IONO_BP_RUNS=1; f=prepared; else f=$fwd; fi
+  timeout 240 python bench.py --forward $f --no-e2e --no-cpu-baseline --steps 30 --warmup 5 \
       > gpurun_out/unrun_bench_$fwd.json 2> gpurun_out/unrun_bench_$fwd.err
   echo "rc=$?"; python - <<PY
 import json
