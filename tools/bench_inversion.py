@@ -20,6 +20,7 @@ ap.add_argument("--grid", type=int, nargs=3, default=[512, 512, 256])
 ap.add_argument("--nt", type=int, default=100)
 ap.add_argument("--iters", type=int, default=50)
 ap.add_argument("--scatter", action="store_true")
+ap.add_argument("--prepared", action="store_true", help="prepared forward projector (see ForwardProjector)")
 args = ap.parse_args()
 nx, ny, nz = args.grid
 w = make_workload(Nt=args.nt, nx=nx, ny=ny, nz=nz)
@@ -36,7 +37,7 @@ if not args.scatter and need > 0.9 * free:
 torch.cuda.synchronize()
 t0 = time.time()
 prob = InversionProblem(rays, w["K_ne"], ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_prior"]), 0, dobs, CdCt,
-                        binned=not args.scatter)
+                        binned=not args.scatter, prepared=args.prepared)
 torch.cuda.synchronize()
 t_build = time.time() - t0
 t0 = time.time()
@@ -50,5 +51,6 @@ print(json.dumps({
     "iterations": len(info["S"]) - 1, "seconds": dt, "s_per_iteration": dt / max(1, len(info["S"]) - 1),
     "n_forward": info["n_forward"], "n_gradient": info["n_gradient"], "operator_build_s": t_build,
     "operator_gb": (prob.bp.nbytes / 1e9) if prob.bp else 0.0, "adjoint": "scatter" if args.scatter else "binned",
+    "forward": "prepared" if args.prepared else "sweep", "forward_operator_gb": (prob.fp.nbytes / 1e9) if prob.fp else 0.0,
     "misfit_first": info["S"][0], "misfit_last": info["S"][-1], "mean_abs_model_error": [err0, err1],
     "peak_hbm_gb": torch.cuda.max_memory_allocated() / 1e9}))
