@@ -715,3 +715,27 @@ def test_binned_backprojector_run_compressed(ib, shape, monkeypatch):
     assert torch.equal(run_bp.apply(y), ref_bp.apply(y))
     out = torch.empty_like(scale)
     assert torch.equal(run_bp.apply_overlapped(y, scale=scale, out=out, n_chunks=4), ref_bp.apply(y, scale=scale))
+
+
+@unrun
+def test_sweep_shrinks_cta_for_large_axis_tables(ib):
+    """6004 axis nodes = 94 KB of cell tables in shared memory: the sweep must drop to fewer warps per CTA
+    (launch_sweep) instead of refusing, and still agree with the oracle (forward and exact adjoint)."""
+    rng = np.random.RandomState(5)
+    nx, ny, nz, Ns = 3000, 3000, 4, 12
+    xvec, yvec, zvec = np.linspace(-60., 60., nx), np.linspace(-55., 65., ny), np.linspace(-10., 1010., nz)
+    ne = 1. + rng.uniform(size=(nx, ny, nz))
+    P = small_problem(6, 3, 2, 3, Ns, 5, 5, 5)
+    rays = O.cast_ray(P["origins"], P["directions"], 1000., Ns)
+    tci = ib.TriCubic(xvec, yvec, zvec, np.log(ne))
+    dtec, tec = ib.forward_equation(rays, 1e13, tci, 0, return_tec=True)
+    ref = O.tec(rays, xvec, yvec, zvec, ne)
+    assert relerr(tec, ref) < TOL
+    from ionotomo_b200.inversion.gradient import backproject
+    import torch
+    coef = rng.normal(size=rays.shape[:3])
+    acc = backproject(torch.as_tensor(rays).cuda(), tci.grid(), torch.as_tensor(coef).cuda(), (nx, ny, nz))
+    x = rng.normal(size=(nx, ny, nz))
+    lhs = float((O.tec(rays, xvec, yvec, zvec, x) * coef).sum())
+    rhs = float((acc.cpu().numpy() * x).sum())
+    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), 1e-300)

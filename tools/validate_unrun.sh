@@ -10,7 +10,7 @@ echo "== validated suite"
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 echo "== not-yet-run kernels"
 IONO_TEST_UNRUN=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -q \
-    -k "gaussian or forward_projector or run_compressed" 2>&1 | tail -15
+    -k "gaussian or forward_projector or run_compressed or large_axis" 2>&1 | tail -15
 for fwd in sweep prepared runs; do
   echo "== bench variant $fwd (runs = prepared forward + run-compressed binned adjoint)"
   if [ $fwd = runs ]; then export IONO_BP_RUNS=1; f=prepared; else f=$fwd; fi
