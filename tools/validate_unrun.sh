@@ -25,3 +25,16 @@ except Exception as e:
     print("no bench line:", e)
 PY
 done
+# ncu only after the plain runs above exited 0 (never under a multi-rank launch)
+if [ -s gpurun_out/unrun_bench_runs.json ]; then
+  echo "== launch list of the bench with the prepared operators"
+  IONO_BP_RUNS=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+      --log-file gpurun_out/launches_prepared.csv python bench.py --forward prepared --no-e2e --no-cpu-baseline \
+      --steps 2 --warmup 1 > gpurun_out/ncu_launches.log 2>&1
+  echo "rc=$?"
+  echo "== ncu --set full of the two apply kernels"
+  NT=100 IONO_BP_RUNS=1 timeout 900 ncu --set full --clock-control none --import-source on \
+      -k regex:"prepared_forward|backproject_wruns" -c 4 -f -o gpurun_out/prof_prepared \
+      python tools/profile_prepared.py > gpurun_out/ncu_prepared.log 2>&1
+  echo "rc=$?"
+fi
