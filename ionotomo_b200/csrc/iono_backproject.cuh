@@ -742,6 +742,14 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
         BP_TRY(cudaMemcpyAsync(&M, d_runs, sizeof(long long), cudaMemcpyDeviceToHost, st));
         BP_TRY(cudaStreamSynchronize(st));
         cudaFree(tmp); tmp = nullptr;
+        // DeviceRunLengthEncode (row table below) counts with a plain int in this CUB, and row/segment
+        // indices are ints throughout the apply: refuse larger operators instead of truncating
+        if (M > 0x7fffffffLL - 2 * BP_SEG) {
+            cleanup();
+            iono_backprojector_destroy(h);
+            return fail(IONO_EBADARG, "iono_backprojector_create: more than 2^31 operator entries; shard the rays "
+                                      "(or use the stateless adjoint)");
+        }
         // release the sorted inputs before allocating the final arrays
         if (ks == k0) { cudaFree(k0); k0 = nullptr; cudaFree(v0); v0 = nullptr; }
         else          { cudaFree(k1); k1 = nullptr; cudaFree(v1); v1 = nullptr; }
@@ -889,6 +897,7 @@ extern "C" int iono_backprojector_apply_chunks_f64(iono_backprojector_t h, const
                                                    double *out, int c0, int c1, void *stream) {
     if (!h || !out || (h->R > 0 && !coef) || c0 < 0 || c1 > 16 || c0 >= c1)
         return fail(IONO_EBADARG, "iono_backprojector_apply_chunks_f64: bad argument");
+    if (device_check(h->device, "iono_backprojector_apply")) return IONO_EBADARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int ctas = sm_count() * 8;
     if (c0 == 0) {

@@ -49,6 +49,14 @@ static int sm_count() {
     return cached[dev];
 }
 
+// Handles cache device pointers: refuse to launch on another device than the one they were built on.
+static int device_check(int handle_device, const char *what) {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != handle_device)
+        return fail(IONO_EBADARG, "%s: the handle was created on another CUDA device than the current one", what);
+    return IONO_OK;
+}
+
 extern "C" int iono_version(void) { return IONO_ABI_VERSION; }
 extern "C" const char *iono_last_error(void) { return g_err; }
 
@@ -88,7 +96,10 @@ extern "C" int iono_grid_create(const double *xv, const double *yv, const double
         if (!axis_monotone(g[a], n[a])) return fail(IONO_EBADARG, "iono_grid_create: axis not strictly increasing");
     iono_grid *h = new iono_grid();
     h->nx = nx; h->ny = ny; h->nz = nz;
-    CU_CHECK(cudaGetDevice(&h->device));
+    {
+        cudaError_t e0 = cudaGetDevice(&h->device);
+        if (e0 != cudaSuccess) { delete h; return fail(IONO_ECUDA, "cudaGetDevice: %s", cudaGetErrorString(e0)); }
+    }
     size_t total = (size_t)nx + ny + nz;
     std::vector<double2> host(total);
     size_t off = 0;
@@ -536,8 +547,9 @@ __global__ void __launch_bounds__(256) convolve3d_nearest_kernel(const double *_
 
 extern "C" int iono_convolve3d_nearest_f64(const double *phi, int nx, int ny, int nz, const double *stencil, int m,
                                            double *out, void *stream) {
-    if (nx < 0 || ny < 0 || nz < 0 || m < 1 || (m & 1) == 0 || m > 31)
-        return fail(IONO_EBADARG, "iono_convolve3d_nearest_f64: bad argument (odd stencil size 1..31)");
+    // 29^3 doubles = 195 KB of shared memory; 31^3 would exceed the 227 KB a CTA can opt into
+    if (nx < 0 || ny < 0 || nz < 0 || m < 1 || (m & 1) == 0 || m > 29)
+        return fail(IONO_EBADARG, "iono_convolve3d_nearest_f64: bad argument (odd stencil size 1..29)");
     const long long n = (long long)nx * ny * nz;
     if (n == 0) return IONO_OK;
     if (!phi || !stencil || !out || phi == out) return fail(IONO_EBADARG, "iono_convolve3d_nearest_f64: bad pointer");

@@ -253,6 +253,7 @@ extern "C" int iono_forwardprojector_apply_f64(iono_forwardprojector_t h, const 
                                                void *stream) {
     if (!h || !ne || (h->R > 0 && !tec_out))
         return fail(IONO_EBADARG, "iono_forwardprojector_apply_f64: bad argument");
+    if (device_check(h->device, "iono_forwardprojector_apply_f64")) return IONO_EBADARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (h->R == 0) return IONO_OK;
     if (h->Ns < 2) {

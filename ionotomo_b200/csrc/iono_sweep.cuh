@@ -370,6 +370,7 @@ static int launch_sweep_t(const SweepParams &p, const SweepConfig &cfg, size_t s
 
 template <int MODE>
 static int launch_sweep(SweepParams p, iono_grid_t grid, cudaStream_t st) {
+    if (device_check(grid->device, "ray sweep")) return IONO_EBADARG;
     SweepConfig cfg = sweep_config(MODE, p.Ns);
     p.stages = cfg.stages;
     const size_t stage_bytes = cfg.chunk == 64 ? StageLayout<64>::BYTES : StageLayout<128>::BYTES;

@@ -110,8 +110,10 @@ class BackProjector(object):
         assert n_chunks in (1, 2, 4, 8, 16)
         lib = _lib.load()
         coef = _lib.to_device(coef)
+        assert tuple(coef.shape) == self.ray_shape
         acc = out if out is not None else torch.empty(self.shape, dtype=torch.float64, device=coef.device)
-        flat = acc.reshape(-1)
+        assert acc.is_contiguous(), "apply_overlapped reduces views of `out`: it must be contiguous"
+        flat = acc.view(-1)
         V = flat.numel()
         bounds = [V * j // n_chunks for j in range(n_chunks + 1)]
         step = 16 // n_chunks

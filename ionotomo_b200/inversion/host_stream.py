@@ -39,7 +39,7 @@ def _pinned_like(key, shape):
 
 
 def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_times=None, check_bounds=True,
-                        reduce_fn=None, timings=None, copy_results=True):
+                        reduce_fn=None, timings=None, copy_results=True, reduce_scalar=None):
     """``(dtec, S, gradient)`` as NumPy/float from host arrays.
 
     ``rays`` may be a NumPy array or a (preferably pinned) CPU tensor of shape
@@ -50,6 +50,12 @@ def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_t
     Results are read back into cached *pinned* host buffers.  With ``copy_results=False`` the
     returned arrays are views of those buffers (valid until the next call) -- what an optimiser
     loop wants; the default returns private copies.
+
+    With sharded rays pass ``reduce_fn`` (sum of the voxel accumulator over ranks, applied in place
+    to a CUDA tensor) AND ``reduce_scalar`` (0-d CUDA tensor -> float summed over ranks, e.g.
+    ``sharding.sharded_misfit``): the returned ``(S, gradient)`` pair is then the global one on
+    every rank; ``dtec`` always covers the local rays only.  Without ``reduce_scalar`` the misfit
+    is the shard-local one.
     """
     import time as _time
     _t0 = _time.time()
@@ -136,7 +142,7 @@ def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_t
     grad_h = _pinned_like("grad", acc.shape)
     dtec_h.copy_(dtec, non_blocking=True)
     grad_h.copy_(acc, non_blocking=True)
-    S = float(S)                                   # synchronises
+    S = float(reduce_scalar(S)) if reduce_scalar is not None else float(S)   # synchronises
     torch.cuda.current_stream().synchronize()
     if timings is not None:
         timings["finish_ms"] = (_time.time() - _t0) * 1e3

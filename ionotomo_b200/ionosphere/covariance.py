@@ -13,7 +13,7 @@ import torch
 from .. import _lib
 
 
-def exponential_sep_stencil(dx, dy, dz, sigma=1., l=20., threshold=0.05, max_m=31):
+def exponential_sep_stencil(dx, dy, dz, sigma=1., l=20., threshold=0.05, max_m=29):
     """Stencil of the default kernel of ``Covariance.__init__`` (covariance.py:21-23): the product over
     the three axes of Matern-1/2 (exponential) kernels ``sigma^2 exp(-|r_d|/l)``, grown from 5 points
     per axis until its edge falls below ``threshold`` of its centre (``create_c_stencil``, :46-62)."""
