@@ -105,7 +105,7 @@ def test_apply_overlapped_host_logic_with_fake_library(monkeypatch):
     monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
     monkeypatch.setattr(_lib, "call", lambda name, *args: calls.append((name, args[4], args[5])))
     bp = object.__new__(G.BackProjector)
-    bp.handle, bp.shape = None, (6, 5, 4)
+    bp.handle, bp.shape, bp.ray_shape = None, (6, 5, 4), (2, 2, 2)
 
     class Handle(object):
         waited = 0
@@ -163,7 +163,7 @@ def _overlap_worker(rank, world, port, out):
     _lib.stream_ptr = lambda: None
     _lib.call = fake_call
     bp = object.__new__(G.BackProjector)
-    bp.handle, bp.shape = None, shape
+    bp.handle, bp.shape, bp.ray_shape = None, shape, (1,)
     ok = True
     for n_chunks in (1, 2, 4, 8, 16):
         acc = torch.full(shape, -1.0, dtype=torch.float64)
