@@ -108,6 +108,20 @@ int iono_tci_interp_f64(iono_grid_t grid, const double *M, const double *x, cons
 int iono_tec_forward_f64(iono_grid_t grid, const double *ne, const double *rays, int Na, int Nt,
                          int Nd, int Ns, int order, double *tec_out,
                          unsigned long long *oob_count, void *stream);
+/* Quad layout of a grid field for the forward gathers: record v = (ix*ny+iy)*nz+iz holds
+ * { f[ix,iy,iz], f[ix,iy,iz+1], f[ix,iy+1,iz], f[ix,iy+1,iz+1] } (32 B, steps past the last node
+ * clamped), so the 8 corners of a cell are two 256-bit loads.  quads_out: 4*nx*ny*nz doubles,
+ * 32-byte aligned.  iono_ne_quads_from_m_f64 fuses ne = exp(m)*scale (forward_equation.py:41-43):
+ * one launch writes the quad records and, if ne_out != NULL, the plain ne grid as well.
+ * iono_tec_forward_f64 / iono_forwardprojector_apply_f64 (plain ne in) build the records themselves
+ * in a stream-ordered temporary when that pays (IONO_FWD_LAYOUT=plain|quads overrides); the
+ * *_quads_f64 entry points take records the caller keeps, e.g. across a forward and its line search. */
+int iono_quads_from_ne_f64(const double *ne, int nx, int ny, int nz, double *quads_out, void *stream);
+int iono_ne_quads_from_m_f64(const double *m, int nx, int ny, int nz, double scale, double *ne_out,
+                             double *quads_out, void *stream);
+int iono_tec_forward_quads_f64(iono_grid_t grid, const double *quads, const double *rays, int Na, int Nt,
+                               int Nd, int Ns, int order, double *tec_out,
+                               unsigned long long *oob_count, void *stream);
 /* dtec_out = tec - tec[i0,:,:] (inversion/forward_equation.py:50); may alias tec */
 int iono_dtec_f64(const double *tec, int Na, int Nt, int Nd, int i0, double *dtec_out, void *stream);
 
@@ -116,6 +130,15 @@ int iono_dtec_f64(const double *tec, int Na, int Nt, int Nd, int i0, double *dte
  * dd = (g-dobs)/(CdCt+1e-15) (inversion/gradient.py:33-37). */
 int iono_adjoint_coef_f64(const double *g, const double *dobs, const double *CdCt, int Na, int Nt,
                           int Nd, int i0, double *coef_out, void *stream);
+/* Everything between the forward and the adjoint in one launch: dtec_out = tec - tec[i0]
+ * (forward_equation.py:50), misfit_out[0] = sum((dtec-dobs)^2/(CdCt+1e-15))/2 (line_search.py:48-49),
+ * coef_out as iono_adjoint_coef_f64 (may be NULL), coef_perm_out = the same coefficients in the
+ * back-projector's internal order (antenna, direction, time) for iono_backprojector_apply_permuted_f64
+ * (may be NULL).  scratch: iono_residual_scratch_elems() doubles.  Deterministic. */
+int64_t iono_residual_scratch_elems(void);
+int iono_residual_f64(const double *tec, const double *dobs, const double *CdCt, int Na, int Nt, int Nd,
+                      int i0, double *dtec_out, double *coef_out, double *coef_perm_out, double *scratch,
+                      double *misfit_out, void *stream);
 /* acc[v] (+)= sum_ray coef[ray] sum_s w_s(ray) phi_v(x_s); zero_first!=0 clears
  * acc before accumulating.  acc: (nx,ny,nz).  The voxel gradient of the misfit
  * is ne[v]*acc[v] (iono_mul_f64) after the cross-GPU sum of acc. */
@@ -137,6 +160,8 @@ int iono_forwardprojector_create(iono_grid_t grid, const double *rays, int Na, i
                                  void *stream);
 int iono_forwardprojector_apply_f64(iono_forwardprojector_t fp, const double *ne, double *tec_out,
                                     void *stream);
+int iono_forwardprojector_apply_quads_f64(iono_forwardprojector_t fp, const double *quads, double *tec_out,
+                                          void *stream);
 long long iono_forwardprojector_bytes(iono_forwardprojector_t fp);
 int iono_forwardprojector_destroy(iono_forwardprojector_t fp);
 
@@ -175,8 +200,8 @@ int iono_phase_assemble_f64(const double *integrals, int Na, int Nt, int Nd, int
 
 /* ---- voxel-binned back-projector (adjoint without atomics) ----------------------
  * The same linear map as iono_tec_adjoint_f64, assembled once per ray geometry in
- * voxel-major sparse form (sorted (voxel, ray, weight) triples; needs ~12 B per
- * distinct (voxel, ray) pair, ~520 pairs per ray at the LOFAR case) and then applied
+ * voxel-major sparse form (sorted (voxel, ray, weight) triples; ~9.5 B per distinct (voxel, ray)
+ * pair with run-compressed ray indices, ~520 pairs per ray at the LOFAR case) and then applied
  * as a gather: out[v] = scale[v] * sum_ray A[v,ray] * coef[ray]  (scale may be NULL).
  * Worth it when the rays are reused across iterations, as in every reference driver
  * (tests/test_inversion.py:30-39, bfgs_dask.py:207-340, iterative_newton.py:954-1017).
@@ -191,6 +216,10 @@ int iono_backprojector_apply_f64(iono_backprojector_t bp, const double *coef, co
  * out[chunk_voxels(c0) : chunk_voxels(c1)) is final and may be all-reduced while later chunks run. */
 int iono_backprojector_apply_chunks_f64(iono_backprojector_t bp, const double *coef, const double *scale,
                                         double *out, int c0, int c1, void *stream);
+/* the same with the coefficients already in the internal (antenna, direction, time) order
+ * (coef_perm_out of iono_residual_f64): no permutation pass */
+int iono_backprojector_apply_permuted_f64(iono_backprojector_t bp, const double *coef_perm, const double *scale,
+                                          double *out, int c0, int c1, void *stream);
 long long iono_backprojector_chunk_voxels(iono_backprojector_t bp, int c);
 long long iono_backprojector_nnz(iono_backprojector_t bp);
 long long iono_backprojector_bytes(iono_backprojector_t bp);

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libionob200.so")
+LIB_PATH = os.environ.get("IONO_LIB") or os.path.join(_HERE, "libionob200.so")   # IONO_LIB: kernel-variant builds (tools/)
 
 IONO_OK, IONO_EBADARG, IONO_EOOB, IONO_ECUDA = 0, 1, 2, 3
 ORDER_NATURAL, ORDER_TIME, ORDER_ANTENNA = 0, 1, 2
@@ -36,6 +36,11 @@ SIGNATURES = {
     "iono_optical_path_f64": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "iono_tci_interp_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "iono_tec_forward_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "iono_quads_from_ne_f64": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "iono_ne_quads_from_m_f64": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp]),
+    "iono_tec_forward_quads_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "iono_residual_scratch_elems": (_i64, []),
+    "iono_residual_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "iono_dtec_f64": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "iono_adjoint_coef_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "iono_tec_adjoint_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
@@ -50,12 +55,14 @@ SIGNATURES = {
     "iono_backprojector_create": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp, _vp]),
     "iono_backprojector_apply_f64": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "iono_backprojector_apply_chunks_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "iono_backprojector_apply_permuted_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "iono_backprojector_chunk_voxels": (ctypes.c_longlong, [_vp, _i]),
     "iono_backprojector_nnz": (ctypes.c_longlong, [_vp]),
     "iono_backprojector_bytes": (ctypes.c_longlong, [_vp]),
     "iono_backprojector_destroy": (_i, [_vp]),
     "iono_forwardprojector_create": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp, _vp]),
     "iono_forwardprojector_apply_f64": (_i, [_vp, _vp, _vp, _vp]),
+    "iono_forwardprojector_apply_quads_f64": (_i, [_vp, _vp, _vp, _vp]),
     "iono_forwardprojector_bytes": (ctypes.c_longlong, [_vp]),
     "iono_forwardprojector_destroy": (_i, [_vp]),
 }
@@ -69,7 +76,9 @@ KERNEL_LAUNCHES = {
     "iono_phase_integrals_f64": 1, "iono_phase_assemble_f64": 1, "iono_chord_adjoint_f64": 1,
     "iono_gaussian_adjoint_f64": 1,
     "iono_backprojector_apply_f64": 4, "iono_backprojector_apply_chunks_f64": 3,
-    "iono_forwardprojector_create": 1, "iono_forwardprojector_apply_f64": 1,
+    "iono_backprojector_apply_permuted_f64": 3,
+    "iono_forwardprojector_create": 1, "iono_forwardprojector_apply_f64": 2, "iono_forwardprojector_apply_quads_f64": 1,
+    "iono_quads_from_ne_f64": 1, "iono_ne_quads_from_m_f64": 1, "iono_tec_forward_quads_f64": 1, "iono_residual_f64": 1,
 }
 launch_count = 0
 

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) permute_coef_kernel(const double *__restr
     }
 }
 
-template <bool UNIFORM>
+template <int AXK>
 __global__ void __launch_bounds__(256) emit_entries_kernel(Grid g, const double *__restrict__ rays, int R, int Nt,
                                                             int Nd, int Ns,
                                                             unsigned long long *__restrict__ keys,
@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(256) emit_entries_kernel(Grid g, const double 
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     const int ny = g.ax[1].n, nz = g.ax[2].n;
     const bool n_odd = Ns & 1;
+    const AxisR ax = axis_regs(g.ax[0]), ay = axis_regs(g.ax[1]), az = axis_regs(g.ax[2]);
     unsigned int n_oob = 0;
     for (int ray = warp_global; ray < R; ray += n_warps) {
         const double *rp = rays + (long long)ray * 4 * Ns;
@@ -94,11 +95,9 @@ __global__ void __launch_bounds__(256) emit_entries_kernel(Grid g, const double 
         for (int i = lane; i < Ns; i += 32) {
             int ix, iy, iz;
             double tx, ty, tz;
-            bool oob = false;
-            locate<UNIFORM>(g.ax[0].tab, g.ax[0], __ldg(rp + i), ix, tx, oob);
-            locate<UNIFORM>(g.ax[1].tab, g.ax[1], __ldg(rp + Ns + i), iy, ty, oob);
-            locate<UNIFORM>(g.ax[2].tab, g.ax[2], __ldg(rp + 2 * Ns + i), iz, tz, oob);
-            n_oob += oob;
+            // the same cell and in-cell coordinates as the forward sweep derives (one operator, two directions)
+            n_oob += locate3<AXK>(g.ax[0].tab, g.ax[1].tab, g.ax[2].tab, ax, ay, az, __ldg(rp + i), __ldg(rp + Ns + i),
+                                  __ldg(rp + 2 * Ns + i), ix, iy, iz, tx, ty, tz);
             const double sm2 = (i >= 2) ? __ldg(sp + i - 2) : 0.0, sm1 = (i >= 1) ? __ldg(sp + i - 1) : 0.0;
             const double s0 = __ldg(sp + i);
             const double sp1 = (i + 1 < Ns) ? __ldg(sp + i + 1) : 0.0, sp2 = (i + 2 < Ns) ? __ldg(sp + i + 2) : 0.0;
@@ -141,16 +140,14 @@ struct KeyVoxel {
 
 // Apply = a balanced sweep over the ENTRY stream, not over voxels: row lengths range from 0 to
 // ~1e6 (heavy voxels sit under the array core, where every ray of a station starts in the same
-// cell), so the entry index space is cut into segments of BP_SEG entries, one CTA each:
-//   1. products weight[k]*coef[ray_idx[k]] of the segment -> shared memory (coalesced, 4 loads
-//      in flight per thread);
-//   2. every row (voxel) that intersects the segment is summed from shared memory by one warp;
+// cell), so the entry index space is cut into segments of BP_WSEG entries, one WARP each:
+//   1. products weight[k]*coef[ray(k)] of the segment -> shared memory (8 gathers in flight per lane);
+//   2. every row (voxel) that intersects the segment is summed from shared memory by the warp;
 //      rows completely inside are written to out[], the (at most two) rows that continue into
 //      a neighbouring segment go to partial[2*seg + slot];
 //   3. a small kernel adds the partials of each straddling row in segment order.
 // slot 0: the row covers the segment's first entry; slot 1: the row begins inside the segment.
 // Everything is a fixed reduction tree: bit-reproducible.
-constexpr int BP_SEG_DEFAULT = 1024;   // entries per segment (IONO_BP_SEG=1024|2048 at create time)
 
 // voxel (row) that contains entry k: largest v with ptr[v] <= k
 __device__ __forceinline__ long long row_of_entry(const long long *__restrict__ ptr, long long V, long long k) {
@@ -190,107 +187,6 @@ __global__ void __launch_bounds__(256) find_straddling_rows_kernel(const long lo
             const int k = atomicAdd(count, 1);
             if (k < cap) rows[k] = (int)v;
         }
-    }
-}
-
-template <int BP_SEG>
-__global__ void __launch_bounds__(256) backproject_segments_kernel(const int2 *__restrict__ seg_rows,
-                                                                    const long long *__restrict__ ptr,
-                                                                    const unsigned int *__restrict__ row_voxel,
-                                                                    const unsigned int *__restrict__ ray_idx,
-                                                                    const double *__restrict__ weight,
-                                                                    const double *__restrict__ coef,
-                                                                    const double *__restrict__ scale, long long nnz,
-                                                                    long long seg_begin, long long seg_end,
-                                                                    double *__restrict__ out,
-                                                                    double *__restrict__ partial) {
-    // double-buffered segment of the entry stream, filled by TMA bulk copies
-    extern __shared__ __align__(128) unsigned char bp_smem[];
-    double (*w_s)[BP_SEG] = reinterpret_cast<double (*)[BP_SEG]>(bp_smem);
-    unsigned int (*r_s)[BP_SEG] = reinterpret_cast<unsigned int (*)[BP_SEG]>(bp_smem + 2 * BP_SEG * 8);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(bp_smem + 2 * BP_SEG * 12);
-    double *part = reinterpret_cast<double *>(bp_smem + 2 * BP_SEG * 12 + 16);   // [8]
-    int *next_row = reinterpret_cast<int *>(bp_smem + 2 * BP_SEG * 12 + 16 + 64);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long nseg = seg_end;
-    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-    const uint64_t pol = policy_evict_first();
-    auto issue = [&](long long seg, int buf) {   // arrays are padded to a whole number of segments
-        mbar_expect_tx(&bar[buf], BP_SEG * 12);
-        bulk_g2s(w_s[buf], weight + seg * BP_SEG, BP_SEG * 8, &bar[buf], pol);
-        bulk_g2s(r_s[buf], ray_idx + seg * BP_SEG, BP_SEG * 4, &bar[buf], pol);
-    };
-    if (threadIdx.x == 0 && seg_begin + (long long)blockIdx.x < nseg) issue(seg_begin + blockIdx.x, 0);
-    unsigned int phase = 0;
-    int buf = 0;
-    constexpr int PER = BP_SEG / 256;
-    for (long long seg = seg_begin + blockIdx.x; seg < nseg; seg += gridDim.x, buf ^= 1) {
-        const long long k0 = seg * BP_SEG, k1 = min(k0 + (long long)BP_SEG, nnz);
-        const int2 rr = seg_rows[seg];
-        if (threadIdx.x == 0) {
-            if (seg + gridDim.x < nseg) issue(seg + gridDim.x, buf ^ 1);
-            *next_row = rr.x + 8;
-        }
-        mbar_wait(&bar[buf], (phase >> buf) & 1u);
-        phase ^= 1u << buf;
-        double *prod = w_s[buf];
-        double c[PER];
-#pragma unroll
-        for (int u = 0; u < PER; ++u) c[u] = __ldg(coef + r_s[buf][threadIdx.x + u * 256]);
-        if (rr.x == rr.y) {
-            // the whole segment lies in one (long) row: block-wide sum, no staging of products
-            // (padding entries beyond nnz have weight 0)
-            double s = 0.0;
-#pragma unroll
-            for (int u = 0; u < PER; ++u) s = fma(prod[threadIdx.x + u * 256], c[u], s);
-            s = warp_sum(s);
-            if (lane == 0) part[warp] = s;
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                double t = threadIdx.x < 8 ? part[threadIdx.x] : 0.0;
-                t = warp_sum(t);
-                if (threadIdx.x == 0) {
-                    const long long b = ptr[rr.x], e = ptr[rr.x + 1];
-                    if (b >= k0 && e <= k1) {
-                        const unsigned int v = row_voxel[rr.x];
-                        out[v] = scale ? t * scale[v] : t;
-                    } else {
-                        partial[2 * seg + (b > k0 ? 1 : 0)] = t;
-                    }
-                }
-            }
-            __syncthreads();
-            continue;
-        }
-        // 1. products in place
-#pragma unroll
-        for (int u = 0; u < PER; ++u) prod[threadIdx.x + u * 256] *= c[u];
-        __syncthreads();
-        // 2. rows are handed to warps dynamically (a long row keeps one warp busy while the
-        //    others move on); each row is still summed by a fixed lane pattern
-        int r = rr.x + warp;
-        while (r <= rr.y) {
-            const long long b = __ldg(ptr + r), e = __ldg(ptr + r + 1);
-            const int lo = (int)(max(b, k0) - k0), hi = (int)(min(e, k1) - k0);
-            double s0 = 0.0, s1 = 0.0;
-            int j = lo + lane;
-            for (; j + 32 < hi; j += 64) { s0 += prod[j]; s1 += prod[j + 32]; }
-            if (j < hi) s0 += prod[j];
-            const double s = warp_sum(s0 + s1);
-            if (lane == 0) {
-                if (b >= k0 && e <= k1) {
-                    const unsigned int v = __ldg(row_voxel + r);
-                    out[v] = scale ? s * __ldg(scale + v) : s;
-                } else {
-                    partial[2 * seg + (b > k0 ? 1 : 0)] = s;
-                }
-                r = atomicAdd(next_row, 1);
-            }
-            r = __shfl_sync(0xffffffffu, r, 0);
-        }
-        __syncthreads();
     }
 }
 
@@ -401,18 +297,19 @@ __global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *
 }
 
 // ---------------------------------------------------------------------------------------------
-// Run-compressed ray indices (experimental, IONO_BP_RUNS=1).  In the internal ray order (time
-// fastest) a voxel's sorted entry list consists of RUNS of consecutive ray numbers -- the rays of
-// one (antenna, direction) at successive times cross the same voxels; measured on the LOFAR-like
-// geometry: 8.6 entries per run -- so 4 bytes of index per entry are mostly redundant.  Per segment
-// of BP_WSEG entries the index array is replaced by a record
-//     [8 x u32 mask: bit b of word u set <=> entry 32u+b starts a run][u32 ray index of every head]
-// (entry 0 always starts a run; the record is padded to 16 bytes for the bulk copy).  The ray of
-// entry j is  head[rank(j) - 1] + (j - pos(j))  with rank = number of heads at positions <= j and pos
-// the position of the last of them: one popc and one clz on the mask word of the entry, the counts
-// of the earlier words carried along the unrolled loop.  ~9 bytes per entry instead of 12.
+// Run-compressed ray indices (the default; IONO_BP_RUNS=0 at create time keeps the plain 4-byte indices).
+// In the internal ray order (time fastest) a voxel's sorted entry list consists of RUNS of consecutive
+// ray numbers -- the rays of one (antenna, direction) at successive times cross the same voxels;
+// measured on the LOFAR-like geometry: 8.6 entries per run -- so 4 bytes of index per entry are mostly
+// redundant.  Per segment of BP_WSEG entries the index array is replaced by a record
+//     [BP_WSEG x u8 run number, lane-major: byte lane*8 + u belongs to entry 32u + lane]
+//     [n_runs x u32 base = ray index of the run's head - position of the head], padded to 16 bytes
+// and the ray of entry j is  base[run(j)] + j : one shared-memory byte extract, one table read and one add
+// per entry (a first version with a 256-bit head mask decoded by popc/clz was 0.6 B smaller per entry
+// and instruction-bound: 20 instructions per 32 entries for the decode alone).  ~9.5 B per entry
+// instead of 12.
 // ---------------------------------------------------------------------------------------------
-constexpr int BP_RUNREC_MAX = 32 + BP_WSEG * 4;   // mask + a head for every entry
+constexpr int BP_RUNREC_MAX = BP_WSEG + BP_WSEG * 4;   // run numbers + a base for every entry
 
 // head flags of segment `seg` as ballot words: lane b, word u <-> entry 32u+b
 __device__ __forceinline__ unsigned int run_head_word(const unsigned int *__restrict__ ray_idx, long long k0, int u,
@@ -431,7 +328,7 @@ __global__ void __launch_bounds__(256) run_record_units_kernel(const unsigned in
     for (long long seg = warp_global; seg < nseg; seg += n_warps) {
         int nh = 0;
         for (int u = 0; u < BP_WSEG / 32; ++u) nh += __popc(run_head_word(ray_idx, seg * BP_WSEG, u, lane));
-        if (lane == 0) units[seg] = (unsigned long long)((32 + 4 * nh + 15) / 16);
+        if (lane == 0) units[seg] = (unsigned long long)((BP_WSEG + 4 * nh + 15) / 16);
     }
     if (warp_global == 0 && lane == 0) units[nseg] = 0;
 }
@@ -444,20 +341,24 @@ __global__ void __launch_bounds__(256) run_record_fill_kernel(const unsigned int
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     for (long long seg = warp_global; seg < nseg; seg += n_warps) {
-        unsigned int *rec = reinterpret_cast<unsigned int *>(runs + run_ptr[seg] * 16ull);
-        unsigned int *heads = rec + 8;
+        unsigned char *rec = runs + run_ptr[seg] * 16ull;
+        unsigned int *bases = reinterpret_cast<unsigned int *>(rec + BP_WSEG);
         const long long k0 = seg * BP_WSEG;
         int cum = 0;
         for (int u = 0; u < BP_WSEG / 32; ++u) {
             const unsigned int m = run_head_word(ray_idx, k0, u, lane);
-            if (lane == 0) rec[u] = m;
-            if ((m >> lane) & 1u) heads[cum + __popc(m & ((1u << lane) - 1u))] = ray_idx[k0 + 32 * u + lane];
+            const int run = cum + __popc(m & (0xffffffffu >> (31 - lane))) - 1;   // heads at positions <= mine
+            rec[lane * 8 + u] = (unsigned char)run;
+            if ((m >> lane) & 1u) bases[run] = ray_idx[k0 + 32 * u + lane] - (unsigned int)(32 * u + lane);
             cum += __popc(m);
         }
     }
 }
 
-// backproject_wsegments_kernel with the ray indices reconstructed from the run records.
+// backproject_wsegments_kernel with the ray indices reconstructed from the run records, the row tables
+// of the NEXT segment and the record offsets of the one after prefetched into registers (the dependent
+// seg_rows -> ptr / row_voxel -> scale loads otherwise sit exposed at the head of every segment), and
+// 32-bit offsets relative to the segment in the row loop.
 __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__restrict__ seg_rows,
                                                                  const long long *__restrict__ ptr,
                                                                  const unsigned int *__restrict__ row_voxel,
@@ -479,59 +380,80 @@ __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__re
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
+    if (gw >= nseg) return;
     const uint64_t pol = policy_evict_first();
-    auto issue = [&](long long seg, int buf) {
+    auto issue = [&](long long seg, int buf, unsigned long long u0, unsigned long long u1) {
         if (lane == 0) {
-            const unsigned long long u0 = __ldg(run_ptr + seg), u1 = __ldg(run_ptr + seg + 1);
             const unsigned int rec_bytes = (unsigned int)(u1 - u0) * 16u;
             mbar_expect_tx(&bar[buf], BP_WSEG * 8 + rec_bytes);
             bulk_g2s(mine + buf * STAGE, weight + seg * BP_WSEG, BP_WSEG * 8, &bar[buf], pol);
             bulk_g2s(mine + buf * STAGE + BP_WSEG * 8, runs + u0 * 16ull, rec_bytes, &bar[buf], pol);
         }
     };
-    if (gw < nseg) issue(gw, 0);
+    // row table of up to 31 rows starting at row `first`: lane q holds ptr[first + q] (q <= n) and the voxel (q < n)
+    auto load_rows = [&](int first, int n, long long &p, unsigned int &vox) {
+        p = 0; vox = 0;
+        if (lane <= min(n, 31)) p = __ldg(ptr + first + lane);
+        if (lane < min(n, 31)) vox = __ldg(row_voxel + first + lane);
+    };
+    // software pipeline: rr/rr1 = row ranges of this and the next segment, (v0,v1) = record offsets of the next
+    int2 rr = __ldg(seg_rows + gw);
+    int2 rr1 = make_int2(0, -1);
+    unsigned long long v0 = 0, v1 = 0;
+    issue(gw, 0, __ldg(run_ptr + gw), __ldg(run_ptr + gw + 1));
+    if (gw + gstride < nseg) {
+        rr1 = __ldg(seg_rows + gw + gstride);
+        v0 = __ldg(run_ptr + gw + gstride);
+        v1 = __ldg(run_ptr + gw + gstride + 1);
+    }
+    long long myptr;
+    unsigned int myvox;
+    load_rows(rr.x, rr.y - rr.x + 1, myptr, myvox);
     unsigned int phase = 0;
     int buf = 0;
     constexpr int PER = BP_WSEG / 32;
     for (long long seg = gw; seg < nseg; seg += gstride, buf ^= 1) {
-        const long long k0 = seg * BP_WSEG, k1 = min(k0 + (long long)BP_WSEG, nnz);
-        const int2 rr = __ldg(seg_rows + seg);
-        if (seg + gstride < nseg) issue(seg + gstride, buf ^ 1);
-        const int n_rows = rr.y - rr.x + 1;
-        long long myptr = 0;
-        unsigned int myvox = 0;
-        double myscale = 1.0;
-        if (lane <= min(n_rows, 31)) myptr = __ldg(ptr + rr.x + lane);
-        if (lane < min(n_rows, 31)) {
-            myvox = __ldg(row_voxel + rr.x + lane);
-            if (scale) myscale = __ldg(scale + myvox);
+        const long long k0 = seg * BP_WSEG;
+        const int kend = (int)(min(k0 + (long long)BP_WSEG, nnz) - k0);
+        const long long nxt = seg + gstride, nxt2 = nxt + gstride;
+        if (nxt < nseg) issue(nxt, buf ^ 1, v0, v1);
+        // prefetches: rows of the next segment, row range and record offsets of the one after
+        long long nptr = 0;
+        unsigned int nvox = 0;
+        if (nxt < nseg) load_rows(rr1.x, rr1.y - rr1.x + 1, nptr, nvox);
+        int2 rr2 = make_int2(0, -1);
+        unsigned long long w0 = 0, w1 = 0;
+        if (nxt2 < nseg) {
+            rr2 = __ldg(seg_rows + nxt2);
+            w0 = __ldg(run_ptr + nxt2);
+            w1 = __ldg(run_ptr + nxt2 + 1);
         }
+        const int n_rows = rr.y - rr.x + 1;
+        double myscale = 1.0;
+        if (scale && lane < min(n_rows, 31)) myscale = __ldg(scale + myvox);
+        // start of row q relative to the segment, clipped to [-1, BP_WSEG + 1] (-1: begins before the segment)
+        int pb = (int)max(min(myptr - k0, (long long)(BP_WSEG + 1)), -1LL);
         mbar_wait(&bar[buf], (phase >> buf) & 1u);
         phase ^= 1u << buf;
         double *prod = reinterpret_cast<double *>(mine + buf * STAGE);
-        const unsigned int *mk = reinterpret_cast<const unsigned int *>(mine + buf * STAGE + BP_WSEG * 8);
-        const unsigned int *heads = mk + 8;
+        const unsigned char *rec = mine + buf * STAGE + BP_WSEG * 8;
+        const uint2 idw = *reinterpret_cast<const uint2 *>(rec + lane * 8);
+        const unsigned int *bases = reinterpret_cast<const unsigned int *>(rec + BP_WSEG);
         double c[PER];
-        int cum = 0, lastpos = 0;
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
-            const unsigned int m = mk[u];
-            const unsigned int mle = m & (0xffffffffu >> (31 - lane));   // heads at positions <= mine in this word
-            const int rank = cum + __popc(mle);
-            const int pos = mle ? (32 * u + 31 - __clz(mle)) : lastpos;
-            c[u] = __ldg(coef + (heads[rank - 1] + (unsigned int)(32 * u + lane - pos)));
-            cum += __popc(m);
-            if (m) lastpos = 32 * u + 31 - __clz(m);
+            const unsigned int run = ((u < 4 ? idw.x : idw.y) >> (8 * (u & 3))) & 0xffu;
+            c[u] = __ldg(coef + (bases[run] + (unsigned int)(32 * u + lane)));
         }
         if (n_rows == 1) {
             double s = 0.0;
 #pragma unroll
             for (int u = 0; u < PER; ++u) s = fma(prod[lane + u * 32], c[u], s);   // padding has weight 0
             s = warp_sum(s);
-            const long long b = __shfl_sync(0xffffffffu, myptr, 0), e = __shfl_sync(0xffffffffu, myptr, 1);
+            const int b = __shfl_sync(0xffffffffu, pb, 0), e = __shfl_sync(0xffffffffu, pb, 1);
             if (lane == 0) {
-                if (b >= k0 && e <= k1) out[myvox] = s * myscale;
-                else partial[2 * seg + (b > k0 ? 1 : 0)] = s;
+                if (b >= 0 && e <= kend) out[myvox] = s * myscale;
+                else partial[2 * seg + (b > 0 ? 1 : 0)] = s;
             }
         } else {
 #pragma unroll
@@ -542,29 +464,29 @@ __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__re
                 const int nb = min(n_rows - r0, 31);
                 double mysum = 0.0;
                 for (int q = 0; q < nb; ++q) {
-                    const long long b = __shfl_sync(0xffffffffu, myptr, q), e = __shfl_sync(0xffffffffu, myptr, q + 1);
-                    const int lo = (int)(max(b, k0) - k0), hi = (int)(min(e, k1) - k0);
+                    const int b = __shfl_sync(0xffffffffu, pb, q), e = __shfl_sync(0xffffffffu, pb, q + 1);
+                    const int lo = max(b, 0), hi = min(e, kend);
                     double s = 0.0;
                     for (int j = lo + lane; j < hi; j += 32) s += prod[j];
                     s = warp_sum(s);
                     if (lane == q) mysum = s;
                 }
-                const long long mye = __shfl_down_sync(0xffffffffu, myptr, 1);
+                const int mye = __shfl_down_sync(0xffffffffu, pb, 1);
                 if (lane < nb) {
-                    if (myptr >= k0 && mye <= k1) out[myvox] = mysum * myscale;
-                    else partial[2 * seg + (myptr > k0 ? 1 : 0)] = mysum;
+                    if (pb >= 0 && mye <= kend) out[myvox] = mysum * myscale;
+                    else partial[2 * seg + (pb > 0 ? 1 : 0)] = mysum;
                 }
                 r0 += nb;
                 if (r0 >= n_rows) break;
-                myptr = 0; myvox = 0; myscale = 1.0;
-                if (lane <= min(n_rows - r0, 31)) myptr = __ldg(ptr + rr.x + r0 + lane);
-                if (lane < min(n_rows - r0, 31)) {
-                    myvox = __ldg(row_voxel + rr.x + r0 + lane);
-                    if (scale) myscale = __ldg(scale + myvox);
-                }
+                // next batch of rows (segments made of many tiny rows): loaded on demand
+                load_rows(rr.x + r0, n_rows - r0, myptr, myvox);
+                myscale = 1.0;
+                if (scale && lane < min(n_rows - r0, 31)) myscale = __ldg(scale + myvox);
+                pb = (int)max(min(myptr - k0, (long long)(BP_WSEG + 1)), -1LL);
             }
         }
         __syncwarp();
+        rr = rr1; rr1 = rr2; v0 = w0; v1 = w1; myptr = nptr; myvox = nvox;
     }
 }
 
@@ -680,8 +602,7 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
 
     iono_backprojector *h = new iono_backprojector();
     for (int c = 0; c <= 16; ++c) { h->chunk_seg[c] = 0; h->chunk_row[c] = 0; h->chunk_vox[c] = (c == 16) ? V : 0; h->chunk_short[c] = 0; h->chunk_vlong[c] = 0; }
-    h->seg = BP_WSEG;   // warp-private segments (default); IONO_BP_SEG=1024|2048 selects the CTA-segment kernel
-    if (const char *es = getenv("IONO_BP_SEG")) h->seg = (atoi(es) == 2048) ? 2048 : (atoi(es) == 1024 ? 1024 : BP_WSEG);
+    h->seg = BP_WSEG;
     const int BP_SEG = h->seg;
     h->ray_idx = nullptr; h->weight = nullptr; h->ptr = nullptr; h->row_voxel = nullptr; h->n_rows = 0; h->long_rows = nullptr; h->n_long = 0; h->vlong_rows = nullptr; h->n_vlong = 0; h->partial = nullptr; h->items = nullptr;
     h->nnz = 0; h->V = V; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->coef_perm = nullptr;
@@ -713,10 +634,12 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
         BP_TRY(cudaMalloc(&k1, N * 8));
         BP_TRY(cudaMalloc(&v1, N * 8));
         const int ctas = sm_count() * 8;
-        if (grid->uniform)
-            emit_entries_kernel<true><<<ctas, 256, 0, st>>>(grid->dev, rays, (int)R, Nt, Nd, Ns, k0, v0, oob_count);
+        if (grid->exact)
+            emit_entries_kernel<2><<<ctas, 256, 0, st>>>(grid->dev, rays, (int)R, Nt, Nd, Ns, k0, v0, oob_count);
+        else if (grid->uniform)
+            emit_entries_kernel<1><<<ctas, 256, 0, st>>>(grid->dev, rays, (int)R, Nt, Nd, Ns, k0, v0, oob_count);
         else
-            emit_entries_kernel<false><<<ctas, 256, 0, st>>>(grid->dev, rays, (int)R, Nt, Nd, Ns, k0, v0, oob_count);
+            emit_entries_kernel<0><<<ctas, 256, 0, st>>>(grid->dev, rays, (int)R, Nt, Nd, Ns, k0, v0, oob_count);
         BP_TRY(cudaGetLastError());
         // sort by (voxel, ray): only the populated key bits
         int rbits = 1, vbits = 1;
@@ -847,7 +770,7 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
         }
         // optional: run-compressed ray indices for the warp-private apply
         const char *er = getenv("IONO_BP_RUNS");
-        if (er && atoi(er) == 1 && BP_SEG == BP_WSEG && nseg > 0) {
+        if (!(er && atoi(er) == 0) && nseg > 0) {
             BP_TRY(cudaMalloc(&h->run_ptr, (size_t)(nseg + 1) * sizeof(unsigned long long)));
             run_record_units_kernel<<<ew_grid(nseg * 32), 256, 0, st>>>(h->ray_idx, nseg, h->run_ptr);
             BP_TRY(cudaGetLastError());
@@ -893,71 +816,62 @@ static cudaError_t bp_combine(iono_backprojector_t h, const double *scale, doubl
 // coefficients, so the chunks of one apply must be issued in increasing order on one stream.  After the
 // call, out[chunk_voxels(c0) : chunk_voxels(c1)) is final -- the caller may start summing that
 // slice across GPUs while the next chunks are computed.
-extern "C" int iono_backprojector_apply_chunks_f64(iono_backprojector_t h, const double *coef, const double *scale,
-                                                   double *out, int c0, int c1, void *stream) {
+static int bp_apply_chunks(iono_backprojector_t h, const double *coef, bool permuted, const double *scale,
+                           double *out, int c0, int c1, cudaStream_t st) {
     if (!h || !out || (h->R > 0 && !coef) || c0 < 0 || c1 > 16 || c0 >= c1)
-        return fail(IONO_EBADARG, "iono_backprojector_apply_chunks_f64: bad argument");
+        return fail(IONO_EBADARG, "iono_backprojector_apply: bad argument");
     if (device_check(h->device, "iono_backprojector_apply")) return IONO_EBADARG;
-    cudaStream_t st = (cudaStream_t)stream;
     const int ctas = sm_count() * 8;
     if (c0 == 0) {
         CU_CHECK(cudaMemsetAsync(out, 0, (size_t)h->V * sizeof(double), st));   // voxels no ray touches
         if (h->nnz == 0) return IONO_OK;
-        permute_coef_kernel<<<ctas, 256, 0, st>>>(coef, h->Na, h->Nt, h->Nd, h->coef_perm);
-        CU_CHECK(cudaGetLastError());
+        if (!permuted) {
+            permute_coef_kernel<<<ctas, 256, 0, st>>>(coef, h->Na, h->Nt, h->Nd, h->coef_perm);
+            CU_CHECK(cudaGetLastError());
+        }
     }
     if (h->nnz == 0) return IONO_OK;
-    const int BP_SEG = h->seg;
+    const double *coef_int = permuted ? coef : h->coef_perm;
     const long long sb = h->chunk_seg[c0], se = h->chunk_seg[c1];
     const long long nseg = se - sb;
     if (nseg > 0) {
-        if (BP_SEG == BP_WSEG) {
-            int warps = 8, per_sm = 4;
-            if (const char *ew = getenv("IONO_BP_WARPS")) warps = atoi(ew);
-            if (const char *ec = getenv("IONO_BP_CTAS")) per_sm = atoi(ec);
-            if (warps < 1 || warps > 8) warps = 8;
-            const int smem = warps * 2 * BP_WSEG * 12 + warps * 16 + 64;
-            const long long cap = (long long)sm_count() * per_sm;
-            const long long want = (nseg + warps - 1) / warps;
-            if (h->use_runs) {
-                const int smem_r = warps * 2 * (BP_WSEG * 8 + BP_RUNREC_MAX) + warps * 16 + 64;
-                CU_CHECK(cudaFuncSetAttribute(backproject_wruns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
-                backproject_wruns_kernel<<<(int)(want < cap ? want : cap), warps * 32, smem_r, st>>>(
-                    h->items, h->ptr, h->row_voxel, h->runs, h->run_ptr, h->weight, h->coef_perm, scale, h->nnz, sb, se,
-                    out, h->partial);
-                CU_CHECK(cudaGetLastError());
-                CU_CHECK(bp_combine(h, scale, out, c0, c1, st));
-                return IONO_OK;
-            }
-            CU_CHECK(cudaFuncSetAttribute(backproject_wsegments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            backproject_wsegments_kernel<<<(int)(want < cap ? want : cap), warps * 32, smem, st>>>(
-                h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, sb, se, out,
-                h->partial);
+        int warps = 8, per_sm = 4;
+        if (const char *ew = getenv("IONO_BP_WARPS")) warps = atoi(ew);
+        if (const char *ec = getenv("IONO_BP_CTAS")) per_sm = atoi(ec);
+        if (warps < 1 || warps > 8) warps = 8;
+        if (per_sm < 1) per_sm = 1;
+        const long long cap = (long long)sm_count() * per_sm;
+        const long long want = (nseg + warps - 1) / warps;
+        const int ctas_seg = (int)(want < cap ? want : cap);
+        if (h->use_runs) {
+            const int smem_r = warps * 2 * (BP_WSEG * 8 + BP_RUNREC_MAX) + warps * 16 + 64;
+            CU_CHECK(cudaFuncSetAttribute(backproject_wruns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
+            backproject_wruns_kernel<<<ctas_seg, warps * 32, smem_r, st>>>(
+                h->items, h->ptr, h->row_voxel, h->runs, h->run_ptr, h->weight, coef_int, scale, h->nnz, sb, se,
+                out, h->partial);
         } else {
-            const int bp_smem_bytes = 2 * BP_SEG * 12 + 16 + 64 + 16;
-            int per_sm = (227 * 1024) / (bp_smem_bytes + 1024);
-            if (per_sm > 8) per_sm = 8;
-            if (const char *ec = getenv("IONO_BP_CTAS")) per_sm = atoi(ec);
-            const long long cap = (long long)sm_count() * per_sm;
-            const int ctas_seg = (int)(nseg < cap ? nseg : cap);
-            if (BP_SEG == 2048) {
-                CU_CHECK(cudaFuncSetAttribute(backproject_segments_kernel<2048>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, bp_smem_bytes));
-                backproject_segments_kernel<2048><<<ctas_seg, 256, bp_smem_bytes, st>>>(
-                    h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, sb, se, out,
-                    h->partial);
-            } else {
-                CU_CHECK(cudaFuncSetAttribute(backproject_segments_kernel<1024>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, bp_smem_bytes));
-                backproject_segments_kernel<1024><<<ctas_seg, 256, bp_smem_bytes, st>>>(
-                    h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, h->coef_perm, scale, h->nnz, sb, se, out,
-                    h->partial);
-            }
+            const int smem = warps * 2 * BP_WSEG * 12 + warps * 16 + 64;
+            CU_CHECK(cudaFuncSetAttribute(backproject_wsegments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            backproject_wsegments_kernel<<<ctas_seg, warps * 32, smem, st>>>(
+                h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, coef_int, scale, h->nnz, sb, se, out,
+                h->partial);
         }
         CU_CHECK(cudaGetLastError());
     }
     CU_CHECK(bp_combine(h, scale, out, c0, c1, st));
     return IONO_OK;
+}
+
+extern "C" int iono_backprojector_apply_chunks_f64(iono_backprojector_t h, const double *coef, const double *scale,
+                                                   double *out, int c0, int c1, void *stream) {
+    return bp_apply_chunks(h, coef, false, scale, out, c0, c1, (cudaStream_t)stream);
+}
+
+// `coef_perm` already in the operator's internal ray order (antenna, direction, time) -- what
+// iono_residual_f64 writes -- so no permutation pass; chunks as above.
+extern "C" int iono_backprojector_apply_permuted_f64(iono_backprojector_t h, const double *coef_perm,
+                                                     const double *scale, double *out, int c0, int c1, void *stream) {
+    return bp_apply_chunks(h, coef_perm, true, scale, out, c0, c1, (cudaStream_t)stream);
 }
 
 extern "C" long long iono_backprojector_chunk_voxels(iono_backprojector_t h, int c) {

@@ -67,7 +67,8 @@ struct iono_grid {
     Grid dev;          // by-value kernel argument
     double2 *tables;   // one allocation, x|y|z
     int nx, ny, nz;
-    int uniform;
+    int uniform;       // all axes: direct cell index (tables in shared memory)
+    int exact;         // all axes: exact linspace, in-cell coordinate by arithmetic (no tables in the sweep)
     int device;
 };
 
@@ -84,6 +85,17 @@ static bool axis_uniform(const double *g, int n) {
     for (int i = 0; i < n; ++i)
         if (fabs(g[i] - (g[0] + i * d)) > 0.25 * d) return false;
     return true;
+}
+
+// exact <=> every node equals g0 + i*d to within a few ulps of the axis extent (what np.linspace
+// produces): the in-cell coordinate (x - g[i])/(g[i+1] - g[i]) may then be computed as
+// frac((x - g0)/d) with an absolute error of ~1e-13, without reading the node table.
+static bool axis_exact(const double *g, int n) {
+    const double d = (g[n - 1] - g[0]) / (n - 1);
+    const double tol = 8.0 * 2.220446049250313e-16 * fmax(fabs(g[0]), fabs(g[n - 1]));
+    for (int i = 0; i < n; ++i)
+        if (fabs(g[i] - (g[0] + i * d)) > tol) return false;
+    return !getenv("IONO_NO_EXACT_AXES");
 }
 
 extern "C" int iono_grid_create(const double *xv, const double *yv, const double *zv, int nx, int ny, int nz,
@@ -106,6 +118,7 @@ extern "C" int iono_grid_create(const double *xv, const double *yv, const double
     cudaError_t e = cudaMalloc(&h->tables, total * sizeof(double2));
     if (e != cudaSuccess) { delete h; return fail(IONO_ECUDA, "cudaMalloc(grid tables): %s", cudaGetErrorString(e)); }
     h->uniform = 1;
+    h->exact = 1;
     for (int a = 0; a < 3; ++a) {
         Axis &A = h->dev.ax[a];
         for (int i = 0; i < n[a]; ++i) {
@@ -115,11 +128,13 @@ extern "C" int iono_grid_create(const double *xv, const double *yv, const double
         A.tab = h->tables + off;
         A.n = n[a];
         A.uniform = axis_uniform(g[a], n[a]) ? 1 : 0;
+        A.exact = (A.uniform && axis_exact(g[a], n[a])) ? 1 : 0;
         A.inv_d = (n[a] - 1) / (g[a][n[a] - 1] - g[a][0]);
         A.c_guess = -g[a][0] * A.inv_d - 0.5;
         A.g0 = g[a][0];
         A.glast = g[a][n[a] - 1];
         h->uniform &= A.uniform;
+        h->exact &= A.exact;
         off += n[a];
     }
     e = cudaMemcpy(h->tables, host.data(), total * sizeof(double2), cudaMemcpyHostToDevice);
@@ -152,6 +167,29 @@ __global__ void __launch_bounds__(256) mul_kernel(const double *__restrict__ a, 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = a[i] * b[i];
 }
 
+// Quad layout (iono_device.cuh): q[v] = { f[v], f[v + dz], f[v + dy], f[v + dy + dz] } with the +1 steps in
+// z and y clamped at the last node.  `m` != NULL: f = exp(m) * scale, computed on the fly (and written to
+// ne_out if that is given), so that one launch turns the model into both layouts.
+__global__ void __launch_bounds__(256) quads_kernel(const double *__restrict__ f, const double *__restrict__ m,
+                                                     double scale, int ny, int nz, int64_t n,
+                                                     double *__restrict__ ne_out, double4 *__restrict__ q) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        const int iz = (int)(v % nz);
+        const int iy = (int)((v / nz) % ny);
+        const int64_t dz = (iz + 1 < nz) ? 1 : 0, dy = (iy + 1 < ny) ? nz : 0;
+        double a, b, c, d;
+        if (m) {
+            a = exp(m[v]) * scale; b = exp(m[v + dz]) * scale;
+            c = exp(m[v + dy]) * scale; d = exp(m[v + dy + dz]) * scale;
+            if (ne_out) ne_out[v] = a;
+        } else {
+            a = f[v]; b = f[v + dz]; c = f[v + dy]; d = f[v + dy + dz];
+        }
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(q + v), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+    }
+}
+
 static int ew_grid(int64_t n) {
     int64_t blocks = (n + 255) / 256;
     int64_t cap = (int64_t)sm_count() * 8;
@@ -162,6 +200,27 @@ extern "C" int iono_ne_from_m_f64(const double *m, int64_t nvox, double scale, d
     if (!m || !ne_out || nvox < 0) return fail(IONO_EBADARG, "iono_ne_from_m_f64: bad argument");
     if (nvox == 0) return IONO_OK;
     ne_from_m_kernel<<<ew_grid(nvox), 256, 0, (cudaStream_t)stream>>>(m, nvox, scale, ne_out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
+extern "C" int iono_quads_from_ne_f64(const double *ne, int nx, int ny, int nz, double *quads_out, void *stream) {
+    const int64_t n = (int64_t)nx * ny * nz;
+    if (!ne || !quads_out || nx < 1 || ny < 1 || nz < 1 || ((uintptr_t)quads_out & 31))
+        return fail(IONO_EBADARG, "iono_quads_from_ne_f64: bad argument (quads_out must be 32-byte aligned)");
+    quads_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(ne, nullptr, 1.0, ny, nz, n, nullptr,
+                                                              reinterpret_cast<double4 *>(quads_out));
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
+extern "C" int iono_ne_quads_from_m_f64(const double *m, int nx, int ny, int nz, double scale, double *ne_out,
+                                        double *quads_out, void *stream) {
+    const int64_t n = (int64_t)nx * ny * nz;
+    if (!m || !quads_out || nx < 1 || ny < 1 || nz < 1 || ((uintptr_t)quads_out & 31))
+        return fail(IONO_EBADARG, "iono_ne_quads_from_m_f64: bad argument (quads_out must be 32-byte aligned)");
+    quads_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(nullptr, m, scale, ny, nz, n, ne_out,
+                                                              reinterpret_cast<double4 *>(quads_out));
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
 }
@@ -490,6 +549,108 @@ extern "C" int iono_misfit_f64(const double *g, const double *dobs, const double
     misfit_stage1<<<blocks, 256, 0, st>>>(g, dobs, CdCt, n, scratch);
     CU_CHECK(cudaGetLastError());
     misfit_stage2<<<1, 256, 0, st>>>(scratch, blocks, out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Fused per-ray step between the forward and the adjoint: dTEC (forward_equation.py:50), weighted residual
+// and adjoint coefficients (gradient.py:33-37 + the reference-antenna term of the exact transpose), misfit
+// (line_search.py:48-49) -- one launch instead of dtec + misfit x 2 + adjoint_coef + permute_coef, with the
+// arithmetic of those kernels (bit-identical g, coef; the misfit is summed in a different, still fixed,
+// order).  A CTA owns 8 times x 32 directions and walks the antennas, so the coefficients can also be written
+// in the back-projector's internal (antenna, direction, time) order through a shared-memory transpose.
+// ---------------------------------------------------------------------------
+constexpr int RES_TT = 8, RES_TD = 32;
+
+__global__ void __launch_bounds__(256) residual_kernel(const double *__restrict__ tec, const double *__restrict__ dobs,
+                                                        const double *__restrict__ CdCt, int Na, int Nt, int Nd, int i0,
+                                                        double *__restrict__ dtec, double *__restrict__ coef,
+                                                        double *__restrict__ coef_perm, double *__restrict__ scratch,
+                                                        unsigned int *counter, double *__restrict__ out_S) {
+    __shared__ double tile[RES_TT][RES_TD + 1];
+    __shared__ bool last;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int dl = threadIdx.x >> 3, tl = threadIdx.x & 7;   // transposed role: direction, time within the tile
+    const int tiles_d = (Nd + RES_TD - 1) / RES_TD, tiles_t = (Nt + RES_TT - 1) / RES_TT;
+    const long long ntd = (long long)Nt * Nd;
+    double S = 0.0;
+    for (int b = blockIdx.x; b < tiles_d * tiles_t; b += gridDim.x) {
+        const int t0 = (b / tiles_d) * RES_TT, d0 = (b % tiles_d) * RES_TD;
+        const int t = t0 + ty, d = d0 + tx;
+        const bool ok = t < Nt && d < Nd;
+        const bool okT = (d0 + dl < Nd) && (t0 + tl < Nt);
+        const long long j = (long long)t * Nd + d;
+        const double ref = ok ? tec[(long long)i0 * ntd + j] : 0.0;
+        double sum = 0.0, dd_ref = 0.0;
+        for (int a = 0; a < Na; ++a) {
+            double dd = 0.0;
+            if (ok) {
+                const long long k = a * ntd + j;
+                const double g = tec[k] - ref;
+                const double r = g - dobs[k];
+                const double w = CdCt[k] + 1e-15;
+                dd = r / w;
+                S += r * r / w;
+                sum += dd;
+                dtec[k] = g;
+                if (a == i0) dd_ref = dd;
+                else if (coef) coef[k] = dd;
+            }
+            if (coef_perm && a != i0) {
+                __syncthreads();
+                tile[ty][tx] = dd;
+                __syncthreads();
+                if (okT) coef_perm[((long long)a * Nd + d0 + dl) * Nt + t0 + tl] = tile[tl][dl];
+            }
+        }
+        // reference antenna: c = dd - sum over antennas (the -tec[i0] term of dTEC, transposed)
+        const double c_ref = dd_ref - sum;
+        if (ok && coef) coef[(long long)i0 * ntd + j] = c_ref;
+        if (coef_perm) {
+            __syncthreads();
+            tile[ty][tx] = c_ref;
+            __syncthreads();
+            if (okT) coef_perm[((long long)i0 * Nd + d0 + dl) * Nt + t0 + tl] = tile[tl][dl];
+        }
+    }
+    // misfit: per-CTA partial, the last CTA to arrive adds the partials in CTA order
+    S = block_sum_256(S);
+    if (threadIdx.x == 0) {
+        scratch[blockIdx.x] = S;
+        __threadfence();
+        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double s = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(scratch + i);
+        s = block_sum_256(s);
+        if (threadIdx.x == 0) { out_S[0] = 0.5 * s; *counter = 0u; }
+    }
+}
+
+extern "C" int64_t iono_residual_scratch_elems(void) { return MISFIT_BLOCKS + 1; }
+
+extern "C" int iono_residual_f64(const double *tec, const double *dobs, const double *CdCt, int Na, int Nt, int Nd,
+                                 int i0, double *dtec_out, double *coef_out, double *coef_perm_out, double *scratch,
+                                 double *misfit_out, void *stream) {
+    if (Na < 0 || Nt < 0 || Nd < 0 || !scratch || !misfit_out)
+        return fail(IONO_EBADARG, "iono_residual_f64: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((long long)Na * Nt * Nd == 0) {
+        CU_CHECK(cudaMemsetAsync(misfit_out, 0, sizeof(double), st));
+        return IONO_OK;
+    }
+    if (!tec || !dobs || !CdCt || !dtec_out || i0 < 0 || i0 >= Na)
+        return fail(IONO_EBADARG, "iono_residual_f64: bad argument");
+    const int tiles = ((Nd + RES_TD - 1) / RES_TD) * ((Nt + RES_TT - 1) / RES_TT);
+    const int blocks = tiles < MISFIT_BLOCKS ? tiles : MISFIT_BLOCKS;
+    unsigned int *counter = reinterpret_cast<unsigned int *>(scratch + MISFIT_BLOCKS);
+    CU_CHECK(cudaMemsetAsync(counter, 0, sizeof(double), st));
+    residual_kernel<<<blocks, 256, 0, st>>>(tec, dobs, CdCt, Na, Nt, Nd, i0, dtec_out, coef_out, coef_perm_out, scratch,
+                                            counter, misfit_out);
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
 }

@@ -37,7 +37,7 @@ __device__ __forceinline__ long long prepared_ray_of(int q, int Na, int Nt, int 
     return ((long long)a * Nt + t) * Nd + d;
 }
 
-template <bool UNIFORM>
+template <int AXK>
 __global__ void __launch_bounds__(256) prepare_samples_kernel(Grid g, const double *__restrict__ rays, int R, int Na,
                                                                int Nt, int Nd, int Ns, int Nsp,
                                                                int *__restrict__ cell, double *__restrict__ frac,
@@ -58,16 +58,7 @@ __global__ void __launch_bounds__(256) prepare_samples_kernel(Grid g, const doub
             const double *sp = rp + 3 * Ns;
             const double px = rp[i], py = rp[Ns + i], pz = rp[2 * Ns + i];
             int ix, iy, iz;
-            locate_fast<UNIFORM>(tabx, ax, px, ix, tx);
-            locate_fast<UNIFORM>(taby, ay, py, iy, ty);
-            locate_fast<UNIFORM>(tabz, az, pz, iz, tz);
-            if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
-                bool oob = false;
-                locate_repair(tabx, ax.nm2, ax.g0, ax.glast, px, ix, tx, oob);
-                locate_repair(taby, ay.nm2, ay.g0, ay.glast, py, iy, ty, oob);
-                locate_repair(tabz, az.nm2, az.g0, az.glast, pz, iz, tz, oob);
-                n_oob += oob;
-            }
+            n_oob += locate3<AXK>(tabx, taby, tabz, ax, ay, az, px, py, pz, ix, iy, iz, tx, ty, tz);
             // neighbours outside [0, Ns) are never used by simpson_weight; clamp the reads
             w = simpson_weight(i, Ns, n_odd, sp[max(i - 2, 0)], sp[max(i - 1, 0)], sp[i], sp[min(i + 1, Ns - 1)],
                                sp[min(i + 2, Ns - 1)]);
@@ -112,7 +103,7 @@ __device__ __forceinline__ void fill_prepared(double *stage, uint64_t *bar, cons
     }
 }
 
-template <int C, bool BULK, int MAXT>
+template <int C, bool BULK, int MAXT, int LAYOUT>
 __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const double *__restrict__ frac,
                                                                     const int *__restrict__ cell,
                                                                     const double *__restrict__ field,
@@ -178,7 +169,13 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const double 
 #pragma unroll 2
             for (int jb = 0; jb < n_c; jb += 32) {
                 const int j = jb + lane;
-                if (j < n_c) acc = fma(w_[j], trilerp(field + cell_[j], sy, sx, tx_[j], ty_[j], tz_[j]), acc);
+                if (j < n_c) {
+                    if (LAYOUT == 1)
+                        acc = fma(w_[j], trilerp_quads(reinterpret_cast<const double4 *>(field) + cell_[j], sx, tx_[j],
+                                                       ty_[j], tz_[j]), acc);
+                    else
+                        acc = fma(w_[j], trilerp(field + cell_[j], sy, sx, tx_[j], ty_[j], tz_[j]), acc);
+                }
             }
             us = (us + 1 == stages) ? 0 : us + 1;
             __syncwarp();
@@ -222,12 +219,15 @@ extern "C" int iono_forwardprojector_create(iono_grid_t grid, const double *rays
             iono_forwardprojector_destroy(h);
             return fail(IONO_ECUDA, "iono_forwardprojector_create: cudaMalloc: %s", cudaGetErrorString(e));
         }
-        if (grid->uniform)
-            prepare_samples_kernel<true><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
-                                                                     h->cell, h->frac, oob_count);
+        if (grid->exact)
+            prepare_samples_kernel<2><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
+                                                                  h->cell, h->frac, oob_count);
+        else if (grid->uniform)
+            prepare_samples_kernel<1><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
+                                                                  h->cell, h->frac, oob_count);
         else
-            prepare_samples_kernel<false><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
-                                                                      h->cell, h->frac, oob_count);
+            prepare_samples_kernel<0><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
+                                                                  h->cell, h->frac, oob_count);
         e = cudaGetLastError();
         if (e != cudaSuccess) {
             iono_forwardprojector_destroy(h);
@@ -238,10 +238,10 @@ extern "C" int iono_forwardprojector_create(iono_grid_t grid, const double *rays
     return IONO_OK;
 }
 
-template <int C, bool BULK, int MAXT>
+template <int C, bool BULK, int MAXT, int LAYOUT>
 static int launch_prepared_t(iono_forwardprojector_t h, const double *ne, double *tec, int warps, int stages,
                              size_t smem, int ctas, cudaStream_t st) {
-    auto kern = prepared_forward_kernel<C, BULK, MAXT>;
+    auto kern = prepared_forward_kernel<C, BULK, MAXT, LAYOUT>;
     CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctas, warps * 32, smem, st>>>(h->frac, h->cell, ne, tec, (int)h->R, h->Na, h->Nt, h->Nd, h->Ns, h->Nsp,
                                          stages, h->nz, h->ny * h->nz);
@@ -249,12 +249,9 @@ static int launch_prepared_t(iono_forwardprojector_t h, const double *ne, double
     return IONO_OK;
 }
 
-extern "C" int iono_forwardprojector_apply_f64(iono_forwardprojector_t h, const double *ne, double *tec_out,
-                                               void *stream) {
-    if (!h || !ne || (h->R > 0 && !tec_out))
-        return fail(IONO_EBADARG, "iono_forwardprojector_apply_f64: bad argument");
-    if (device_check(h->device, "iono_forwardprojector_apply_f64")) return IONO_EBADARG;
-    cudaStream_t st = (cudaStream_t)stream;
+template <int LAYOUT>
+static int forwardprojector_apply(iono_forwardprojector_t h, const double *field, double *tec_out, cudaStream_t st) {
+    if (device_check(h->device, "iono_forwardprojector_apply")) return IONO_EBADARG;
     if (h->R == 0) return IONO_OK;
     if (h->Ns < 2) {
         CU_CHECK(cudaMemsetAsync(tec_out, 0, (size_t)h->R * sizeof(double), st));
@@ -281,13 +278,37 @@ extern "C" int iono_forwardprojector_apply_f64(iono_forwardprojector_t h, const 
     const int n_bundles = (int)((h->R + warps - 1) / warps);
     int ctas = sm_count();
     if (ctas > n_bundles) ctas = n_bundles;
-#define IONO_PREP_DISPATCH(CC, B)                                                                        \
-    do {                                                                                                 \
-        if (warps > 24) return launch_prepared_t<CC, B, 1024>(h, ne, tec_out, warps, stages, smem, ctas, st); \
-        if (warps > 16) return launch_prepared_t<CC, B, 768>(h, ne, tec_out, warps, stages, smem, ctas, st);  \
-        return launch_prepared_t<CC, B, 512>(h, ne, tec_out, warps, stages, smem, ctas, st);             \
+#define IONO_PREP_DISPATCH(CC, B)                                                                                \
+    do {                                                                                                         \
+        if (warps > 24) return launch_prepared_t<CC, B, 1024, LAYOUT>(h, field, tec_out, warps, stages, smem, ctas, st); \
+        if (warps > 16) return launch_prepared_t<CC, B, 768, LAYOUT>(h, field, tec_out, warps, stages, smem, ctas, st);  \
+        return launch_prepared_t<CC, B, 512, LAYOUT>(h, field, tec_out, warps, stages, smem, ctas, st);          \
     } while (0)
     if (chunk == 64) { if (bulk) IONO_PREP_DISPATCH(64, true); else IONO_PREP_DISPATCH(64, false); }
     else             { if (bulk) IONO_PREP_DISPATCH(128, true); else IONO_PREP_DISPATCH(128, false); }
 #undef IONO_PREP_DISPATCH
+}
+
+extern "C" int iono_forwardprojector_apply_f64(iono_forwardprojector_t h, const double *ne, double *tec_out,
+                                               void *stream) {
+    if (!h || !ne || (h->R > 0 && !tec_out))
+        return fail(IONO_EBADARG, "iono_forwardprojector_apply_f64: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->R > 0 && h->Ns >= 2) {
+        double4 *q = quads_temporary(ne, h->nx, h->ny, h->nz, h->R * h->Ns, st);
+        if (q) {
+            int rc = forwardprojector_apply<1>(h, reinterpret_cast<const double *>(q), tec_out, st);
+            cudaFreeAsync(q, st);
+            return rc;
+        }
+    }
+    return forwardprojector_apply<0>(h, ne, tec_out, st);
+}
+
+// the same on the quad layout of ne (iono_quads_from_ne_f64 / iono_ne_quads_from_m_f64)
+extern "C" int iono_forwardprojector_apply_quads_f64(iono_forwardprojector_t h, const double *quads, double *tec_out,
+                                                     void *stream) {
+    if (!h || !quads || ((uintptr_t)quads & 31) || (h->R > 0 && !tec_out))
+        return fail(IONO_EBADARG, "iono_forwardprojector_apply_quads_f64: bad argument");
+    return forwardprojector_apply<1>(h, quads, tec_out, (cudaStream_t)stream);
 }

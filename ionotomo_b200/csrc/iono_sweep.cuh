@@ -19,6 +19,7 @@
 struct SweepParams {
     Grid g;
     const double *field;   // forward: ne (nx,ny,nz)
+    const double4 *quads;  // forward, quad layout of ne (iono_device.cuh); used instead of `field` when LAYOUT == 1
     double *acc;           // adjoint: accumulator (nx,ny,nz)
     const double *rays;    // (R,4,Ns)
     const double *coef;    // adjoint: per-ray coefficient (R)
@@ -115,6 +116,61 @@ __device__ __forceinline__ void locate_repair(const double2 *__restrict__ tab, i
     oob = oob || !(x >= g0 && x <= glast);
 }
 
+// Exact-linspace axis (AXK == 2): no table read.  v = (x - g0)/d - 1/2 is rounded to the nearest integer
+// by the magic-number add, t = (v - round(v)) + 1/2.  `ir` is the unclamped index.
+__device__ __forceinline__ void locate_arith(const AxisR &a, double x, int &ir, double &t) {
+    const double v = fma(x, a.inv_d, a.c_guess);
+    const double r = v + IONO_MAGIC;
+    ir = __double2loint(r);
+    t = (v - (r - IONO_MAGIC)) + 0.5;
+}
+// 0 < t < 1 (strict; -0, +0, negatives, 1 and NaN fail): the fast path of locate_arith needs no check
+__device__ __forceinline__ bool in_open_unit(double t) {
+    return (unsigned int)__double2hiint(t) - 1u < 0x3FF00000u - 1u;
+}
+__device__ __forceinline__ void locate_arith_repair(const AxisR &a, double x, int ir, int &i, double &t, bool &oob) {
+    i = min(max(ir, 0), a.nm2);
+    if (i != ir) t = (fma(x, a.inv_d, a.c_guess) - (double)i) + 0.5;
+    oob = oob || !(x >= a.g0 && x <= a.glast);
+    if (!(x == x)) i = 0;   // NaN: any valid cell, the sample is counted as out of bounds
+}
+
+// AXK: 0 = bisection + table, 1 = direct index + table (nodes within a quarter cell of a linspace),
+//      2 = exact linspace, arithmetic only (no shared-memory table reads in the hot loop).
+// Cell (ix,iy,iz) and in-cell coordinates of one sample; returns true if the sample is outside the grid.
+template <int AXK>
+__device__ __forceinline__ bool locate3(const double2 *__restrict__ tabx, const double2 *__restrict__ taby,
+                                        const double2 *__restrict__ tabz, const AxisR &ax, const AxisR &ay,
+                                        const AxisR &az, double px, double py, double pz, int &ix, int &iy, int &iz,
+                                        double &tx, double &ty, double &tz) {
+    bool oob = false;
+    if (AXK == 2) {
+        locate_arith(ax, px, ix, tx);
+        locate_arith(ay, py, iy, ty);
+        locate_arith(az, pz, iz, tz);
+        const bool fast = in_open_unit(tx) & in_open_unit(ty) & in_open_unit(tz) &
+                          ((unsigned int)ix <= (unsigned int)ax.nm2) & ((unsigned int)iy <= (unsigned int)ay.nm2) &
+                          ((unsigned int)iz <= (unsigned int)az.nm2);
+        if (!fast) {   // on a node, at/over the grid faces, or NaN
+            const int rx = ix, ry = iy, rz = iz;
+            locate_arith_repair(ax, px, rx, ix, tx, oob);
+            locate_arith_repair(ay, py, ry, iy, ty, oob);
+            locate_arith_repair(az, pz, rz, iz, tz, oob);
+        }
+    } else {
+        locate_fast<AXK == 1>(tabx, ax, px, ix, tx);
+        locate_fast<AXK == 1>(taby, ay, py, iy, ty);
+        locate_fast<AXK == 1>(tabz, az, pz, iz, tz);
+        if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
+            // rare: a sample on a cell edge with the guess one off, on the last node, outside the grid, or NaN
+            locate_repair(tabx, ax.nm2, ax.g0, ax.glast, px, ix, tx, oob);
+            locate_repair(taby, ay.nm2, ay.g0, ay.glast, py, iy, ty, oob);
+            locate_repair(tabz, az.nm2, az.g0, az.glast, pz, iz, tz, oob);
+        }
+    }
+    return oob;
+}
+
 // Adjoint scatter of one sample per lane: a * (trilinear hat weights) into the 8 corners of
 // cell v.  Lanes hold consecutive samples of one ray, so the cell of lane l+1 is usually the
 // one directly above the cell of lane l (v+1: same column, next z node); then the upper-node
@@ -158,9 +214,22 @@ __device__ __forceinline__ double trilerp(const double *__restrict__ c, int sy, 
     return fma(tx, c1_ - c0_, c0_);
 }
 
+// same arithmetic as trilerp() on the quad layout: two 256-bit loads
+__device__ __forceinline__ double trilerp_quads(const double4 *__restrict__ q, int sxq, double tx, double ty,
+                                                double tz) {
+    double v000, v001, v010, v011, v100, v101, v110, v111;
+    ld_quad(q, v000, v001, v010, v011);
+    ld_quad(q + sxq, v100, v101, v110, v111);
+    const double c00 = fma(tz, v001 - v000, v000), c01 = fma(tz, v011 - v010, v010);
+    const double c10 = fma(tz, v101 - v100, v100), c11 = fma(tz, v111 - v110, v110);
+    const double c0_ = fma(ty, c01 - c00, c00), c1_ = fma(ty, c11 - c10, c10);
+    return fma(tx, c1_ - c0_, c0_);
+}
+
 // MODE 0: TEC forward, MODE 1: adjoint scatter, MODE 2: phase-domain integrals per frequency
 // (inversion/iterative_newton.py:108-119 and :157-179)
-template <int MODE, bool UNIFORM, int C, bool BULK, int MAXT>
+// LAYOUT 0: plain (nx,ny,nz) field, 1: quad records (MODE 0 only)
+template <int MODE, int AXK, int C, bool BULK, int MAXT, int LAYOUT>
 __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -168,17 +237,20 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
     const int stages = p.stages;
 
     // shared: [axis tables][per-warp mbarriers][per-warp stages]
+    // (no axis tables in shared memory when the in-cell coordinates come from arithmetic, AXK == 2)
     double2 *tabx = reinterpret_cast<double2 *>(smem_raw);
     double2 *taby = tabx + nx;
     double2 *tabz = taby + ny;
-    unsigned int off = ((unsigned int)(nx + ny + nz) * 16u + 127u) / 128u * 128u;
+    unsigned int off = (AXK == 2) ? 0u : ((unsigned int)(nx + ny + nz) * 16u + 127u) / 128u * 128u;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + off) + warp * stages;
     off += ((unsigned int)(nwarp * stages) * 8u + 127u) / 128u * 128u;
     unsigned char *ring = smem_raw + off + (unsigned int)(warp * stages) * StageLayout<C>::BYTES;
 
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) tabx[i] = p.g.ax[0].tab[i];
-    for (int i = threadIdx.x; i < ny; i += blockDim.x) taby[i] = p.g.ax[1].tab[i];
-    for (int i = threadIdx.x; i < nz; i += blockDim.x) tabz[i] = p.g.ax[2].tab[i];
+    if (AXK != 2) {
+        for (int i = threadIdx.x; i < nx; i += blockDim.x) tabx[i] = p.g.ax[0].tab[i];
+        for (int i = threadIdx.x; i < ny; i += blockDim.x) taby[i] = p.g.ax[1].tab[i];
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) tabz[i] = p.g.ax[2].tab[i];
+    }
     if (BULK && lane == 0)
         for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
     if (BULK) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -265,27 +337,31 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
             for (int jb = 0; jb < n_c; jb += 32) {
                 const int j = jb + lane;
                 const bool valid = j < n_c;
+#ifdef IONO_SIMPSON_SHFL
+                // abscissae s[i-2..i+2]: one shared-memory read per lane, the neighbours by shuffle, the halo
+                // (lanes 0, 1, 30, 31) by predicated reads -- 6 instead of 10 shared-memory wavefronts
+                const double s_0 = ss_[j];
+                double s_m1 = __shfl_up_sync(0xffffffffu, s_0, 1), s_m2 = __shfl_up_sync(0xffffffffu, s_0, 2);
+                double s_p1 = __shfl_down_sync(0xffffffffu, s_0, 1), s_p2 = __shfl_down_sync(0xffffffffu, s_0, 2);
+                if (lane < 2) { s_m2 = ss_[j - 2]; if (lane < 1) s_m1 = ss_[j - 1]; }
+                if (lane > 29) { s_p2 = ss_[j + 2]; if (lane > 30) s_p1 = ss_[j + 1]; }
+#endif
                 if (MODE != 1 && !valid) continue;
                 const int i = c0 + j;
                 int ix, iy, iz;
                 double tx, ty, tz;
                 const double px = sx_[j], py = sy_[j], pz = sz_[j];
-                locate_fast<UNIFORM>(tabx, ax, px, ix, tx);
-                locate_fast<UNIFORM>(taby, ay, py, iy, ty);
-                locate_fast<UNIFORM>(tabz, az, pz, iz, tz);
-                if (!(in_unit(tx) & in_unit(ty) & in_unit(tz))) {
-                    // rare: a sample on a cell edge with the guess one off, on the last node, outside
-                    // the grid, or NaN
-                    bool oob = false;
-                    locate_repair(tabx, ax.nm2, ax.g0, ax.glast, px, ix, tx, oob);
-                    locate_repair(taby, ay.nm2, ay.g0, ay.glast, py, iy, ty, oob);
-                    locate_repair(tabz, az.nm2, az.g0, az.glast, pz, iz, tz, oob);
-                    n_oob += (oob && valid);
-                }
+                const bool oob = locate3<AXK>(tabx, taby, tabz, ax, ay, az, px, py, pz, ix, iy, iz, tx, ty, tz);
+                n_oob += (oob && valid);
+#ifdef IONO_SIMPSON_SHFL
+                const double w = simpson_weight(i, Ns, n_odd, s_m2, s_m1, s_0, s_p1, s_p2);
+#else
                 const double w = simpson_weight(i, Ns, n_odd, ss_[j - 2], ss_[j - 1], ss_[j], ss_[j + 1], ss_[j + 2]);
+#endif
                 const int v = (ix * ny + iy) * nz + iz;
                 if (MODE == 0) {
-                    acc = fma(w, trilerp(p.field + v, sy, sx, tx, ty, tz), acc);
+                    if (LAYOUT == 1) acc = fma(w, trilerp_quads(p.quads + v, sx, tx, ty, tz), acc);
+                    else acc = fma(w, trilerp(p.field + v, sy, sx, tx, ty, tz), acc);
                 } else if (MODE == 2) {
                     const double ne_s = trilerp(p.field + v, sy, sx, tx, ty, tz);
                     const bool penalty = p.field2 != nullptr;
@@ -359,22 +435,41 @@ static RayOrder make_order(int order, int Na, int Nt, int Nd) {
     return o;
 }
 
-template <int MODE, bool UNIFORM, int C, bool BULK, int MAXT>
+template <int MODE, int AXK, int C, bool BULK, int MAXT, int LAYOUT>
 static int launch_sweep_t(const SweepParams &p, const SweepConfig &cfg, size_t smem, int ctas, cudaStream_t st) {
-    auto kern = ray_sweep_kernel<MODE, UNIFORM, C, BULK, MAXT>;
+    auto kern = ray_sweep_kernel<MODE, AXK, C, BULK, MAXT, LAYOUT>;
     CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctas, cfg.warps * 32, smem, st>>>(p);
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
 }
 
-template <int MODE>
+template <int MODE, int AXK, int LAYOUT>
+static int launch_sweep_a(const SweepParams &p, const SweepConfig &cfg, size_t smem, int ctas, bool bulk,
+                          cudaStream_t st) {
+    const bool wide = (MODE != 2 && cfg.warps > 16);
+    if (cfg.chunk == 64) {
+        if (bulk) return wide ? launch_sweep_t<MODE, AXK, 64, true, 768, LAYOUT>(p, cfg, smem, ctas, st)
+                              : launch_sweep_t<MODE, AXK, 64, true, 512, LAYOUT>(p, cfg, smem, ctas, st);
+        return wide ? launch_sweep_t<MODE, AXK, 64, false, 768, LAYOUT>(p, cfg, smem, ctas, st)
+                    : launch_sweep_t<MODE, AXK, 64, false, 512, LAYOUT>(p, cfg, smem, ctas, st);
+    }
+    if (bulk) return wide ? launch_sweep_t<MODE, AXK, 128, true, 768, LAYOUT>(p, cfg, smem, ctas, st)
+                          : launch_sweep_t<MODE, AXK, 128, true, 512, LAYOUT>(p, cfg, smem, ctas, st);
+    return wide ? launch_sweep_t<MODE, AXK, 128, false, 768, LAYOUT>(p, cfg, smem, ctas, st)
+                : launch_sweep_t<MODE, AXK, 128, false, 512, LAYOUT>(p, cfg, smem, ctas, st);
+}
+
+// LAYOUT 1 (quad records in p.quads) is offered for MODE 0 only
+template <int MODE, int LAYOUT>
 static int launch_sweep(SweepParams p, iono_grid_t grid, cudaStream_t st) {
     if (device_check(grid->device, "ray sweep")) return IONO_EBADARG;
     SweepConfig cfg = sweep_config(MODE, p.Ns);
     p.stages = cfg.stages;
+    const int axk = grid->exact ? 2 : (grid->uniform ? 1 : 0);
     const size_t stage_bytes = cfg.chunk == 64 ? StageLayout<64>::BYTES : StageLayout<128>::BYTES;
-    const size_t table_bytes = (((size_t)(grid->nx + grid->ny + grid->nz) * sizeof(double2)) + 127) / 128 * 128;
+    const size_t table_bytes =
+        (axk == 2) ? 0 : (((size_t)(grid->nx + grid->ny + grid->nz) * sizeof(double2)) + 127) / 128 * 128;
     auto smem_for = [&](int warps) {
         return table_bytes + (((size_t)warps * cfg.stages * sizeof(uint64_t)) + 127) / 128 * 128 +
                (size_t)warps * cfg.stages * stage_bytes;
@@ -387,20 +482,9 @@ static int launch_sweep(SweepParams p, iono_grid_t grid, cudaStream_t st) {
     const int n_bundles = (p.R + cfg.warps - 1) / cfg.warps;
     int ctas = sm_count();
     if (ctas > n_bundles) ctas = n_bundles;
-    const bool uni = grid->uniform != 0;
-#define IONO_DISPATCH4(U, CC, B)                                                              \
-    do {                                                                                      \
-        if (MODE != 2 && cfg.warps > 16) return launch_sweep_t<MODE, U, CC, B, 768>(p, cfg, smem, ctas, st); \
-        return launch_sweep_t<MODE, U, CC, B, 512>(p, cfg, smem, ctas, st);                   \
-    } while (0)
-    if (cfg.chunk == 64) {
-        if (uni) { if (bulk) IONO_DISPATCH4(true, 64, true); else IONO_DISPATCH4(true, 64, false); }
-        else     { if (bulk) IONO_DISPATCH4(false, 64, true); else IONO_DISPATCH4(false, 64, false); }
-    } else {
-        if (uni) { if (bulk) IONO_DISPATCH4(true, 128, true); else IONO_DISPATCH4(true, 128, false); }
-        else     { if (bulk) IONO_DISPATCH4(false, 128, true); else IONO_DISPATCH4(false, 128, false); }
-    }
-#undef IONO_DISPATCH4
+    if (axk == 2) return launch_sweep_a<MODE, 2, LAYOUT>(p, cfg, smem, ctas, bulk, st);
+    if (axk == 1) return launch_sweep_a<MODE, 1, LAYOUT>(p, cfg, smem, ctas, bulk, st);
+    return launch_sweep_a<MODE, 0, LAYOUT>(p, cfg, smem, ctas, bulk, st);
 }
 
 static int sweep_size_check(iono_grid_t grid, long long R, int Ns) {
@@ -411,14 +495,33 @@ static int sweep_size_check(iono_grid_t grid, long long R, int Ns) {
     return IONO_OK;
 }
 
-extern "C" int iono_tec_forward_f64(iono_grid_t grid, const double *ne, const double *rays, int Na, int Nt, int Nd,
-                                    int Ns, int order, double *tec_out, unsigned long long *oob_count,
-                                    void *stream) {
+// Policy of the plain-layout entry points: rewrite ne as quad records into a stream-ordered temporary when the
+// quad grid stays <= 512 MB and the gathers that follow are long enough to pay for it (the rewrite moves
+// 5 x the grid; IONO_FWD_LAYOUT=plain|quads overrides).  Returns NULL for "use the plain layout".
+static double4 *quads_temporary(const double *ne, int nx, int ny, int nz, long long samples, cudaStream_t st) {
+    const long long V = (long long)nx * ny * nz;
+    bool use_quads = (V <= (1LL << 24)) && (samples >= 4 * V);
+    if (const char *e = getenv("IONO_FWD_LAYOUT")) {
+        if (!strcmp(e, "plain")) use_quads = false;
+        else if (!strcmp(e, "quads")) use_quads = true;
+    }
+    if (!use_quads) return nullptr;
+    double4 *q = nullptr;
+    if (cudaMallocAsync((void **)&q, (size_t)V * sizeof(double4), st) != cudaSuccess) {
+        cudaGetLastError();   // no memory for the temporary: the plain layout works too
+        return nullptr;
+    }
+    quads_kernel<<<ew_grid(V), 256, 0, st>>>(ne, nullptr, 1.0, ny, nz, V, nullptr, q);
+    return q;
+}
+
+static int tec_forward_common(iono_grid_t grid, const double *ne, const double4 *quads, const double *rays, int Na,
+                              int Nt, int Nd, int Ns, int order, double *tec_out, unsigned long long *oob_count,
+                              cudaStream_t st, const char *what) {
     const long long R = (long long)Na * Nt * Nd;
-    if (!grid || !ne || !oob_count || Na < 0 || Nt < 0 || Nd < 0 || Ns < 1 || (R > 0 && (!rays || !tec_out)))
-        return fail(IONO_EBADARG, "iono_tec_forward_f64: bad argument");
+    if (!grid || (!ne && !quads) || !oob_count || Na < 0 || Nt < 0 || Nd < 0 || Ns < 1 || (R > 0 && (!rays || !tec_out)))
+        return fail(IONO_EBADARG, "%s: bad argument", what);
     if (sweep_size_check(grid, R, Ns)) return IONO_EBADARG;
-    cudaStream_t st = (cudaStream_t)stream;
     CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
     if (R == 0) return IONO_OK;
     if (Ns < 2) {  // simps of a single sample is 0
@@ -427,9 +530,39 @@ extern "C" int iono_tec_forward_f64(iono_grid_t grid, const double *ne, const do
     }
     SweepParams p;
     memset(&p, 0, sizeof(p));
-    p.g = grid->dev; p.field = ne; p.rays = rays; p.tec = tec_out; p.oob_count = oob_count;
+    p.g = grid->dev; p.field = ne; p.quads = quads; p.rays = rays; p.tec = tec_out; p.oob_count = oob_count;
     p.R = (int)R; p.Ns = Ns; p.order = make_order(order, Na, Nt, Nd);
-    return launch_sweep<0>(p, grid, st);
+    return quads ? launch_sweep<0, 1>(p, grid, st) : launch_sweep<0, 0>(p, grid, st);
+}
+
+// Forward on the quad layout of ne (iono_quads_from_ne_f64 / iono_ne_quads_from_m_f64).
+extern "C" int iono_tec_forward_quads_f64(iono_grid_t grid, const double *quads, const double *rays, int Na, int Nt,
+                                          int Nd, int Ns, int order, double *tec_out, unsigned long long *oob_count,
+                                          void *stream) {
+    if ((uintptr_t)quads & 31) return fail(IONO_EBADARG, "iono_tec_forward_quads_f64: quads must be 32-byte aligned");
+    return tec_forward_common(grid, nullptr, reinterpret_cast<const double4 *>(quads), rays, Na, Nt, Nd, Ns, order,
+                              tec_out, oob_count, (cudaStream_t)stream, "iono_tec_forward_quads_f64");
+}
+
+// Plain-layout entry point.  When the sweep is long enough to pay for it (IONO_FWD_LAYOUT=auto, the default),
+// ne is first rewritten as quad records into a stream-ordered temporary (4 x the grid, cudaMallocAsync) and the
+// sweep gathers from those; IONO_FWD_LAYOUT=plain keeps the 8 scalar corner loads.
+extern "C" int iono_tec_forward_f64(iono_grid_t grid, const double *ne, const double *rays, int Na, int Nt, int Nd,
+                                    int Ns, int order, double *tec_out, unsigned long long *oob_count,
+                                    void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long R = (long long)Na * Nt * Nd;
+    if (grid && ne && R > 0 && Ns >= 2) {
+        double4 *q = quads_temporary(ne, grid->nx, grid->ny, grid->nz, R * Ns, st);
+        if (q) {
+            int rc = tec_forward_common(grid, nullptr, q, rays, Na, Nt, Nd, Ns, order, tec_out, oob_count, st,
+                                        "iono_tec_forward_f64");
+            cudaFreeAsync(q, st);
+            return rc;
+        }
+    }
+    return tec_forward_common(grid, ne, nullptr, rays, Na, Nt, Nd, Ns, order, tec_out, oob_count, st,
+                              "iono_tec_forward_f64");
 }
 
 extern "C" int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
@@ -448,7 +581,7 @@ extern "C" int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na
     memset(&p, 0, sizeof(p));
     p.g = grid->dev; p.acc = acc; p.rays = rays; p.coef = coef; p.oob_count = oob_count;
     p.R = (int)R; p.Ns = Ns; p.order = make_order(order, Na, Nt, Nd);
-    return launch_sweep<1>(p, grid, st);
+    return launch_sweep<1, 0>(p, grid, st);
 }
 
 // ---------------------------------------------------------------------------
@@ -474,7 +607,7 @@ extern "C" int iono_phase_integrals_f64(iono_grid_t grid, const double *ne, cons
     p.g = grid->dev; p.field = ne; p.field2 = dmu; p.rays = rays; p.out_nf = out; p.oob_count = oob_count;
     p.R = (int)R; p.Ns = Ns; p.nf = Nf; p.order = make_order(order, Na, Nt, Nd);
     for (int f = 0; f < Nf; ++f) p.neg_inv_np[f] = -1.0 / (1.2404e-2 * freqs_host[f] * freqs_host[f]);
-    return launch_sweep<2>(p, grid, st);
+    return launch_sweep<2, 0>(p, grid, st);
 }
 
 // out[a,t,d,f] = base[a,t,f] - scale[f] * (I[a,t,d,f] - I[i0,t,d,f]),

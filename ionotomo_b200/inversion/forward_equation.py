@@ -21,6 +21,39 @@ def _ne_from_m(m_dev, K_ne):
     return ne
 
 
+def quads_alloc(shape, device):
+    """Buffer for the quad layout of an ``(nx, ny, nz)`` field (32-byte aligned: torch allocations are)."""
+    q = torch.empty(tuple(shape) + (4,), dtype=torch.float64, device=device)
+    assert q.data_ptr() % 32 == 0
+    return q
+
+
+def ne_quads_from_m(m_dev, K_ne, ne_out=None, quads_out=None, want_ne=True):
+    """``ne = K_ne exp(m)/1e13`` (forward_equation.py:41-43) in one launch as the plain grid (optional)
+    and as the quad records the forward gathers from.  Returns ``(ne or None, quads)``."""
+    nx, ny, nz = m_dev.shape
+    q = quads_out if quads_out is not None else quads_alloc(m_dev.shape, m_dev.device)
+    ne = (ne_out if ne_out is not None else torch.empty_like(m_dev)) if want_ne else None
+    _lib.call("iono_ne_quads_from_m_f64", _lib.ptr(m_dev), nx, ny, nz, float(K_ne) / TECU,
+              _lib.ptr(ne) if ne is not None else None, _lib.ptr(q), _lib.stream_ptr())
+    return ne, q
+
+
+def tec_from_quads(rays_dev, grid, quads, order="time", check_bounds=True, out=None, oob=None):
+    """``tec_from_ne`` on the quad layout of ne (``ne_quads_from_m``)."""
+    Na, Nt, Nd, four, Ns = rays_dev.shape
+    assert four == 4
+    tec = out if out is not None else torch.empty((Na, Nt, Nd), dtype=torch.float64, device=rays_dev.device)
+    if oob is None:
+        oob = torch.zeros(1, dtype=torch.int64, device=rays_dev.device)
+    _lib.call("iono_tec_forward_quads_f64", grid.handle, _lib.ptr(quads), _lib.ptr(rays_dev), Na, Nt, Nd, Ns,
+              _lib.ORDERS[order], _lib.ptr(tec), ctypes.c_void_p(oob.data_ptr()), _lib.stream_ptr())
+    if check_bounds and int(oob.item()) != 0:
+        raise ValueError("One of the requested xi is out of bounds (%d ray samples outside the grid)"
+                         % int(oob.item()))
+    return tec
+
+
 def tec_from_ne(rays_dev, grid, ne_dev, order="time", check_bounds=True):
     """Absolute TEC per ray, ``(Na, Nt, Nd)`` CUDA tensor (do_forward_equation,
     forward_equation.py:13-33).  Raises ``ValueError`` like SciPy's
@@ -72,6 +105,14 @@ class ForwardProjector(object):
         assert tuple(ne_dev.shape) == self.shape and ne_dev.is_contiguous()
         tec = out if out is not None else torch.empty(self.ray_shape, dtype=torch.float64, device=ne_dev.device)
         _lib.call("iono_forwardprojector_apply_f64", self.handle, _lib.ptr(ne_dev), _lib.ptr(tec),
+                  _lib.stream_ptr())
+        return tec
+
+    def tec_quads(self, quads, out=None):
+        """``tec`` on the quad layout of ne (``ne_quads_from_m``): no per-call rewrite of the grid."""
+        assert tuple(quads.shape) == self.shape + (4,) and quads.is_contiguous()
+        tec = out if out is not None else torch.empty(self.ray_shape, dtype=torch.float64, device=quads.device)
+        _lib.call("iono_forwardprojector_apply_quads_f64", self.handle, _lib.ptr(quads), _lib.ptr(tec),
                   _lib.stream_ptr())
         return tec
 

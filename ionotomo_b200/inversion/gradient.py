@@ -30,6 +30,30 @@ def adjoint_coefficients(g, dobs, CdCt, i0):
     return coef
 
 
+def residual(tec, dobs, CdCt, i0, want_coef=True, want_perm=False, out=None):
+    """Everything between the forward and the adjoint in one launch (``iono_residual_f64``):
+    ``dtec = tec - tec[i0]``, the misfit ``S`` (0-d CUDA tensor), the adjoint coefficients in the natural
+    ``(Na,Nt,Nd)`` order (``want_coef``) and/or in the back-projector's internal (antenna, direction, time)
+    order (``want_perm``, for ``BackProjector.apply_permuted``).  ``out``: optional dict of preallocated
+    buffers ``dtec, coef, coef_perm, scratch, S``.  Returns ``(dtec, S, coef, coef_perm)``."""
+    lib = _lib.load()
+    Na, Nt, Nd = tec.shape
+    out = out or {}
+    dev = tec.device
+    dtec = out.get("dtec") if out.get("dtec") is not None else torch.empty_like(tec)
+    coef = (out.get("coef") if out.get("coef") is not None else torch.empty_like(tec)) if want_coef else None
+    perm = (out.get("coef_perm") if out.get("coef_perm") is not None
+            else torch.empty(Na * Nt * Nd, dtype=torch.float64, device=dev)) if want_perm else None
+    scratch = out.get("scratch")
+    if scratch is None:
+        scratch = torch.empty(int(lib.iono_residual_scratch_elems()), dtype=torch.float64, device=dev)
+    S = out.get("S") if out.get("S") is not None else torch.empty(1, dtype=torch.float64, device=dev)
+    _lib.call("iono_residual_f64", _lib.ptr(tec), _lib.ptr(dobs), _lib.ptr(CdCt), Na, Nt, Nd, int(i0), _lib.ptr(dtec),
+              _lib.ptr(coef) if coef is not None else None, _lib.ptr(perm) if perm is not None else None,
+              _lib.ptr(scratch), _lib.ptr(S), _lib.stream_ptr())
+    return dtec, S[0], coef, perm
+
+
 def backproject(rays_dev, grid, coef, shape, order="time", check_bounds=True, out=None):
     """``acc[v] = sum_ray coef[ray] sum_s w_s phi_v(x_s)`` (before the ``ne[v]`` factor and
     before any cross-GPU sum)."""
@@ -92,6 +116,19 @@ class BackProjector(object):
         _lib.call("iono_backprojector_apply_f64", self.handle, _lib.ptr(coef),
                   _lib.ptr(scale) if scale is not None else None, _lib.ptr(acc), _lib.stream_ptr())
         return acc
+
+    def apply_permuted(self, coef_perm, scale=None, out=None, c0=0, c1=16):
+        """``apply`` for coefficients already in the internal (antenna, direction, time) order (``residual(...,
+        want_perm=True)``): no permutation pass.  ``c0, c1``: sixteenths of the operator (in order from 0)."""
+        assert coef_perm.numel() == self.ray_shape[0] * self.ray_shape[1] * self.ray_shape[2]
+        acc = out if out is not None else torch.empty(self.shape, dtype=torch.float64, device=coef_perm.device)
+        _lib.call("iono_backprojector_apply_permuted_f64", self.handle, _lib.ptr(coef_perm),
+                  _lib.ptr(scale) if scale is not None else None, _lib.ptr(acc), int(c0), int(c1), _lib.stream_ptr())
+        return acc
+
+    def chunk_voxels(self, c):
+        """Flat voxel index below which ``out`` is final once chunks ``[0, c)`` have been applied."""
+        return int(_lib.load().iono_backprojector_chunk_voxels(self.handle, int(c)))
 
     def apply_overlapped(self, coef, scale=None, out=None, n_chunks=4, reduce_slice=None):
         """Same result as ``apply`` followed by a sum over ranks, with the two overlapped: the

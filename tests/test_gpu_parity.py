@@ -558,10 +558,10 @@ def test_config1_golden(ib, golden):
     np.testing.assert_allclose(dtec_ref_rays, g["dtec"], rtol=0, atol=1e-10 * np.abs(g["dtec"]).max())
 
 
-@pytest.mark.parametrize("seg", ["256", "1024"])
-def test_binned_backprojector_chunked_apply(ib, seg, monkeypatch):
+@pytest.mark.parametrize("runs", ["1", "0"])
+def test_binned_backprojector_chunked_apply(ib, runs, monkeypatch):
     import torch
-    monkeypatch.setenv("IONO_BP_SEG", seg)
+    monkeypatch.setenv("IONO_BP_RUNS", runs)
     P = small_problem(79, 20, 3, 16, 64, 40, 36, 64)
     tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
     rays = ib.cast_ray((torch.as_tensor(P["origins"]).cuda(), torch.as_tensor(P["directions"]).cuda()),
@@ -687,8 +687,9 @@ def test_forward_projector_edges(ib):
 
 @pytest.mark.parametrize("shape", [(20, 3, 16, 64, 40, 36, 64), (6, 40, 5, 30, 24, 20, 30), (3, 1, 2, 9, 10, 9, 11)])
 def test_binned_backprojector_run_compressed(ib, shape, monkeypatch):
-    """IONO_BP_RUNS=1 replaces the per-entry ray index by per-segment run records; products and sums are
-    formed in the same order, so the result must be bit-identical to the plain warp-private apply."""
+    """The default operator replaces the per-entry ray index by per-segment run records (IONO_BP_RUNS=0 keeps the
+    plain 4-byte indices); products and sums are formed in the same order, so the result must be bit-identical
+    to the plain warp-private apply."""
     import torch
     Na, Nt, Nd, Ns, nx, ny, nz = shape
     P = small_problem(500 + Nt, Na, Nt, Nd, Ns, nx, ny, nz)
@@ -697,10 +698,10 @@ def test_binned_backprojector_run_compressed(ib, shape, monkeypatch):
                        ib.Fermat(tci), 1000., Ns)
     y = torch.randn(rays.shape[:3], dtype=torch.float64, device="cuda")
     scale = torch.rand(P["m"].shape, dtype=torch.float64, device="cuda")
+    monkeypatch.setenv("IONO_BP_RUNS", "0")
     ref_bp = ib.BackProjector(rays, tci)
-    monkeypatch.setenv("IONO_BP_RUNS", "1")
-    run_bp = ib.BackProjector(rays, tci)
     monkeypatch.delenv("IONO_BP_RUNS")
+    run_bp = ib.BackProjector(rays, tci)
     assert run_bp.nnz == ref_bp.nnz
     if Nt >= 16:      # runs of consecutive times exist: the records are smaller than 4 B per entry
         assert run_bp.nbytes < ref_bp.nbytes
@@ -731,3 +732,142 @@ def test_sweep_shrinks_cta_for_large_axis_tables(ib):
     lhs = float((O.tec(rays, xvec, yvec, zvec, x) * coef).sum())
     rhs = float((acc.cpu().numpy() * x).sum())
     assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), 1e-300)
+
+
+# ---------------------------------------------------------------- round 2: quad layout, arithmetic cell lookup,
+# fused residual kernel, device session
+@pytest.mark.parametrize("Ns", [2, 5, 30, 64, 128, 131])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_forward_quads_bit_identical_to_plain_layout(ib, Ns, uniform, monkeypatch):
+    """The quad records hold the same 8 corner values and trilerp_quads repeats trilerp's arithmetic: the
+    stateless sweep and the prepared forward must give the same bits with either layout, and through the
+    explicit *_quads entry points."""
+    import torch
+    from ionotomo_b200.inversion.forward_equation import ne_quads_from_m, tec_from_ne, tec_from_quads, _ne_from_m
+    P = small_problem(700 + Ns, 4, 3, 5, Ns, 13, 11, 17, uniform=uniform)
+    rays = torch.as_tensor(O.cast_ray(P["origins"], P["directions"], P["tmax"], Ns)).cuda()
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    m_dev = tci.device_M()
+    ne = _ne_from_m(m_dev, P["K_ne"])
+    monkeypatch.setenv("IONO_FWD_LAYOUT", "plain")
+    t_plain = tec_from_ne(rays, tci.grid(), ne)
+    fp = ib.ForwardProjector(rays, tci)
+    p_plain = fp.tec(ne)
+    monkeypatch.setenv("IONO_FWD_LAYOUT", "quads")
+    t_quads = tec_from_ne(rays, tci.grid(), ne)
+    p_quads = fp.tec(ne)
+    monkeypatch.delenv("IONO_FWD_LAYOUT")
+    ne2, q = ne_quads_from_m(m_dev, P["K_ne"])
+    assert torch.equal(ne2, ne)
+    # records: { f[v], f[v+dz], f[v+dy], f[v+dy+dz] }, clamped at the last node
+    f = ne.cpu().numpy()
+    fz = np.concatenate([f[:, :, 1:], f[:, :, -1:]], 2)
+    fy = np.concatenate([f[:, 1:], f[:, -1:]], 1)
+    fyz = np.concatenate([fy[:, :, 1:], fy[:, :, -1:]], 2)
+    np.testing.assert_array_equal(q.cpu().numpy(), np.stack([f, fz, fy, fyz], -1))
+    t_explicit = tec_from_quads(rays, tci.grid(), q)
+    p_explicit = fp.tec_quads(q)
+    for t in (t_quads, p_plain, p_quads, t_explicit, p_explicit):
+        assert torch.equal(t, t_plain)
+    ref = O.tec(rays.cpu().numpy(), P["xvec"], P["yvec"], P["zvec"], O.ne_from_m(P["m"], P["K_ne"]))
+    assert relerr(t_plain.cpu().numpy(), ref) < TOL
+
+
+def test_arithmetic_cell_lookup_matches_table_lookup(ib, monkeypatch):
+    """np.linspace axes take the table-free path (in-cell coordinate by arithmetic); IONO_NO_EXACT_AXES=1 at
+    grid creation keeps the node tables.  Same cells, coordinates equal to ~1e-13: forward, exact adjoint
+    and out-of-bounds detection (1 ulp outside the last node raises, the node itself does not) must agree."""
+    import torch
+    from ionotomo_b200.geometry import tri_cubic as T
+    from ionotomo_b200.inversion.gradient import backproject
+    P = small_problem(811, 5, 2, 4, 40, 21, 19, 23)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 40)
+    # samples exactly on nodes, on the first and on the last node of an axis
+    rays[0, 0, 0, 0, 3] = P["xvec"][5]
+    rays[0, 0, 1, 1, 7] = P["yvec"][0]
+    rays[1, 0, 0, 2, 39] = P["zvec"][-1]
+    rays[1, 1, 1, 0, 11] = P["xvec"][-1]
+    res = {}
+    for mode in ("exact", "table"):
+        T._grid_cache.clear()
+        if mode == "table":
+            monkeypatch.setenv("IONO_NO_EXACT_AXES", "1")
+        tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+        dtec, tec = ib.forward_equation(rays, P["K_ne"], tci, 0, return_tec=True)
+        coef = torch.as_tensor(np.random.RandomState(3).normal(size=rays.shape[:3])).cuda()
+        acc = backproject(torch.as_tensor(rays).cuda(), tci.grid(), coef, P["m"].shape).cpu().numpy()
+        bad = rays.copy()
+        bad[2, 1, 2, 0, 5] = np.nextafter(P["xvec"][-1], np.inf)
+        with pytest.raises(ValueError):
+            ib.forward_equation(bad, P["K_ne"], tci, 0)
+        bad = rays.copy()
+        bad[2, 1, 2, 2, 5] = np.nextafter(P["zvec"][0], -np.inf)
+        with pytest.raises(ValueError):
+            ib.forward_equation(bad, P["K_ne"], tci, 0)
+        bad = rays.copy()
+        bad[2, 1, 2, 1, 5] = np.nan
+        with pytest.raises(ValueError):
+            ib.forward_equation(bad, P["K_ne"], tci, 0)
+        res[mode] = (tec, acc)
+        if mode == "table":
+            monkeypatch.delenv("IONO_NO_EXACT_AXES")
+    T._grid_cache.clear()
+    ref = O.tec(rays, P["xvec"], P["yvec"], P["zvec"], O.ne_from_m(P["m"], P["K_ne"]))
+    for mode in res:
+        assert relerr(res[mode][0], ref) < TOL
+    assert relerr(res["exact"][0], res["table"][0]) < 1e-12
+    assert relerr(res["exact"][1], res["table"][1]) < 1e-12
+
+
+@pytest.mark.parametrize("shape", [(5, 3, 7), (3, 17, 70), (2, 8, 32), (62, 9, 33), (4, 1, 1)])
+@pytest.mark.parametrize("i0", [0, 1])
+def test_fused_residual_kernel(ib, shape, i0):
+    """iono_residual_f64 == dtec + misfit + adjoint coefficients (+ permutation to the back-projector's order)."""
+    import torch
+    from ionotomo_b200 import _lib
+    from ionotomo_b200.inversion.gradient import adjoint_coefficients, misfit, residual
+    Na, Nt, Nd = shape
+    rng = np.random.RandomState(Na * 100 + Nt)
+    tec = torch.as_tensor(rng.normal(size=shape) + 10.).cuda()
+    dobs = torch.as_tensor(rng.normal(size=shape)).cuda()
+    C = torch.as_tensor(rng.uniform(0.5, 2., size=shape)).cuda()
+    g0 = torch.empty_like(tec)
+    _lib.call("iono_dtec_f64", _lib.ptr(tec), Na, Nt, Nd, i0, _lib.ptr(g0), _lib.stream_ptr())
+    coef0 = adjoint_coefficients(g0, dobs, C, i0)
+    S0 = float(misfit(g0, dobs, C))
+    g1, S1, coef1, perm1 = residual(tec, dobs, C, i0, want_coef=True, want_perm=True)
+    assert torch.equal(g1, g0) and torch.equal(coef1, coef0)
+    assert torch.equal(perm1.reshape(Na, Nd, Nt), coef0.permute(0, 2, 1).contiguous())
+    assert abs(float(S1) - S0) <= 1e-13 * abs(S0)
+    tn = tec.cpu().numpy()
+    gn = tn - tn[i0]
+    assert abs(float(S1) - 0.5 * (((gn - dobs.cpu().numpy()) ** 2) / (C.cpu().numpy() + 1e-15)).sum()) <= 1e-12 * S0
+    g2, S2, coef2, perm2 = residual(tec, dobs, C, i0, want_coef=False, want_perm=True)
+    assert coef2 is None and torch.equal(perm2, perm1) and float(S2) == float(S1)     # reproducible
+
+
+@pytest.mark.parametrize("forward,adjoint", [("prepared", "binned"), ("sweep", "scatter"), ("sweep", "binned")])
+@pytest.mark.parametrize("graph", [True, False])
+def test_device_session_matches_separate_calls(ib, forward, adjoint, graph):
+    import torch
+    from ionotomo_b200.inversion.session import DeviceSession
+    P = small_problem(901, 6, 5, 7, 34, 15, 14, 18)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 34)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    g_true = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], 2)
+    dobs = g_true + 0.01 * P["rng"].normal(size=g_true.shape)
+    CdCt = np.full(g_true.shape, 1e-4)
+    ses = DeviceSession(rays, P["K_ne"], tci, 2, dobs, CdCt, forward=forward, adjoint=adjoint, use_graph=graph)
+    for k in range(3):          # first call eager (+ capture), then graph replays with a changed model
+        m = P["m"] + 0.05 * k * np.sin(np.arange(P["m"].size)).reshape(P["m"].shape)
+        S, grad = ses.misfit_and_gradient(torch.as_tensor(m).cuda())
+        g_ref = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], m, 2)
+        grad_ref = O.gradient_exact(rays, g_ref, dobs, 2, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], m, CdCt)
+        S_ref = 0.5 * ((g_ref - dobs) ** 2 / (CdCt + 1e-15)).sum()
+        tec_scale = np.abs(O.tec(rays, P["xvec"], P["yvec"], P["zvec"], O.ne_from_m(m, P["K_ne"]))).max()
+        assert np.abs(ses.dtec.cpu().numpy() - g_ref).max() < TOL * tec_scale
+        # the misfit and the coefficients amplify the forward's rounding by 1/CdCt
+        assert abs(float(S) - S_ref) <= 1e-7 * S_ref
+        assert np.abs(grad.cpu().numpy() - grad_ref).max() < 1e-7 * np.abs(grad_ref).max()
+    dtec, S2 = ses.forward(torch.as_tensor(P["m"]).cuda())
+    assert np.abs(dtec.cpu().numpy() - g_true).max() < TOL * tec_scale

@@ -143,34 +143,28 @@ def test_gaussian_adjoint_kernel_model_non_monotone_ray(golden):
 # ---------------------------------------------------------------- run-compressed ray indices
 def run_records_model(idx, seg=256):
     """run_record_units_kernel / run_record_fill_kernel (csrc/iono_backproject.cuh): per segment of `seg`
-    entries the 8 mask words (bit b of word u <-> entry 32u+b starts a run) and the ray index of every head."""
+    entries one run number per entry, stored lane-major (byte lane*8 + u <-> entry 32u + lane), and per run
+    the base = ray index of its head - position of the head (mod 2^32)."""
     recs = []
     for k0 in range(0, len(idx), seg):
-        words, heads = [], []
+        ids, bases = bytearray(seg), []
         for u in range(seg // 32):
-            m = 0
             for lane in range(32):
                 j = 32 * u + lane
                 if j == 0 or idx[k0 + j] != (idx[k0 + j - 1] + 1) & 0xffffffff:
-                    m |= 1 << lane
-                    heads.append(int(idx[k0 + j]))
-            words.append(m)
-        recs.append((words, heads))
+                    bases.append((int(idx[k0 + j]) - j) & 0xffffffff)
+                ids[lane * 8 + u] = len(bases) - 1
+        recs.append((bytes(ids), bases))
     return recs
 
 
-def run_index_model(words, heads, u, lane):
-    """Ray index of entry 32u+lane as backproject_wruns_kernel reconstructs it."""
-    cum, lastpos = 0, 0
-    for w in range(u):                       # what the unrolled loop has carried along so far
-        m = words[w]
-        cum += bin(m).count("1")
-        if m:
-            lastpos = 32 * w + m.bit_length() - 1          # 31 - clz(m)
-    mle = words[u] & (0xffffffff >> (31 - lane))
-    rank = cum + bin(mle).count("1")
-    pos = 32 * u + mle.bit_length() - 1 if mle else lastpos
-    return heads[rank - 1] + (32 * u + lane - pos)
+def run_index_model(ids, bases, u, lane):
+    """Ray index of entry 32u+lane as backproject_wruns_kernel reconstructs it: the lane's 8 run numbers are one
+    64-bit shared-memory load (two 32-bit words), byte u of them selects the base."""
+    lo = int.from_bytes(ids[lane * 8:lane * 8 + 4], "little")
+    hi = int.from_bytes(ids[lane * 8 + 4:lane * 8 + 8], "little")
+    run = ((lo if u < 4 else hi) >> (8 * (u & 3))) & 0xff
+    return (bases[run] + 32 * u + lane) & 0xffffffff
 
 
 def test_run_compressed_indices_model():
@@ -188,13 +182,12 @@ def test_run_compressed_indices_model():
     recs = run_records_model(idx)
     assert len(recs) == 5
     n_heads = 0
-    for g, (words, heads) in enumerate(recs):
-        assert words[0] & 1                                  # entry 0 of a segment always starts a run
-        assert len(heads) == sum(bin(m).count("1") for m in words) <= 256
-        n_heads += len(heads)
+    for g, (ids, bases) in enumerate(recs):
+        assert 1 <= len(bases) <= 256                        # run numbers fit a byte
+        n_heads += len(bases)
         for u in range(8):
             for lane in range(32):
-                assert run_index_model(words, heads, u, lane) == idx[g * 256 + 32 * u + lane]
+                assert run_index_model(ids, bases, u, lane) == idx[g * 256 + 32 * u + lane]
     assert n_heads < len(idx) / 4                            # the point of the format
     # record size in 16-byte units as the build computes it
-    assert all((32 + 4 * len(h) + 15) // 16 * 16 <= 32 + 256 * 4 for _, h in recs)
+    assert all((256 + 4 * len(b) + 15) // 16 * 16 <= 256 + 256 * 4 for _, b in recs)

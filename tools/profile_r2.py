@@ -1,0 +1,35 @@
+#!/usr/bin/env python
+"""ncu target (round 2): one launch of each hot kernel at the benchmark size -- stateless sweep (quad layout),
+prepared forward (quad layout), fused residual kernel, run-compressed binned adjoint, scatter adjoint.
+    NT=100 ncu --set full --clock-control none --import-source on -k regex:"ray_sweep|prepared_forward|backproject_w|residual" \
+        -o gpurun_out/prof python tools/profile_r2.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import ionotomo_b200 as ib
+from ionotomo_b200.ionosphere.synthetic import make_workload
+from ionotomo_b200.inversion.forward_equation import ForwardProjector, ne_quads_from_m, tec_from_quads
+from ionotomo_b200.inversion.gradient import BackProjector, backproject, residual
+
+nt = int(os.environ.get("NT", "100"))
+w = make_workload(Na=62, Nt=nt, Nd=200, nx=256, ny=256, nz=128, device="cuda")
+m_tci = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_prior"])
+rays = ib.cast_ray((w["origins"], w["directions"]), ib.Fermat(m_tci), w["tmax"], w["Ns"])
+ne, quads = ne_quads_from_m(m_tci.device_M(), w["K_ne"])
+fp = ForwardProjector(rays, m_tci)
+bp = BackProjector(rays, m_tci)
+dobs = torch.zeros(rays.shape[:3], dtype=torch.float64, device="cuda")
+C = torch.full_like(dobs, 1e-4)
+for _ in range(2):
+    tec = tec_from_quads(rays, m_tci.grid(), quads, check_bounds=False)
+    tec = fp.tec_quads(quads)
+    g, S, coef, perm = residual(tec, dobs, C, 0, want_coef=True, want_perm=True)
+    acc = bp.apply_permuted(perm, scale=ne)
+if os.environ.get("SCATTER", "0") == "1":
+    backproject(rays, m_tci.grid(), coef, tuple(ne.shape), check_bounds=False)
+torch.cuda.synchronize()
+print("ok", float(S))
