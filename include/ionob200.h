@@ -162,6 +162,12 @@ int iono_forwardprojector_apply_f64(iono_forwardprojector_t fp, const double *ne
                                     void *stream);
 int iono_forwardprojector_apply_quads_f64(iono_forwardprojector_t fp, const double *quads, double *tec_out,
                                           void *stream);
+/* quad records of ne = scale * exp(m) for the records this projector reads only (its rays touch a fraction
+ * of the grid; the list is assembled by create): the per-iteration replacement of iono_ne_quads_from_m_f64
+ * when this projector is the only consumer of quads_out.  Other records are left untouched. */
+int iono_forwardprojector_quads_from_m_f64(iono_forwardprojector_t fp, const double *m, double scale,
+                                           double *quads_out, void *stream);
+long long iono_forwardprojector_n_records(iono_forwardprojector_t fp);
 long long iono_forwardprojector_bytes(iono_forwardprojector_t fp);
 int iono_forwardprojector_destroy(iono_forwardprojector_t fp);
 
@@ -220,10 +226,46 @@ int iono_backprojector_apply_chunks_f64(iono_backprojector_t bp, const double *c
  * (coef_perm_out of iono_residual_f64): no permutation pass */
 int iono_backprojector_apply_permuted_f64(iono_backprojector_t bp, const double *coef_perm, const double *scale,
                                           double *out, int c0, int c1, void *stream);
+/* The voxel gradient in one call: out[v] = k * exp(m[v]) * sum_ray A[v,ray] coef[ray] -- the chain-rule factor
+ * ne[v] = K_ne exp(m[v]) / 1e13 (k = K_ne/1e13; inversion/gradient.py:49-51 with :19) is evaluated for the
+ * rows the rays touch only, so no ne grid is needed. */
+int iono_backprojector_apply_gradient_f64(iono_backprojector_t bp, const double *coef_perm, const double *m,
+                                          double k, double *out, int c0, int c1, void *stream);
+/* Sharded rays (one process per GPU): row r of this rank's operator is stored, unscaled, at
+ * out_compact[row_dst[r]]; the caller numbers the voxels that ANY rank touches consecutively (from
+ * iono_backprojector_row_voxels of every rank), clears out_compact, and sums that compact vector across
+ * ranks instead of the whole grid (reference fan-out being replaced: inversion/gradient.py:52-54 da.sum). */
+int iono_backprojector_apply_compact_f64(iono_backprojector_t bp, const double *coef_perm,
+                                         const unsigned int *row_dst, double *out_compact, int c0, int c1,
+                                         void *stream);
+long long iono_backprojector_n_rows(iono_backprojector_t bp);
+int iono_backprojector_row_voxels(iono_backprojector_t bp, unsigned int *row_voxels_out, void *stream);
 long long iono_backprojector_chunk_voxels(iono_backprojector_t bp, int c);
 long long iono_backprojector_nnz(iono_backprojector_t bp);
 long long iono_backprojector_bytes(iono_backprojector_t bp);
 int iono_backprojector_destroy(iono_backprojector_t bp);
+
+/* ---- cross-GPU sum over NVLink peer memory (one process per GPU) ---------------------------------
+ * Replaces the reference's da.sum over dask workers (inversion/gradient.py:52-54).  Buffers that peers
+ * read or write are allocated with iono_peer_alloc (cudaMalloc + zero fill + CUDA IPC handle, 64 bytes,
+ * to be sent to the other processes) and mapped on the other ranks with iono_peer_open.
+ * iono_peer_reduce_expand_f64, called by EVERY rank with the same arguments but `me`:
+ *   sum[k]   = sum over ranks r = 0..N-1 (in that order: same bits on every rank) of acc[r][k],  k < L
+ *   grad[union_voxels[k]] = k_scale * exp(m[union_voxels[k]]) * sum[k]     for k < n_union   (local grid)
+ *   misfit_out[0] = sum[n_union]                                           (if misfit_out != NULL)
+ * as ONE kernel per rank: flag handshake, reduce-scatter by peer loads, all-gather by peer stores, flag
+ * handshake, expansion.  acc, res, flags: arrays of N device pointers (index = rank; entry `me` is this
+ * rank's own allocation): compact accumulators (L doubles, L even, n_union < L), result vectors (L doubles)
+ * and flag blocks (iono_peer_flag_bytes(), zeroed).  The launch has no per-call arguments (the call
+ * counter lives in the flag block), so it can be replayed from a CUDA graph. */
+int iono_peer_alloc(int64_t bytes, void **ptr_out, void *ipc_handle_out64);
+int iono_peer_open(const void *ipc_handle64, void **ptr_out);
+int iono_peer_close(void *ptr);
+int iono_peer_free(void *ptr);
+int64_t iono_peer_flag_bytes(void);
+int iono_peer_reduce_expand_f64(void *const *acc, void *const *res, void *const *flags, int N, int me,
+                                int64_t L, const int *union_voxels, int64_t n_union, const double *m,
+                                double k_scale, double *grad, double *misfit_out, void *stream);
 
 /* ---- misfit ---------------------------------------------------------------
  * out[0] = sum((g-dobs)^2/(CdCt+1e-15))/2 (inversion/line_search.py:48-49).

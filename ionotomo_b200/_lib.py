@@ -56,13 +56,25 @@ SIGNATURES = {
     "iono_backprojector_apply_f64": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "iono_backprojector_apply_chunks_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "iono_backprojector_apply_permuted_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "iono_backprojector_apply_gradient_f64": (_i, [_vp, _vp, _vp, _d, _vp, _i, _i, _vp]),
+    "iono_backprojector_apply_compact_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "iono_backprojector_n_rows": (ctypes.c_longlong, [_vp]),
+    "iono_backprojector_row_voxels": (_i, [_vp, _vp, _vp]),
     "iono_backprojector_chunk_voxels": (ctypes.c_longlong, [_vp, _i]),
     "iono_backprojector_nnz": (ctypes.c_longlong, [_vp]),
     "iono_backprojector_bytes": (ctypes.c_longlong, [_vp]),
     "iono_backprojector_destroy": (_i, [_vp]),
+    "iono_peer_alloc": (_i, [_i64, ctypes.POINTER(_vp), _vp]),
+    "iono_peer_open": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "iono_peer_close": (_i, [_vp]),
+    "iono_peer_free": (_i, [_vp]),
+    "iono_peer_flag_bytes": (_i64, []),
+    "iono_peer_reduce_expand_f64": (_i, [_vp, _vp, _vp, _i, _i, _i64, _vp, _i64, _vp, _d, _vp, _vp, _vp]),
     "iono_forwardprojector_create": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp, _vp]),
     "iono_forwardprojector_apply_f64": (_i, [_vp, _vp, _vp, _vp]),
     "iono_forwardprojector_apply_quads_f64": (_i, [_vp, _vp, _vp, _vp]),
+    "iono_forwardprojector_quads_from_m_f64": (_i, [_vp, _vp, _d, _vp, _vp]),
+    "iono_forwardprojector_n_records": (ctypes.c_longlong, [_vp]),
     "iono_forwardprojector_bytes": (ctypes.c_longlong, [_vp]),
     "iono_forwardprojector_destroy": (_i, [_vp]),
 }
@@ -76,8 +88,10 @@ KERNEL_LAUNCHES = {
     "iono_phase_integrals_f64": 1, "iono_phase_assemble_f64": 1, "iono_chord_adjoint_f64": 1,
     "iono_gaussian_adjoint_f64": 1,
     "iono_backprojector_apply_f64": 4, "iono_backprojector_apply_chunks_f64": 3,
-    "iono_backprojector_apply_permuted_f64": 3,
+    "iono_backprojector_apply_permuted_f64": 3, "iono_backprojector_apply_gradient_f64": 3,
+    "iono_backprojector_apply_compact_f64": 3, "iono_forwardprojector_quads_from_m_f64": 1,
     "iono_forwardprojector_create": 1, "iono_forwardprojector_apply_f64": 2, "iono_forwardprojector_apply_quads_f64": 1,
+    "iono_peer_reduce_expand_f64": 1,
     "iono_quads_from_ne_f64": 1, "iono_ne_quads_from_m_f64": 1, "iono_tec_forward_quads_f64": 1, "iono_residual_f64": 1,
 }
 launch_count = 0

@@ -51,6 +51,22 @@ struct iono_backprojector {
     int use_runs;
 };
 
+// Per-row factor applied when a finished row is stored: nothing, a grid array (scale[v]), or the chain-rule
+// factor of the log-density model computed on the spot, k * exp(p[v]) (ne[v] = K_ne exp(m[v]) / 1e13) -- the
+// operator touches a fifth of the voxels, so this replaces a full-grid ne pass by ~1.6 M exps.
+// `index` (optional) replaces row_voxel as the destination index of a row: the compact accumulator of the
+// sharded adjoint (rows of all ranks numbered consecutively, ionotomo_b200/inversion/session.py).
+struct RowScale {
+    const double *p;
+    double k;
+    int mode;   // 0: 1, 1: p[v], 2: k * exp(p[v])
+};
+__device__ __forceinline__ double row_scale(const RowScale &rs, unsigned int v) {
+    if (rs.mode == 1) return __ldg(rs.p + v);
+    if (rs.mode == 2) return rs.k * exp(__ldg(rs.p + v));
+    return 1.0;
+}
+
 // Internal ray numbering of the back-projector: time fastest, (a*Nd + d)*Nt + t.  Rays of one
 // (antenna, direction) at consecutive times are nearly identical and meet in the same voxels,
 // so with this order a voxel's sorted entry list references runs of adjacent coefficients
@@ -203,7 +219,7 @@ __global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *
                                                                      const unsigned int *__restrict__ ray_idx,
                                                                      const double *__restrict__ weight,
                                                                      const double *__restrict__ coef,
-                                                                     const double *__restrict__ scale, long long nnz,
+                                                                     const RowScale scale, long long nnz,
                                                                      long long seg_begin, long long seg_end,
                                                                      double *__restrict__ out,
                                                                      double *__restrict__ partial) {
@@ -241,7 +257,7 @@ __global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *
         if (lane <= min(n_rows, 31)) myptr = __ldg(ptr + rr.x + lane);
         if (lane < min(n_rows, 31)) {
             myvox = __ldg(row_voxel + rr.x + lane);
-            if (scale) myscale = __ldg(scale + myvox);
+            myscale = row_scale(scale, myvox);
         }
         mbar_wait(&bar[buf], (phase >> buf) & 1u);
         phase ^= 1u << buf;
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *
                 if (lane <= min(n_rows - r0, 31)) myptr = __ldg(ptr + rr.x + r0 + lane);
                 if (lane < min(n_rows - r0, 31)) {
                     myvox = __ldg(row_voxel + rr.x + r0 + lane);
-                    if (scale) myscale = __ldg(scale + myvox);
+                    myscale = row_scale(scale, myvox);
                 }
             }
         }
@@ -366,7 +382,7 @@ __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__re
                                                                  const unsigned long long *__restrict__ run_ptr,
                                                                  const double *__restrict__ weight,
                                                                  const double *__restrict__ coef,
-                                                                 const double *__restrict__ scale, long long nnz,
+                                                                 const RowScale scale, long long nnz,
                                                                  long long seg_begin, long long seg_end,
                                                                  double *__restrict__ out,
                                                                  double *__restrict__ partial) {
@@ -430,7 +446,7 @@ __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__re
         }
         const int n_rows = rr.y - rr.x + 1;
         double myscale = 1.0;
-        if (scale && lane < min(n_rows, 31)) myscale = __ldg(scale + myvox);
+        if (lane < min(n_rows, 31)) myscale = row_scale(scale, myvox);
         // start of row q relative to the segment, clipped to [-1, BP_WSEG + 1] (-1: begins before the segment)
         int pb = (int)max(min(myptr - k0, (long long)(BP_WSEG + 1)), -1LL);
         mbar_wait(&bar[buf], (phase >> buf) & 1u);
@@ -481,7 +497,7 @@ __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__re
                 // next batch of rows (segments made of many tiny rows): loaded on demand
                 load_rows(rr.x + r0, n_rows - r0, myptr, myvox);
                 myscale = 1.0;
-                if (scale && lane < min(n_rows - r0, 31)) myscale = __ldg(scale + myvox);
+                if (lane < min(n_rows - r0, 31)) myscale = row_scale(scale, myvox);
                 pb = (int)max(min(myptr - k0, (long long)(BP_WSEG + 1)), -1LL);
             }
         }
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(256) backproject_combine_short_kernel(const in
                                                                          int seg, const long long *__restrict__ ptr,
                                                                          const unsigned int *__restrict__ row_voxel,
                                                                          const double *__restrict__ partial,
-                                                                         const double *__restrict__ scale,
+                                                                         const RowScale scale,
                                                                          double *__restrict__ out) {
     const int stride = gridDim.x * blockDim.x;
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
@@ -506,7 +522,7 @@ __global__ void __launch_bounds__(256) backproject_combine_short_kernel(const in
         for (long long sg = s_first; sg <= s_last; ++sg)
             s += partial[2 * sg + ((sg == s_first && b > sg * seg) ? 1 : 0)];
         const long long v = row_voxel[row];
-        out[v] = scale ? s * scale[v] : s;
+        out[v] = s * row_scale(scale, (unsigned int)v);
     }
 }
 
@@ -516,7 +532,7 @@ __global__ void __launch_bounds__(256) backproject_combine_kernel(const int *__r
                                                                    const long long *__restrict__ ptr,
                                                                    const unsigned int *__restrict__ row_voxel,
                                                                    const double *__restrict__ partial,
-                                                                   const double *__restrict__ scale,
+                                                                   const RowScale scale,
                                                                    double *__restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -532,7 +548,7 @@ __global__ void __launch_bounds__(256) backproject_combine_kernel(const int *__r
             s += partial[2 * sg + slot];
         }
         s = warp_sum(s);
-        if (lane == 0) out[v] = scale ? s * scale[v] : s;
+        if (lane == 0) out[v] = s * row_scale(scale, (unsigned int)v);
     }
 }
 
@@ -800,15 +816,15 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
 }
 
 // combine the straddling rows completed in chunks [c0, c1)
-static cudaError_t bp_combine(iono_backprojector_t h, const double *scale, double *out, int c0, int c1,
-                              cudaStream_t st) {
+static cudaError_t bp_combine(iono_backprojector_t h, const unsigned int *row_dst, const RowScale scale, double *out,
+                              int c0, int c1, cudaStream_t st) {
     const int ns = h->chunk_short[c1] - h->chunk_short[c0], nv = h->chunk_vlong[c1] - h->chunk_vlong[c0];
     if (ns > 0)
         backproject_combine_short_kernel<<<ew_grid(ns), 256, 0, st>>>(h->long_rows + h->chunk_short[c0], ns, h->seg,
-                                                                    h->ptr, h->row_voxel, h->partial, scale, out);
+                                                                    h->ptr, row_dst, h->partial, scale, out);
     if (nv > 0)
         backproject_combine_kernel<<<(nv + 7) / 8, 256, 0, st>>>(h->vlong_rows + h->chunk_vlong[c0], nv, h->seg, h->ptr,
-                                                                 h->row_voxel, h->partial, scale, out);
+                                                                 row_dst, h->partial, scale, out);
     return cudaGetLastError();
 }
 
@@ -816,14 +832,16 @@ static cudaError_t bp_combine(iono_backprojector_t h, const double *scale, doubl
 // coefficients, so the chunks of one apply must be issued in increasing order on one stream.  After the
 // call, out[chunk_voxels(c0) : chunk_voxels(c1)) is final -- the caller may start summing that
 // slice across GPUs while the next chunks are computed.
-static int bp_apply_chunks(iono_backprojector_t h, const double *coef, bool permuted, const double *scale,
-                           double *out, int c0, int c1, cudaStream_t st) {
+// row_dst == NULL: rows are stored at their voxel index and `out` (V doubles) is cleared first;
+// row_dst != NULL: row r is stored at out[row_dst[r]] and the caller has cleared `out`.
+static int bp_apply_chunks(iono_backprojector_t h, const double *coef, bool permuted, const RowScale scale,
+                           const unsigned int *row_dst, double *out, int c0, int c1, cudaStream_t st) {
     if (!h || !out || (h->R > 0 && !coef) || c0 < 0 || c1 > 16 || c0 >= c1)
         return fail(IONO_EBADARG, "iono_backprojector_apply: bad argument");
     if (device_check(h->device, "iono_backprojector_apply")) return IONO_EBADARG;
     const int ctas = sm_count() * 8;
     if (c0 == 0) {
-        CU_CHECK(cudaMemsetAsync(out, 0, (size_t)h->V * sizeof(double), st));   // voxels no ray touches
+        if (!row_dst) CU_CHECK(cudaMemsetAsync(out, 0, (size_t)h->V * sizeof(double), st));   // voxels no ray touches
         if (h->nnz == 0) return IONO_OK;
         if (!permuted) {
             permute_coef_kernel<<<ctas, 256, 0, st>>>(coef, h->Na, h->Nt, h->Nd, h->coef_perm);
@@ -832,6 +850,7 @@ static int bp_apply_chunks(iono_backprojector_t h, const double *coef, bool perm
     }
     if (h->nnz == 0) return IONO_OK;
     const double *coef_int = permuted ? coef : h->coef_perm;
+    const unsigned int *dst = row_dst ? row_dst : h->row_voxel;
     const long long sb = h->chunk_seg[c0], se = h->chunk_seg[c1];
     const long long nseg = se - sb;
     if (nseg > 0) {
@@ -847,31 +866,61 @@ static int bp_apply_chunks(iono_backprojector_t h, const double *coef, bool perm
             const int smem_r = warps * 2 * (BP_WSEG * 8 + BP_RUNREC_MAX) + warps * 16 + 64;
             CU_CHECK(cudaFuncSetAttribute(backproject_wruns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
             backproject_wruns_kernel<<<ctas_seg, warps * 32, smem_r, st>>>(
-                h->items, h->ptr, h->row_voxel, h->runs, h->run_ptr, h->weight, coef_int, scale, h->nnz, sb, se,
+                h->items, h->ptr, dst, h->runs, h->run_ptr, h->weight, coef_int, scale, h->nnz, sb, se,
                 out, h->partial);
         } else {
             const int smem = warps * 2 * BP_WSEG * 12 + warps * 16 + 64;
             CU_CHECK(cudaFuncSetAttribute(backproject_wsegments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             backproject_wsegments_kernel<<<ctas_seg, warps * 32, smem, st>>>(
-                h->items, h->ptr, h->row_voxel, h->ray_idx, h->weight, coef_int, scale, h->nnz, sb, se, out,
+                h->items, h->ptr, dst, h->ray_idx, h->weight, coef_int, scale, h->nnz, sb, se, out,
                 h->partial);
         }
         CU_CHECK(cudaGetLastError());
     }
-    CU_CHECK(bp_combine(h, scale, out, c0, c1, st));
+    CU_CHECK(bp_combine(h, dst, scale, out, c0, c1, st));
     return IONO_OK;
 }
 
 extern "C" int iono_backprojector_apply_chunks_f64(iono_backprojector_t h, const double *coef, const double *scale,
                                                    double *out, int c0, int c1, void *stream) {
-    return bp_apply_chunks(h, coef, false, scale, out, c0, c1, (cudaStream_t)stream);
+    return bp_apply_chunks(h, coef, false, RowScale{scale, 1.0, scale ? 1 : 0}, nullptr, out, c0, c1, (cudaStream_t)stream);
 }
 
 // `coef_perm` already in the operator's internal ray order (antenna, direction, time) -- what
 // iono_residual_f64 writes -- so no permutation pass; chunks as above.
 extern "C" int iono_backprojector_apply_permuted_f64(iono_backprojector_t h, const double *coef_perm,
                                                      const double *scale, double *out, int c0, int c1, void *stream) {
-    return bp_apply_chunks(h, coef_perm, true, scale, out, c0, c1, (cudaStream_t)stream);
+    return bp_apply_chunks(h, coef_perm, true, RowScale{scale, 1.0, scale ? 1 : 0}, nullptr, out, c0, c1, (cudaStream_t)stream);
+}
+
+// The voxel gradient in one call: out[v] = k * exp(m[v]) * sum_ray A[v,ray] coef[ray] -- the chain-rule factor
+// ne[v] = K_ne exp(m[v]) / 1e13 (k = K_ne/1e13) is evaluated for the touched rows only, no ne grid needed.
+extern "C" int iono_backprojector_apply_gradient_f64(iono_backprojector_t h, const double *coef_perm, const double *m,
+                                                     double k, double *out, int c0, int c1, void *stream) {
+    if (!m) return fail(IONO_EBADARG, "iono_backprojector_apply_gradient_f64: bad argument");
+    return bp_apply_chunks(h, coef_perm, true, RowScale{m, k, 2}, nullptr, out, c0, c1, (cudaStream_t)stream);
+}
+
+// Sharded adjoint: row r of this rank's operator is stored (unscaled) at out_compact[row_dst[r]], where the
+// caller numbers the voxels any rank touches consecutively (row voxels: iono_backprojector_row_voxels) and has
+// cleared out_compact; the cross-rank sum then moves that compact vector instead of the whole grid.
+extern "C" int iono_backprojector_apply_compact_f64(iono_backprojector_t h, const double *coef_perm,
+                                                    const unsigned int *row_dst, double *out_compact, int c0, int c1,
+                                                    void *stream) {
+    if (!row_dst) return fail(IONO_EBADARG, "iono_backprojector_apply_compact_f64: bad argument");
+    return bp_apply_chunks(h, coef_perm, true, RowScale{nullptr, 1.0, 0}, row_dst, out_compact, c0, c1,
+                           (cudaStream_t)stream);
+}
+
+extern "C" long long iono_backprojector_n_rows(iono_backprojector_t h) { return h ? h->n_rows : 0; }
+
+// voxel index of every non-empty row, ascending (device array of n_rows uint32)
+extern "C" int iono_backprojector_row_voxels(iono_backprojector_t h, unsigned int *out, void *stream) {
+    if (!h || (h->n_rows > 0 && !out)) return fail(IONO_EBADARG, "iono_backprojector_row_voxels: bad argument");
+    if (h->n_rows > 0)
+        CU_CHECK(cudaMemcpyAsync(out, h->row_voxel, (size_t)h->n_rows * sizeof(unsigned int), cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream));
+    return IONO_OK;
 }
 
 extern "C" long long iono_backprojector_chunk_voxels(iono_backprojector_t h, int c) {

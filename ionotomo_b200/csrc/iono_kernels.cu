@@ -445,6 +445,7 @@ extern "C" int iono_tci_interp_f64(iono_grid_t grid, const double *M, const doub
 #include "iono_chord.cuh"
 #include "iono_gaussian.cuh"
 #include "iono_optical.cuh"
+#include "iono_peer.cuh"
 
 // ---------------------------------------------------------------------------
 // small per-ray kernels
@@ -561,14 +562,14 @@ extern "C" int iono_misfit_f64(const double *g, const double *dobs, const double
 // order).  A CTA owns 8 times x 32 directions and walks the antennas, so the coefficients can also be written
 // in the back-projector's internal (antenna, direction, time) order through a shared-memory transpose.
 // ---------------------------------------------------------------------------
-constexpr int RES_TT = 8, RES_TD = 32;
+constexpr int RES_TT = 8, RES_TD = 32, RES_AG = 8;   // tile of 8 times x 32 directions, 8 antennas per round
 
 __global__ void __launch_bounds__(256) residual_kernel(const double *__restrict__ tec, const double *__restrict__ dobs,
                                                         const double *__restrict__ CdCt, int Na, int Nt, int Nd, int i0,
                                                         double *__restrict__ dtec, double *__restrict__ coef,
                                                         double *__restrict__ coef_perm, double *__restrict__ scratch,
                                                         unsigned int *counter, double *__restrict__ out_S) {
-    __shared__ double tile[RES_TT][RES_TD + 1];
+    __shared__ double tile[RES_AG][RES_TT][RES_TD + 1];
     __shared__ bool last;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int dl = threadIdx.x >> 3, tl = threadIdx.x & 7;   // transposed role: direction, time within the tile
@@ -583,25 +584,46 @@ __global__ void __launch_bounds__(256) residual_kernel(const double *__restrict_
         const long long j = (long long)t * Nd + d;
         const double ref = ok ? tec[(long long)i0 * ntd + j] : 0.0;
         double sum = 0.0, dd_ref = 0.0;
-        for (int a = 0; a < Na; ++a) {
-            double dd = 0.0;
-            if (ok) {
-                const long long k = a * ntd + j;
-                const double g = tec[k] - ref;
-                const double r = g - dobs[k];
-                const double w = CdCt[k] + 1e-15;
-                dd = r / w;
-                S += r * r / w;
-                sum += dd;
-                dtec[k] = g;
-                if (a == i0) dd_ref = dd;
-                else if (coef) coef[k] = dd;
+        // antennas in rounds of RES_AG: the loads of a round are independent (8 x 3 in flight per thread) and
+        // one barrier pair serves the transposed stores of the whole round; the sum over antennas stays in
+        // antenna order
+        for (int a0 = 0; a0 < Na; a0 += RES_AG) {
+            double tv[RES_AG], ov[RES_AG], cv[RES_AG];
+#pragma unroll
+            for (int u = 0; u < RES_AG; ++u) {
+                const bool in = ok && (a0 + u < Na);
+                const long long k = (long long)(a0 + u) * ntd + j;
+                tv[u] = in ? tec[k] : 0.0;
+                ov[u] = in ? dobs[k] : 0.0;
+                cv[u] = in ? CdCt[k] : 1.0;
             }
-            if (coef_perm && a != i0) {
+            if (coef_perm) __syncthreads();     // the previous round's transposed reads are done
+#pragma unroll
+            for (int u = 0; u < RES_AG; ++u) {
+                const int a = a0 + u;
+                double dd = 0.0;
+                if (ok && a < Na) {
+                    const long long k = (long long)a * ntd + j;
+                    const double g = tv[u] - ref;
+                    const double r = g - ov[u];
+                    const double w = cv[u] + 1e-15;
+                    dd = r / w;
+                    S += r * r / w;
+                    sum += dd;
+                    dtec[k] = g;
+                    if (a == i0) dd_ref = dd;
+                    else if (coef) coef[k] = dd;
+                }
+                if (coef_perm) tile[u][ty][tx] = dd;
+            }
+            if (coef_perm) {
                 __syncthreads();
-                tile[ty][tx] = dd;
-                __syncthreads();
-                if (okT) coef_perm[((long long)a * Nd + d0 + dl) * Nt + t0 + tl] = tile[tl][dl];
+#pragma unroll
+                for (int u = 0; u < RES_AG; ++u) {
+                    const int a = a0 + u;
+                    if (okT && a < Na && a != i0)
+                        coef_perm[((long long)a * Nd + d0 + dl) * Nt + t0 + tl] = tile[u][tl][dl];
+                }
             }
         }
         // reference antenna: c = dd - sum over antennas (the -tec[i0] term of dTEC, transposed)
@@ -609,12 +631,13 @@ __global__ void __launch_bounds__(256) residual_kernel(const double *__restrict_
         if (ok && coef) coef[(long long)i0 * ntd + j] = c_ref;
         if (coef_perm) {
             __syncthreads();
-            tile[ty][tx] = c_ref;
+            tile[0][ty][tx] = c_ref;
             __syncthreads();
-            if (okT) coef_perm[((long long)i0 * Nd + d0 + dl) * Nt + t0 + tl] = tile[tl][dl];
+            if (okT) coef_perm[((long long)i0 * Nd + d0 + dl) * Nt + t0 + tl] = tile[0][tl][dl];
         }
     }
     // misfit: per-CTA partial, the last CTA to arrive adds the partials in CTA order
+    __syncthreads();
     S = block_sum_256(S);
     if (threadIdx.x == 0) {
         scratch[blockIdx.x] = S;

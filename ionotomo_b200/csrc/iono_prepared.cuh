@@ -17,10 +17,13 @@
 // sample against the 32 B of the raw ray rows; the roofline fraction is still quoted on the
 // algorithmic bytes of the reference's API boundary.
 #pragma once
+#include <cub/cub.cuh>
 
 struct iono_forwardprojector {
     int *cell;        // (R, Nsp) flat index of the cell's low corner
     double *frac;     // (R, 4, Nsp) rows tx, ty, tz, w
+    int *records;     // quad records (iono_device.cuh) the samples read: cells v and v + ny*nz, ascending
+    long long n_records;
     long long R;
     int Na, Nt, Nd, Ns, Nsp;   // Nsp = Ns rounded up to a multiple of 4 (16-byte rows for the bulk copies)
     int nx, ny, nz;
@@ -41,6 +44,7 @@ template <int AXK>
 __global__ void __launch_bounds__(256) prepare_samples_kernel(Grid g, const double *__restrict__ rays, int R, int Na,
                                                                int Nt, int Nd, int Ns, int Nsp,
                                                                int *__restrict__ cell, double *__restrict__ frac,
+                                                               unsigned char *__restrict__ used,
                                                                unsigned long long *oob_count) {
     const int ny = g.ax[1].n, nz = g.ax[2].n;
     const AxisR ax = axis_regs(g.ax[0]), ay = axis_regs(g.ax[1]), az = axis_regs(g.ax[2]);
@@ -63,6 +67,8 @@ __global__ void __launch_bounds__(256) prepare_samples_kernel(Grid g, const doub
             w = simpson_weight(i, Ns, n_odd, sp[max(i - 2, 0)], sp[max(i - 1, 0)], sp[i], sp[min(i + 1, Ns - 1)],
                                sp[min(i + 2, Ns - 1)]);
             v = (ix * ny + iy) * nz + iz;
+            used[v] = 1;                 // quad records this sample gathers from (benign race: all writers store 1)
+            used[v + ny * nz] = 1;
         }
         cell[k] = v;
         double *f = frac + (long long)q * 4 * Nsp + i;
@@ -185,8 +191,39 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const double 
     }
 }
 
+// quad records of ne = k * exp(m) for the listed records only (the rays of a shard touch ~12-20 % of the grid)
+__global__ void __launch_bounds__(256) quads_list_kernel(const double *__restrict__ m, double k,
+                                                          const int *__restrict__ list, long long n, int ny, int nz,
+                                                          double4 *__restrict__ q) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int v = list[i];
+        const int iz = v % nz, iy = (v / nz) % ny;
+        const int dz = (iz + 1 < nz) ? 1 : 0, dy = (iy + 1 < ny) ? nz : 0;
+        const double a = exp(m[v]) * k, b = exp(m[v + dz]) * k, c = exp(m[v + dy]) * k, d = exp(m[v + dy + dz]) * k;
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(q + v), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+    }
+}
+
+extern "C" long long iono_forwardprojector_n_records(iono_forwardprojector_t h) { return h ? h->n_records : 0; }
+
+// quads_out[v] for the records this projector reads (other records are left untouched): the per-iteration
+// replacement of iono_ne_quads_from_m_f64 when only this projector consumes the quad grid.
+extern "C" int iono_forwardprojector_quads_from_m_f64(iono_forwardprojector_t h, const double *m, double scale,
+                                                      double *quads_out, void *stream) {
+    if (!h || !m || !quads_out || ((uintptr_t)quads_out & 31))
+        return fail(IONO_EBADARG, "iono_forwardprojector_quads_from_m_f64: bad argument");
+    if (device_check(h->device, "iono_forwardprojector_quads_from_m_f64")) return IONO_EBADARG;
+    if (h->n_records == 0) return IONO_OK;
+    quads_list_kernel<<<ew_grid(h->n_records), 256, 0, (cudaStream_t)stream>>>(
+        m, scale, h->records, h->n_records, h->ny, h->nz, reinterpret_cast<double4 *>(quads_out));
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
 extern "C" int iono_forwardprojector_destroy(iono_forwardprojector_t h) {
     if (!h) return IONO_OK;
+    cudaFree(h->records);
     cudaFree(h->cell);
     cudaFree(h->frac);
     delete h;
@@ -207,7 +244,7 @@ extern "C" int iono_forwardprojector_create(iono_grid_t grid, const double *rays
     cudaStream_t st = (cudaStream_t)stream;
     CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
     iono_forwardprojector *h = new iono_forwardprojector();
-    h->cell = nullptr; h->frac = nullptr; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->Ns = Ns;
+    h->cell = nullptr; h->frac = nullptr; h->records = nullptr; h->n_records = 0; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->Ns = Ns;
     h->Nsp = (Ns + 3) / 4 * 4;
     h->nx = grid->nx; h->ny = grid->ny; h->nz = grid->nz;
     cudaGetDevice(&h->device);
@@ -219,19 +256,51 @@ extern "C" int iono_forwardprojector_create(iono_grid_t grid, const double *rays
             iono_forwardprojector_destroy(h);
             return fail(IONO_ECUDA, "iono_forwardprojector_create: cudaMalloc: %s", cudaGetErrorString(e));
         }
+        const long long V = (long long)grid->nx * grid->ny * grid->nz;
+        unsigned char *used = nullptr;
+        long long *d_n = nullptr;
+        void *tmp = nullptr;
+        auto bail = [&](const char *what) {
+            cudaFree(used); cudaFree(d_n); cudaFree(tmp);
+            iono_forwardprojector_destroy(h);
+            return fail(IONO_ECUDA, "iono_forwardprojector_create: %s: %s", what, cudaGetErrorString(e));
+        };
+        if ((e = cudaMalloc(&used, (size_t)V)) != cudaSuccess) return bail("cudaMalloc");
+        if ((e = cudaMemsetAsync(used, 0, (size_t)V, st)) != cudaSuccess) return bail("cudaMemsetAsync");
         if (grid->exact)
             prepare_samples_kernel<2><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
-                                                                  h->cell, h->frac, oob_count);
+                                                                  h->cell, h->frac, used, oob_count);
         else if (grid->uniform)
             prepare_samples_kernel<1><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
-                                                                  h->cell, h->frac, oob_count);
+                                                                  h->cell, h->frac, used, oob_count);
         else
             prepare_samples_kernel<0><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
-                                                                  h->cell, h->frac, oob_count);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) {
-            iono_forwardprojector_destroy(h);
-            return fail(IONO_ECUDA, "iono_forwardprojector_create: launch: %s", cudaGetErrorString(e));
+                                                                  h->cell, h->frac, used, oob_count);
+        if ((e = cudaGetLastError()) != cudaSuccess) return bail("launch");
+        // list of the quad records in use (ascending)
+        if ((e = cudaMalloc(&d_n, sizeof(long long))) != cudaSuccess) return bail("cudaMalloc");
+        if ((e = cudaMalloc(&h->records, (size_t)V * sizeof(int))) != cudaSuccess) return bail("cudaMalloc");
+        size_t tmp_bytes = 0;
+        cub::CountingInputIterator<int> ids(0);
+        if ((e = cub::DeviceSelect::Flagged(nullptr, tmp_bytes, ids, used, h->records, d_n, (int)V, st)) != cudaSuccess)
+            return bail("select");
+        if ((e = cudaMalloc(&tmp, tmp_bytes)) != cudaSuccess) return bail("cudaMalloc");
+        if ((e = cub::DeviceSelect::Flagged(tmp, tmp_bytes, ids, used, h->records, d_n, (int)V, st)) != cudaSuccess)
+            return bail("select");
+        if ((e = cudaMemcpyAsync(&h->n_records, d_n, sizeof(long long), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(st)) != cudaSuccess)
+            return bail("select");
+        cudaFree(used); cudaFree(d_n); cudaFree(tmp);
+        // shrink the list to its size
+        if (h->n_records < V) {
+            int *small = nullptr;
+            if (cudaMalloc(&small, (size_t)(h->n_records > 0 ? h->n_records : 1) * sizeof(int)) == cudaSuccess) {
+                cudaMemcpy(small, h->records, (size_t)h->n_records * sizeof(int), cudaMemcpyDeviceToDevice);
+                cudaFree(h->records);
+                h->records = small;
+            } else {
+                cudaGetLastError();
+            }
         }
     }
     *out = h;

@@ -70,16 +70,6 @@ def backproject(rays_dev, grid, coef, shape, order="time", check_bounds=True, ou
     return acc
 
 
-def released_slices(bounds, nxt, done):
-    """Common slices ``[bounds[j], bounds[j+1])``, ``j >= nxt``, that lie entirely below ``done``
-    (the number of leading voxels this rank has finished)."""
-    out = []
-    while nxt + 1 < len(bounds) and bounds[nxt + 1] <= done:
-        out.append((bounds[nxt], bounds[nxt + 1]))
-        nxt += 1
-    return out
-
-
 class BackProjector(object):
     """Voxel-binned form of the adjoint for a fixed ray geometry (``iono_backprojector_*``).
 
@@ -129,45 +119,6 @@ class BackProjector(object):
     def chunk_voxels(self, c):
         """Flat voxel index below which ``out`` is final once chunks ``[0, c)`` have been applied."""
         return int(_lib.load().iono_backprojector_chunk_voxels(self.handle, int(c)))
-
-    def apply_overlapped(self, coef, scale=None, out=None, n_chunks=4, reduce_slice=None):
-        """Same result as ``apply`` followed by a sum over ranks, with the two overlapped: the
-        operator is applied in ``n_chunks`` pieces (voxel-contiguous, but with boundaries that
-        depend on this rank's rays), and ``reduce_slice(flat_view)`` -- e.g.
-        ``sharding.allreduce_sum_async``; may return a handle with ``.wait()`` -- is called on
-        slices of ``out`` as soon as they are final, while the next piece is being computed.
-
-        The slices handed to ``reduce_slice`` are the ``n_chunks`` EQUAL parts of the flattened
-        grid, in order, on every rank (a collective needs identical sizes and order everywhere);
-        a part is released once this rank's own progress has passed its end.
-
-        EXPERIMENTAL: checked against ``apply`` on one GPU; the multi-rank NCCL run of this
-        variant is still to be validated (tests/test_gpu_multi.py, IONO_TEST_OVERLAP=1).
-        """
-        assert n_chunks in (1, 2, 4, 8, 16)
-        lib = _lib.load()
-        coef = _lib.to_device(coef)
-        assert tuple(coef.shape) == self.ray_shape
-        acc = out if out is not None else torch.empty(self.shape, dtype=torch.float64, device=coef.device)
-        assert acc.is_contiguous(), "apply_overlapped reduces views of `out`: it must be contiguous"
-        flat = acc.view(-1)
-        V = flat.numel()
-        bounds = [V * j // n_chunks for j in range(n_chunks + 1)]
-        step = 16 // n_chunks
-        handles = []
-        nxt = 0
-        for c0 in range(0, 16, step):
-            _lib.call("iono_backprojector_apply_chunks_f64", self.handle, _lib.ptr(coef),
-                      _lib.ptr(scale) if scale is not None else None, _lib.ptr(acc), c0, c0 + step, _lib.stream_ptr())
-            done = int(lib.iono_backprojector_chunk_voxels(self.handle, c0 + step))
-            for a_, b_ in released_slices(bounds, nxt, done):
-                if reduce_slice is not None and b_ > a_:
-                    handles.append(reduce_slice(flat[a_:b_]))
-                nxt += 1
-        for hdl in handles:
-            if hdl is not None and hasattr(hdl, "wait"):
-                hdl.wait()
-        return acc
 
     def __del__(self):
         try:

@@ -149,3 +149,71 @@ def misfit_and_gradient(rays, K_ne, m_tci, i0, dobs, CdCt, order="time", block_t
     if copy_results:   # private copies, so that the next call cannot overwrite them
         return dtec_h.numpy().copy(), S, grad_h.numpy().copy()
     return dtec_h.numpy(), S, grad_h.numpy()
+
+
+class HostSession(object):
+    """Host-level iteration API: geometry, data and the prepared operators stay on the GPU for the whole solve;
+    per call only the model goes in and ``(dtec, S, gradient)`` come out.
+
+    The reference computes its rays once per solve (``inversion_pipeline.py:195-197``) and then calls
+    ``func_and_gradient(m)`` every iteration (``tests/test_inversion.py:30-39``); this is that call for host
+    (NumPy) callers.  ``rays`` may be the materialised host array, or ``None`` with ``origins`` / ``directions``
+    (``(Na,Nt,Nd,3)``) given: the rays are then generated on the device (``cast_ray``), 60 MB of input
+    instead of 5 GB.  All arrays returned are views of pinned host buffers owned by the session, valid until
+    the next call; ``m_host`` is a pinned buffer the caller may fill in place (pass ``m=None`` then).
+
+    With ``torch.distributed`` initialised and the rays sharded over the ranks (direction or time blocks)
+    every rank returns the global ``S`` and gradient and the ``dtec`` of its own rays.
+    """
+
+    def __init__(self, rays, K_ne, m_tci, i0, dobs, CdCt, origins=None, directions=None, tmax=1000., Ns=None,
+                 **session_kw):
+        from ..geometry.calc_rays import cast_ray
+        from .fermat import Fermat
+        from .session import DeviceSession
+        _lib.require_cuda()
+        if rays is None:
+            assert origins is not None and directions is not None
+            rays = cast_ray((_lib.to_device(origins), _lib.to_device(directions)), Fermat(m_tci), tmax,
+                            Ns if Ns is not None else m_tci.nz)
+        self.session = DeviceSession(rays, K_ne, m_tci, i0, dobs, CdCt, **session_kw)
+        s = self.session
+        self.m_host = torch.empty(s.shape, dtype=torch.float64, pin_memory=True)
+        self.dtec_host = torch.empty(s.ray_shape, dtype=torch.float64, pin_memory=True)
+        self.grad_host = torch.empty(s.shape, dtype=torch.float64, pin_memory=True)
+        self.S_host = torch.empty(1, dtype=torch.float64, pin_memory=True)
+        self.h2d_bytes_per_call = self.m_host.numel() * 8
+        self.d2h_bytes_per_call = (self.dtec_host.numel() + self.grad_host.numel() + 1) * 8
+
+    def misfit_and_gradient(self, m=None):
+        """``(dtec, S, gradient)`` for the model ``m`` (NumPy ``(nx,ny,nz)``; ``None``: ``self.m_host`` as filled by
+        the caller)."""
+        s = self.session
+        if m is not None:
+            src = torch.as_tensor(m, dtype=torch.float64).reshape(s.shape)
+            if src.data_ptr() != self.m_host.data_ptr():
+                self.m_host.copy_(src)
+        s.m.copy_(self.m_host, non_blocking=True)
+        s.misfit_and_gradient(None)
+        self.dtec_host.copy_(s.dtec, non_blocking=True)
+        self.grad_host.copy_(s.grad, non_blocking=True)
+        self.S_host.copy_(s.S, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.dtec_host.numpy(), float(self.S_host[0]), self.grad_host.numpy()
+
+    def forward(self, m=None):
+        """``(dtec, S)`` only (line searches)."""
+        s = self.session
+        if m is not None:
+            src = torch.as_tensor(m, dtype=torch.float64).reshape(s.shape)
+            if src.data_ptr() != self.m_host.data_ptr():
+                self.m_host.copy_(src)
+        s.m.copy_(self.m_host, non_blocking=True)
+        s.forward(None)
+        self.dtec_host.copy_(s.dtec, non_blocking=True)
+        self.S_host.copy_(s.S, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.dtec_host.numpy(), float(self.S_host[0])
+
+    def close(self):
+        self.session.close()

@@ -1,5 +1,6 @@
 """Device-resident session for one inversion: fixed ray geometry + data, repeated
-``(misfit, gradient)`` evaluations for changing models.
+``(misfit, gradient)`` evaluations for changing models -- on one GPU or with the rays sharded over the
+GPUs of a node (one process per GPU).
 
 This is how the reference's drivers use the path: rays are computed ONCE per solve
 (``inversion_pipeline.py:195-197``), then every iteration calls the forward and the gradient with a
@@ -8,26 +9,32 @@ new model (``tests/test_inversion.py:30-39`` ``func_and_gradient(m)``; ``bfgs_da
 (``ForwardProjector``, ``BackProjector``), keeps every buffer of the step allocated, and replays
 the step as ONE CUDA graph:
 
-    quad records of ne = K exp(m)/1e13      iono_ne_quads_from_m_f64
-    TEC per ray                             iono_forwardprojector_apply_quads_f64 (or the stateless sweep)
+    quad records of ne = K exp(m)/1e13      iono_forwardprojector_quads_from_m_f64 (touched records only)
+    TEC per ray                             iono_forwardprojector_apply_quads_f64  (or the stateless sweep)
     dTEC, misfit, adjoint coefficients      iono_residual_f64
-    gradient = ne * A^T coef                iono_backprojector_apply_permuted_f64 (or the scatter adjoint)
+    gradient = ne * A^T coef                iono_backprojector_apply_gradient_f64  (or the scatter adjoint)
 
-With rays sharded over ranks pass ``reduce_grad`` / ``reduce_scalar`` (see ``ionotomo_b200.sharding``);
-collectives are not captured, the graph is then split around them.
+Sharded (``torch.distributed`` initialised, world size > 1; shard the direction or time axis so that the
+reference antenna is local): the forward needs no exchange; the back-projector of every rank writes into a
+COMPACT accumulator that numbers only the voxels some rank's rays touch, the misfit rides along as its last
+element, and ``iono_peer_reduce_expand_f64`` sums, scales and expands it over NVLink peer memory inside the
+same graph (``reducer="peer"``), or ``torch.distributed.all_reduce`` does between two graphs
+(``reducer="nccl"``; gloo in the CPU tests of the host logic).
 """
 import ctypes
 
 import torch
+import torch.distributed as dist
 
 from .. import _lib
-from .forward_equation import ForwardProjector, ne_quads_from_m, quads_alloc, tec_from_quads
+from .. import sharding
+from .forward_equation import ForwardProjector, TECU, ne_quads_from_m, quads_alloc, tec_from_quads
 from .gradient import BackProjector, backproject, residual
 
 
 class DeviceSession(object):
     def __init__(self, rays, K_ne, m_tci, i0, dobs, CdCt, forward="prepared", adjoint="binned", order="time",
-                 use_graph=True, keep_rays=None, check_bounds=True):
+                 use_graph=True, keep_rays=None, check_bounds=True, group=None, reducer="peer"):
         lib = _lib.load()
         self.rays = _lib.to_device(rays)
         Na, Nt, Nd, four, Ns = self.rays.shape
@@ -44,6 +51,12 @@ class DeviceSession(object):
         self.dobs = _lib.to_device(dobs).reshape(self.ray_shape).contiguous()
         self.CdCt = _lib.to_device(CdCt).reshape(self.ray_shape).contiguous()
         assert forward in ("prepared", "sweep") and adjoint in ("binned", "scatter")
+        self.group = group
+        self.rank, self.world = sharding.world() if group is None else (dist.get_rank(group), dist.get_world_size(group))
+        self.sharded = self.world > 1
+        if self.sharded:
+            assert adjoint == "binned", "sharded rays: the compact accumulator is written by the binned adjoint"
+            assert reducer in ("peer", "nccl")
         self.fp = ForwardProjector(self.rays, m_tci, check_bounds=check_bounds) if forward == "prepared" else None
         self.bp = BackProjector(self.rays, m_tci, check_bounds=check_bounds) if adjoint == "binned" else None
         if keep_rays is None:
@@ -53,7 +66,7 @@ class DeviceSession(object):
             self.rays = None           # both operators are prepared: the 4 x Ns doubles per ray are not read again
         f64 = dict(dtype=torch.float64, device=dev)
         self.m = torch.empty(self.shape, **f64)                 # static input of the graph
-        self.ne = torch.empty(self.shape, **f64)
+        self.ne = torch.empty(self.shape, **f64) if self.bp is None else None
         self.quads = quads_alloc(self.shape, dev)
         self.tec = torch.empty(self.ray_shape, **f64)
         self.dtec = torch.empty(self.ray_shape, **f64)
@@ -61,35 +74,76 @@ class DeviceSession(object):
         self.coef_perm = torch.empty(Na * Nt * Nd, **f64) if self.bp is not None else None
         self.scratch = torch.empty(int(lib.iono_residual_scratch_elems()), **f64)
         self.S = torch.zeros(1, **f64)
-        self.grad = torch.empty(self.shape, **f64)
+        self.S_local = self.S
+        self.grad = torch.zeros(self.shape, **f64)     # voxels no ray touches stay zero for the whole session
         self.oob = torch.zeros(1, dtype=torch.int64, device=dev)
         self.use_graph = bool(use_graph)
         self._graphs = {}
         self.launches_per_call = {}
         self.n_forward = 0
         self.n_gradient = 0
+        self.reducer = None
+        self.reducer_kind = None
+        if self.sharded:
+            self._setup_sharded(reducer)
+
+    # ---- sharded set-up: common numbering of the voxels any rank touches ---------------------------
+    def _setup_sharded(self, reducer):
+        lib = _lib.load()
+        n_rows = int(lib.iono_backprojector_n_rows(self.bp.handle))
+        rows = torch.empty(max(n_rows, 1), dtype=torch.int32, device=self.device)
+        _lib.call("iono_backprojector_row_voxels", self.bp.handle, ctypes.c_void_p(rows.data_ptr()), _lib.stream_ptr())
+        V = self.shape[0] * self.shape[1] * self.shape[2]
+        self.row_dst, self.union_voxels, self.n_union = sharding.union_index(rows[:n_rows], V, self.group)
+        L = self.n_union + 1                                    # + the misfit
+        self.reducer_kind = reducer
+        if reducer == "peer":
+            from ..peer import PeerReducer
+            self.reducer = PeerReducer(L, self.group)
+            self.acc_c = self.reducer.acc_t
+        else:
+            from ..peer import LocalExpander
+            self.reducer = LocalExpander(L, self.device)
+            self.acc_c = self.reducer.acc_t
+        self.S_local = self.acc_c[self.n_union:self.n_union + 1]   # the residual kernel writes the shard's misfit here
 
     # ---- the step, as enqueued work on the current stream ------------------------------------
     def _enqueue_forward(self):
-        ne_quads_from_m(self.m, self.K_ne, ne_out=self.ne, quads_out=self.quads)
         if self.fp is not None:
+            _lib.call("iono_forwardprojector_quads_from_m_f64", self.fp.handle, _lib.ptr(self.m), self.K_ne / TECU,
+                      _lib.ptr(self.quads), _lib.stream_ptr())
             self.fp.tec_quads(self.quads, out=self.tec)
         else:
+            ne_quads_from_m(self.m, self.K_ne, ne_out=self.ne, quads_out=self.quads, want_ne=self.ne is not None)
             tec_from_quads(self.rays, self.grid, self.quads, order=self.order, check_bounds=False, out=self.tec,
                            oob=self.oob)
+        if self.fp is not None and self.ne is not None:       # prepared forward + scatter adjoint: the plain grid too
+            _lib.call("iono_ne_from_m_f64", _lib.ptr(self.m), self.m.numel(), self.K_ne / TECU, _lib.ptr(self.ne),
+                      _lib.stream_ptr())
 
     def _enqueue_residual(self):
+        if self.sharded:
+            self.acc_c.zero_()
         residual(self.tec, self.dobs, self.CdCt, self.i0, want_coef=self.bp is None, want_perm=self.bp is not None,
-                 out=dict(dtec=self.dtec, coef=self.coef, coef_perm=self.coef_perm, scratch=self.scratch, S=self.S))
+                 out=dict(dtec=self.dtec, coef=self.coef, coef_perm=self.coef_perm, scratch=self.scratch,
+                          S=self.S_local))
 
     def _enqueue_adjoint(self):
-        if self.bp is not None:
-            self.bp.apply_permuted(self.coef_perm, scale=self.ne, out=self.grad)
+        if self.sharded:
+            _lib.call("iono_backprojector_apply_compact_f64", self.bp.handle, _lib.ptr(self.coef_perm),
+                      ctypes.c_void_p(self.row_dst.data_ptr()), _lib.ptr(self.acc_c), 0, 16, _lib.stream_ptr())
+        elif self.bp is not None:
+            _lib.call("iono_backprojector_apply_gradient_f64", self.bp.handle, _lib.ptr(self.coef_perm),
+                      _lib.ptr(self.m), self.K_ne / TECU, _lib.ptr(self.grad), 0, 16, _lib.stream_ptr())
         else:
             backproject(self.rays, self.grid, self.coef, self.shape, order=self.order, check_bounds=False,
                         out=self.grad)
             _lib.call("iono_mul_f64", _lib.ptr(self.ne), _lib.ptr(self.grad), self.grad.numel(), _lib.ptr(self.grad),
                       _lib.stream_ptr())
+
+    def _enqueue_reduce(self):
+        """Sharded: sum over ranks, chain-rule factor, expansion to the grid, summed misfit."""
+        self.reducer.reduce_expand(self.union_voxels, self.n_union, self.m, self.K_ne / TECU, self.grad, self.S)
 
     def _run(self, key, fn):
         """Run ``fn`` (which only enqueues kernels on the current stream) eagerly the first time -- kernel
@@ -99,7 +153,7 @@ class DeviceSession(object):
         g = self._graphs.get(key)
         if g is None:
             l0 = _lib.launch_count
-            fn()                                    # warm-up, eager
+            fn()                                    # first call: eager
             self.launches_per_call[key] = _lib.launch_count - l0
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -117,7 +171,8 @@ class DeviceSession(object):
 
     # ---- public ------------------------------------------------------------------------------
     def forward(self, m=None):
-        """``dtec`` (view of the session's buffer, overwritten by the next call) and misfit for model ``m``."""
+        """``(dtec, S)``: the forward for model ``m`` (view of the session's buffer, overwritten by the next call;
+        the local rays when sharded) and the misfit summed over all ranks (0-d CUDA tensor)."""
         self._set_model(m)
         self.n_forward += 1
 
@@ -125,28 +180,57 @@ class DeviceSession(object):
             self._enqueue_forward()
             self._enqueue_residual()
         self._run("forward", fn)
+        if self.sharded:
+            self.S.copy_(self.S_local)
+            dist.all_reduce(self.S, group=self.group)
         return self.dtec, self.S[0]
 
     def misfit_and_gradient(self, m=None):
-        """``(S, grad)``: 0-d CUDA tensor and ``(nx,ny,nz)`` CUDA tensor (the session's buffers; copy them if
-        they must survive the next call).  ``self.dtec`` holds the forward."""
+        """``(S, grad)``: 0-d CUDA tensor and ``(nx,ny,nz)`` CUDA tensor, both global when sharded (the session's
+        buffers; copy them if they must survive the next call).  ``self.dtec`` holds the forward of the local rays."""
         self._set_model(m)
         self.n_forward += 1
         self.n_gradient += 1
-
-        def fn():
-            self._enqueue_forward()
-            self._enqueue_residual()
-            self._enqueue_adjoint()
-        self._run("step", fn)
+        if self.sharded and self.reducer_kind == "nccl":
+            def fa():
+                self._enqueue_forward()
+                self._enqueue_residual()
+                self._enqueue_adjoint()
+            self._run("step_a", fa)
+            dist.all_reduce(self.acc_c, group=self.group)
+            self._run("step_b", self._enqueue_reduce)
+        else:
+            def fn():
+                self._enqueue_forward()
+                self._enqueue_residual()
+                self._enqueue_adjoint()
+                if self.sharded:
+                    self._enqueue_reduce()
+            self._run("step", fn)
         return self.S[0], self.grad
 
     def gradient_after_forward(self):
-        """Gradient for the model of the last ``forward`` call (reuses its ne and coefficients)."""
+        """Gradient for the model of the last ``forward`` call (reuses its coefficients)."""
         self.n_gradient += 1
-        self._run("adjoint", self._enqueue_adjoint)
+        if self.sharded and self.reducer_kind == "nccl":
+            self._run("adjoint_a", self._enqueue_adjoint)
+            dist.all_reduce(self.acc_c, group=self.group)
+            self._run("step_b", self._enqueue_reduce)
+        else:
+            def fn():
+                self._enqueue_adjoint()
+                if self.sharded:
+                    self._enqueue_reduce()
+            self._run("adjoint", fn)
         return self.grad
 
     @property
     def operator_bytes(self):
         return (self.fp.nbytes if self.fp is not None else 0) + (self.bp.nbytes if self.bp is not None else 0)
+
+    def close(self):
+        """Release the peer mappings (collective when sharded with the peer reducer)."""
+        self._graphs = {}
+        if self.reducer is not None and hasattr(self.reducer, "close"):
+            self.reducer.close()
+            self.reducer = None

@@ -37,8 +37,23 @@ def sharded_misfit(S_local, group=None):
     return float(s[0])
 
 
-def allreduce_sum_async(t, group=None):
-    """Start an in-place sum over ranks and return the work handle (``None`` for one process)."""
+def direction_shard(Nd, rank, world):
+    """Contiguous, balanced block ``[d0, d1)`` of the direction axis for ``rank`` (like ``time_shard``)."""
+    return time_shard(Nd, rank, world)
+
+
+def union_index(row_voxels, V, group=None):
+    """Common compact numbering of the voxels that ANY rank's rays touch.
+
+    ``row_voxels``: ascending voxel indices of this rank's non-empty operator rows (any integer dtype, on the
+    device the collective backend works with).  Returns ``(row_dst, union_voxels, n_union)``: the position of
+    every local row in the union (int32), the ascending voxel index of every union position (int32), and the
+    union's size.  One MAX-allreduce of a V-byte mask, once per geometry."""
+    mask = torch.zeros(int(V), dtype=torch.uint8, device=row_voxels.device)
+    mask[row_voxels.long()] = 1
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True)
-    return None
+        dist.all_reduce(mask, op=dist.ReduceOp.MAX, group=group)
+    union_voxels = torch.nonzero(mask).reshape(-1).to(torch.int32)
+    pos = torch.cumsum(mask, 0, dtype=torch.int32) - 1
+    row_dst = pos[row_voxels.long()].contiguous()
+    return row_dst, union_voxels.contiguous(), int(union_voxels.numel())

@@ -560,6 +560,8 @@ def test_config1_golden(ib, golden):
 
 @pytest.mark.parametrize("runs", ["1", "0"])
 def test_binned_backprojector_chunked_apply(ib, runs, monkeypatch):
+    """The apply in sixteenths of the operator: any split into consecutive chunk ranges gives the bits of the
+    one-shot apply, and after chunks [0, c) every voxel below chunk_voxels(c) is final."""
     import torch
     monkeypatch.setenv("IONO_BP_RUNS", runs)
     P = small_problem(79, 20, 3, 16, 64, 40, 36, 64)
@@ -570,17 +572,26 @@ def test_binned_backprojector_chunked_apply(ib, runs, monkeypatch):
     scale = torch.rand(P["m"].shape, dtype=torch.float64, device="cuda")
     bp = ib.BackProjector(rays, tci)
     ref = bp.apply(y, scale=scale)
+    perm = y.permute(0, 2, 1).contiguous().reshape(-1)          # (antenna, direction, time)
+    assert torch.equal(bp.apply_permuted(perm, scale=scale), ref)
     V = ref.numel()
     for n_chunks in (1, 2, 4, 8, 16):
-        seen = []
         out = torch.full_like(ref, float("nan"))
-        got = bp.apply_overlapped(y, scale=scale, out=out, n_chunks=n_chunks,
-                                  reduce_slice=lambda sl: seen.append((sl.data_ptr(), sl.numel())))
-        assert torch.equal(got, ref)
-        # the slices handed to the reducer are the n_chunks equal parts of the grid, in order
-        base = out.data_ptr()
-        bounds = [V * j // n_chunks for j in range(n_chunks + 1)]
-        assert seen == [(base + 8 * a, b - a) for a, b in zip(bounds[:-1], bounds[1:])]
+        step = 16 // n_chunks
+        for c0 in range(0, 16, step):
+            bp.apply_permuted(perm, scale=scale, out=out, c0=c0, c1=c0 + step)
+            done = bp.chunk_voxels(c0 + step)
+            assert 0 <= done <= V
+            assert torch.equal(out.reshape(-1)[:done], ref.reshape(-1)[:done])
+        assert torch.equal(out, ref)
+    # the chain-rule factor evaluated inside the apply: ne[v] = k exp(m[v]) for the touched rows, zero elsewhere
+    from ionotomo_b200 import _lib
+    m = torch.as_tensor(P["m"]).cuda()
+    grad = torch.empty_like(ref)
+    _lib.call("iono_backprojector_apply_gradient_f64", bp.handle, _lib.ptr(perm), _lib.ptr(m), 0.37, _lib.ptr(grad), 0,
+              16, _lib.stream_ptr())
+    expect = bp.apply(y) * (0.37 * torch.exp(m))
+    assert float((grad - expect).abs().max()) <= 1e-14 * float(expect.abs().max())
 
 
 # ---------------------------------------------------------------- adjoint B, prepared operators, large axis tables
@@ -707,8 +718,6 @@ def test_binned_backprojector_run_compressed(ib, shape, monkeypatch):
         assert run_bp.nbytes < ref_bp.nbytes
     assert torch.equal(run_bp.apply(y, scale=scale), ref_bp.apply(y, scale=scale))
     assert torch.equal(run_bp.apply(y), ref_bp.apply(y))
-    out = torch.empty_like(scale)
-    assert torch.equal(run_bp.apply_overlapped(y, scale=scale, out=out, n_chunks=4), ref_bp.apply(y, scale=scale))
 
 
 def test_sweep_shrinks_cta_for_large_axis_tables(ib):

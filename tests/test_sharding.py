@@ -71,121 +71,68 @@ def test_sharded_gradient_gloo_world2():
     assert out.get(timeout=5) is True
 
 
-def test_released_slices_are_rank_independent():
-    """The overlapped apply hands the reducer the same equal slices in the same order on every rank,
-    whatever the rank's own chunk boundaries are (a collective must match in size and order)."""
-    from ionotomo_b200.inversion.gradient import released_slices
-    V, K = 1000, 4
-    bounds = [V * j // K for j in range(K + 1)]
-    for progress in ([100, 300, 620, 1000], [250, 500, 750, 1000], [999, 999, 1000], [1000]):
-        nxt, got = 0, []
-        for done in progress:
-            rel = released_slices(bounds, nxt, done)
-            got += rel
-            nxt += len(rel)
-        assert got == list(zip(bounds[:-1], bounds[1:]))
-
-
-def test_apply_overlapped_host_logic_with_fake_library(monkeypatch):
-    """BackProjector.apply_overlapped without a GPU: the C entry points are replaced by fakes that
-    record the chunk calls; checks chunk order, the released slices and the waits."""
-    from ionotomo_b200 import _lib
-    from ionotomo_b200.inversion import gradient as G
-    V = 6 * 5 * 4
-    chunk_vox = [0, 3, 9, 20, 20, 31, 40, 47, 55, 60, 71, 80, 88, 97, 105, 111, V]   # this rank's progress table
-    calls = []
-
-    class FakeLib(object):
-        def iono_backprojector_chunk_voxels(self, handle, c):
-            return chunk_vox[c]
-
-    monkeypatch.setattr(_lib, "load", lambda: FakeLib())
-    monkeypatch.setattr(_lib, "to_device", lambda a, device=None: a)
-    monkeypatch.setattr(_lib, "ptr", lambda t: None)
-    monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
-    monkeypatch.setattr(_lib, "call", lambda name, *args: calls.append((name, args[4], args[5])))
-    bp = object.__new__(G.BackProjector)
-    bp.handle, bp.shape, bp.ray_shape = None, (6, 5, 4), (2, 2, 2)
-
-    class Handle(object):
-        waited = 0
-
-        def wait(self):
-            Handle.waited += 1
-
-    for n_chunks in (1, 2, 4, 8, 16):
-        del calls[:]
-        Handle.waited = 0
-        seen = []
-        out = torch.zeros(6, 5, 4, dtype=torch.float64)
-        coef = torch.zeros(2, 2, 2, dtype=torch.float64)
-
-        def reducer(sl):
-            seen.append((sl.data_ptr() - out.data_ptr(), sl.numel()))
-            return Handle()
-        got = bp.apply_overlapped(coef, out=out, n_chunks=n_chunks, reduce_slice=reducer)
-        assert got is out
-        step = 16 // n_chunks
-        assert calls == [("iono_backprojector_apply_chunks_f64", c, c + step) for c in range(0, 16, step)]
-        bounds = [V * j // n_chunks for j in range(n_chunks + 1)]
-        assert seen == [(8 * a, b - a) for a, b in zip(bounds[:-1], bounds[1:])]
-        assert Handle.waited == n_chunks
-
-
-def _overlap_worker(rank, world, port, out):
-    """Two ranks with DIFFERENT chunk-progress tables run apply_overlapped with a real asynchronous
-    all_reduce (gloo): the collectives must match in order and size, or this dead-locks."""
+def _compact_worker(rank, world, port, out):
+    """The sharded session's host logic without a GPU: every rank's non-empty operator rows are numbered in the
+    union of all ranks' rows, the compact accumulators (+ the misfit as last element) are summed, and the
+    expansion ``grad[union_voxels] = ne * sum`` equals the single-process gradient."""
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from ionotomo_b200 import _lib, sharding
-    from ionotomo_b200.inversion import gradient as G
-    shape = (8, 7, 9)
-    V = shape[0] * shape[1] * shape[2]
-    rng = np.random.RandomState(100 + rank)
-    cuts = np.sort(rng.randint(0, V + 1, size=15))
-    chunk_vox = [0] + [int(c) for c in cuts] + [V]          # this rank's own voxel boundaries per sixteenth
-
-    class FakeLib(object):
-        def iono_backprojector_chunk_voxels(self, handle, c):
-            return chunk_vox[c]
-
-    def fake_call(name, handle, coef, scale, acc, c0, c1, stream):
-        assert name == "iono_backprojector_apply_chunks_f64"
-        flat = acc.reshape(-1)
-        if c0 == 0:
-            flat.zero_()
-        flat[chunk_vox[c0]:chunk_vox[c1]] = float(rank + 1)      # "final" values of this rank's finished voxels
-
-    _lib.load = lambda: FakeLib()
-    _lib.to_device = lambda a, device=None: a
-    _lib.ptr = lambda t: t
-    _lib.stream_ptr = lambda: None
-    _lib.call = fake_call
-    bp = object.__new__(G.BackProjector)
-    bp.handle, bp.shape, bp.ray_shape = None, shape, (1,)
-    ok = True
-    for n_chunks in (1, 2, 4, 8, 16):
-        acc = torch.full(shape, -1.0, dtype=torch.float64)
-        got = bp.apply_overlapped(torch.zeros(1, dtype=torch.float64), out=acc, n_chunks=n_chunks,
-                                  reduce_slice=sharding.allreduce_sum_async)
-        ok = ok and bool(torch.all(got == float(sum(range(1, world + 1)))))
+    from oracle import ionotomo_oracle as O
+    from tests.problems import small_problem
+    from ionotomo_b200 import sharding
+    P = small_problem(43, 4, 3, 7, 16, 12, 11, 12)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 16)
+    i0 = 2
+    g = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], i0)
+    rng = np.random.RandomState(0)
+    dobs = g + 0.01 * rng.normal(size=g.shape)
+    CdCt = np.full(g.shape, 1e-4)
+    d0, d1 = sharding.direction_shard(rays.shape[2], rank, world)
+    sl = (slice(None), slice(None), slice(d0, d1))
+    g_loc = O.forward_equation(rays[sl], P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], i0)
+    assert np.array_equal(g_loc, g[sl])                       # direction blocks keep the reference antenna local
+    dd = O.weighted_residual(g_loc, dobs[sl], CdCt[sl])
+    acc = O.backproject(rays[sl], P["xvec"], P["yvec"], P["zvec"], O.adjoint_ray_coefficients(dd, i0)).reshape(-1)
+    # rows of this rank's operator = voxels with a structurally non-zero entry; emulate with the support of |A| 1
+    support = O.backproject(rays[sl], P["xvec"], P["yvec"], P["zvec"], np.ones(g_loc.shape)).reshape(-1) != 0
+    row_voxels = torch.from_numpy(np.nonzero(support)[0].astype(np.int32))
+    V = acc.size
+    row_dst, union_voxels, n_union = sharding.union_index(row_voxels, V)
+    assert n_union >= row_voxels.numel() and bool((union_voxels[row_dst.long()] == row_voxels).all())
+    assert bool((union_voxels[1:] > union_voxels[:-1]).all())
+    acc_c = torch.zeros(n_union + 1, dtype=torch.float64)
+    acc_c[row_dst.long()] = torch.from_numpy(acc)[row_voxels.long()]
+    acc_c[n_union] = float(O.misfit(g_loc, dobs[sl], CdCt[sl]))
+    sharding.allreduce_sum_(acc_c)
+    grad = np.zeros(V)
+    uv = union_voxels.numpy()
+    grad[uv] = O.ne_from_m(P["m"], P["K_ne"]).reshape(-1)[uv] * acc_c[:n_union].numpy()
+    ref = O.gradient_exact(rays, g, dobs, i0, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], CdCt).reshape(-1)
+    S_ref = O.misfit(g, dobs, CdCt)
+    ok = np.abs(grad - ref).max() <= 1e-12 * np.abs(ref).max() and abs(float(acc_c[n_union]) - S_ref) <= 1e-12 * S_ref
     if rank == 0:
-        out.put(ok)
+        out.put(bool(ok))
     dist.destroy_process_group()
 
 
-def test_overlapped_apply_collectives_match_across_ranks_gloo():
+def test_compact_union_accumulator_gloo_world2():
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    port = 29700 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_overlap_worker, args=(r, 2, port, out)) for r in range(2)]
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_compact_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(120)
-        if p.is_alive():
-            p.terminate()
-            raise AssertionError("overlapped apply dead-locked")
+        p.join(180)
         assert p.exitcode == 0
     assert out.get(timeout=5) is True
+
+
+def test_direction_shard_and_union_index_single_process():
+    from ionotomo_b200 import sharding
+    assert [sharding.direction_shard(200, r, 8) for r in range(8)] == [(25 * r, 25 * r + 25) for r in range(8)]
+    row_dst, uv, n = sharding.union_index(torch.tensor([3, 4, 10], dtype=torch.int32), 16)
+    assert n == 3 and uv.tolist() == [3, 4, 10] and row_dst.tolist() == [0, 1, 2]
+    row_dst, uv, n = sharding.union_index(torch.zeros(0, dtype=torch.int32), 16)
+    assert n == 0 and uv.numel() == 0 and row_dst.numel() == 0

@@ -77,6 +77,24 @@ def main():
         out["prepared_plain"] = timeit(lambda: fp.tec(ne, out=tec), args.reps)
         del os.environ["IONO_FWD_LAYOUT"]
         out["prepared_quads"] = timeit(lambda: fp.tec_quads(quads, out=tec), args.reps)
+        q2 = torch.zeros_like(quads)
+        out["quads_from_m_touched"] = timeit(lambda: _lib.call("iono_forwardprojector_quads_from_m_f64", fp.handle,
+                                                               _lib.ptr(m), K / 1e13, _lib.ptr(q2), _lib.stream_ptr()),
+                                             args.reps)
+        out["fp_records"] = int(_lib.load().iono_forwardprojector_n_records(fp.handle))
+        t_ref = fp.tec_quads(quads).clone()
+        out["touched_quads_same_tec"] = bool(torch.equal(fp.tec_quads(q2), t_ref))
+        del q2
+        # launch-shape variants of the prepared forward (environment is read at every apply)
+        for name, env in (("w32_c64", {"IONO_PREP_WARPS": "32", "IONO_PREP_CHUNK": "64"}),
+                          ("w32_c64_s3", {"IONO_PREP_WARPS": "32", "IONO_PREP_CHUNK": "64", "IONO_PREP_STAGES": "3"}),
+                          ("w24_c64_s4", {"IONO_PREP_WARPS": "24", "IONO_PREP_CHUNK": "64", "IONO_PREP_STAGES": "4"}),
+                          ("w16_c128_s3", {"IONO_PREP_WARPS": "16", "IONO_PREP_CHUNK": "128", "IONO_PREP_STAGES": "3"})):
+            os.environ.update(env)
+            out["prepared_quads_" + name] = timeit(lambda: fp.tec_quads(quads, out=tec), args.reps)
+            assert torch.equal(tec, t_ref)
+            for k in env:
+                del os.environ[k]
     dobs = ib.forward_equation(rays, K, ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_true"]), 0)
     dobs = dobs + 0.01 * torch.randn_like(dobs)
     CdCt = torch.full_like(dobs, 1e-4)
@@ -99,6 +117,18 @@ def main():
         out["apply_runs%s" % runs] = timeit(lambda: bp.apply_permuted(perm, scale=ne, out=acc), args.reps)
         if runs == "1":
             ref = acc.clone()
+            out["apply_gradient"] = timeit(lambda: _lib.call("iono_backprojector_apply_gradient_f64", bp.handle,
+                                                             _lib.ptr(perm), _lib.ptr(m), K / 1e13, _lib.ptr(acc), 0, 16,
+                                                             _lib.stream_ptr()), args.reps)
+            out["apply_gradient_relerr"] = float(((acc - ref).abs().max() / ref.abs().max()).item())
+            out["bp_rows"] = int(_lib.load().iono_backprojector_n_rows(bp.handle))
+            for name, env in (("w8_c3", {"IONO_BP_CTAS": "3"}), ("w6_c5", {"IONO_BP_WARPS": "6", "IONO_BP_CTAS": "5"}),
+                              ("w4_c8", {"IONO_BP_WARPS": "4", "IONO_BP_CTAS": "8"})):
+                os.environ.update(env)
+                out["apply_runs1_" + name] = timeit(lambda: bp.apply_permuted(perm, scale=ne, out=acc), args.reps)
+                assert torch.equal(acc, ref)
+                for k in env:
+                    del os.environ[k]
         else:
             out["runs_vs_plain_equal"] = bool(torch.equal(ref, acc))
         del bp
