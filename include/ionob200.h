@@ -231,6 +231,9 @@ int iono_backprojector_apply_permuted_f64(iono_backprojector_t bp, const double 
  * rows the rays touch only, so no ne grid is needed. */
 int iono_backprojector_apply_gradient_f64(iono_backprojector_t bp, const double *coef_perm, const double *m,
                                           double k, double *out, int c0, int c1, void *stream);
+/* ne_out[v] = k * exp(m[v]) for the voxels of the operator's rows only (the other entries of ne_out are left
+ * untouched): the `scale` of the next apply without a pass over the whole grid. */
+int iono_backprojector_ne_rows_f64(iono_backprojector_t bp, const double *m, double k, double *ne_out, void *stream);
 /* Sharded rays (one process per GPU): row r of this rank's operator is stored, unscaled, at
  * out_compact[row_dst[r]]; the caller numbers the voxels that ANY rank touches consecutively (from
  * iono_backprojector_row_voxels of every rank), clears out_compact, and sums that compact vector across

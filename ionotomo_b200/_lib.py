@@ -58,6 +58,7 @@ SIGNATURES = {
     "iono_backprojector_apply_permuted_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "iono_backprojector_apply_gradient_f64": (_i, [_vp, _vp, _vp, _d, _vp, _i, _i, _vp]),
     "iono_backprojector_apply_compact_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "iono_backprojector_ne_rows_f64": (_i, [_vp, _vp, _d, _vp, _vp]),
     "iono_backprojector_n_rows": (ctypes.c_longlong, [_vp]),
     "iono_backprojector_row_voxels": (_i, [_vp, _vp, _vp]),
     "iono_backprojector_chunk_voxels": (ctypes.c_longlong, [_vp, _i]),
@@ -89,7 +90,7 @@ KERNEL_LAUNCHES = {
     "iono_gaussian_adjoint_f64": 1,
     "iono_backprojector_apply_f64": 4, "iono_backprojector_apply_chunks_f64": 3,
     "iono_backprojector_apply_permuted_f64": 3, "iono_backprojector_apply_gradient_f64": 3,
-    "iono_backprojector_apply_compact_f64": 3, "iono_forwardprojector_quads_from_m_f64": 1,
+    "iono_backprojector_apply_compact_f64": 3, "iono_backprojector_ne_rows_f64": 1, "iono_forwardprojector_quads_from_m_f64": 1,
     "iono_forwardprojector_create": 1, "iono_forwardprojector_apply_f64": 2, "iono_forwardprojector_apply_quads_f64": 1,
     "iono_peer_reduce_expand_f64": 1,
     "iono_quads_from_ne_f64": 1, "iono_ne_quads_from_m_f64": 1, "iono_tec_forward_quads_f64": 1, "iono_residual_f64": 1,

@@ -912,6 +912,27 @@ extern "C" int iono_backprojector_apply_compact_f64(iono_backprojector_t h, cons
                            (cudaStream_t)stream);
 }
 
+__global__ void __launch_bounds__(256) ne_rows_kernel(const unsigned int *__restrict__ row_voxel, long long n_rows,
+                                                      const double *__restrict__ m, double k, double *__restrict__ ne) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const unsigned int v = row_voxel[r];
+        ne[v] = k * exp(m[v]);
+    }
+}
+
+// ne_out[v] = k * exp(m[v]) for the voxels of the operator's rows only (the chain-rule factor the apply needs as
+// `scale`; the other voxels of ne_out are left untouched): ~1.6 M exps instead of a pass over the 8.4 M-voxel grid.
+extern "C" int iono_backprojector_ne_rows_f64(iono_backprojector_t h, const double *m, double k, double *ne_out,
+                                              void *stream) {
+    if (!h || !m || !ne_out) return fail(IONO_EBADARG, "iono_backprojector_ne_rows_f64: bad argument");
+    if (device_check(h->device, "iono_backprojector_ne_rows_f64")) return IONO_EBADARG;
+    if (h->n_rows == 0) return IONO_OK;
+    ne_rows_kernel<<<ew_grid(h->n_rows), 256, 0, (cudaStream_t)stream>>>(h->row_voxel, h->n_rows, m, k, ne_out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
 extern "C" long long iono_backprojector_n_rows(iono_backprojector_t h) { return h ? h->n_rows : 0; }
 
 // voxel index of every non-empty row, ascending (device array of n_rows uint32)

@@ -326,7 +326,9 @@ static int forwardprojector_apply(iono_forwardprojector_t h, const double *field
         CU_CHECK(cudaMemsetAsync(tec_out, 0, (size_t)h->R * sizeof(double), st));
         return IONO_OK;
     }
-    int warps = 24, stages = 2, chunk = (h->Ns <= 64) ? 64 : 128;
+    // 32 warps x 64-sample chunks: the kernel waits on its gathers (long-scoreboard stalls), so more warps per SM
+    // beat longer chunks -- 1.18 ms against 1.26 ms for 24 x 128 at the LOFAR case (profiles/r02_kernel_bench.json)
+    int warps = 32, stages = 2, chunk = 64;
     const char *e;
     if ((e = getenv("IONO_PREP_WARPS"))) warps = atoi(e);
     if ((e = getenv("IONO_PREP_STAGES"))) stages = atoi(e);

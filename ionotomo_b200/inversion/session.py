@@ -12,7 +12,8 @@ the step as ONE CUDA graph:
     quad records of ne = K exp(m)/1e13      iono_forwardprojector_quads_from_m_f64 (touched records only)
     TEC per ray                             iono_forwardprojector_apply_quads_f64  (or the stateless sweep)
     dTEC, misfit, adjoint coefficients      iono_residual_f64
-    gradient = ne * A^T coef                iono_backprojector_apply_gradient_f64  (or the scatter adjoint)
+    gradient = ne * A^T coef                iono_backprojector_ne_rows_f64 + iono_backprojector_apply_permuted_f64
+                                            (or the scatter adjoint)
 
 Sharded (``torch.distributed`` initialised, world size > 1; shard the direction or time axis so that the
 reference antenna is local): the forward needs no exchange; the back-projector of every rank writes into a
@@ -67,6 +68,7 @@ class DeviceSession(object):
         f64 = dict(dtype=torch.float64, device=dev)
         self.m = torch.empty(self.shape, **f64)                 # static input of the graph
         self.ne = torch.empty(self.shape, **f64) if self.bp is None else None
+        self.ne_rows = torch.empty(self.shape, **f64) if (self.bp is not None and not self.sharded) else None
         self.quads = quads_alloc(self.shape, dev)
         self.tec = torch.empty(self.ray_shape, **f64)
         self.dtec = torch.empty(self.ray_shape, **f64)
@@ -133,8 +135,11 @@ class DeviceSession(object):
             _lib.call("iono_backprojector_apply_compact_f64", self.bp.handle, _lib.ptr(self.coef_perm),
                       ctypes.c_void_p(self.row_dst.data_ptr()), _lib.ptr(self.acc_c), 0, 16, _lib.stream_ptr())
         elif self.bp is not None:
-            _lib.call("iono_backprojector_apply_gradient_f64", self.bp.handle, _lib.ptr(self.coef_perm),
-                      _lib.ptr(self.m), self.K_ne / TECU, _lib.ptr(self.grad), 0, 16, _lib.stream_ptr())
+            # chain-rule factor for the touched rows only, then the apply with `scale` (evaluating exp inside the
+            # apply kernel costs 0.2 ms at the LOFAR case: it runs once per segment, not once per row)
+            _lib.call("iono_backprojector_ne_rows_f64", self.bp.handle, _lib.ptr(self.m), self.K_ne / TECU,
+                      _lib.ptr(self.ne_rows), _lib.stream_ptr())
+            self.bp.apply_permuted(self.coef_perm, scale=self.ne_rows, out=self.grad)
         else:
             backproject(self.rays, self.grid, self.coef, self.shape, order=self.order, check_bounds=False,
                         out=self.grad)
