@@ -59,6 +59,9 @@ def parse():
                          "geometry, outside the timed steps, like the binned adjoint); sweep: stateless ray sweep")
     ap.add_argument("--adjoint", default="binned", choices=["binned", "scatter"],
                     help="binned: pre-assembled voxel-binned gather (default); scatter: stateless fp64 atomics")
+    ap.add_argument("--emulate-shard", type=int, default=0,
+                    help="ONE GPU: run rank 0's share of an N-way direction split through the sharded (compact "
+                         "accumulator) step without the link -- what one rank of N executes; for profiling only")
     ap.add_argument("--no-graph", action="store_true", help="launch the step kernel by kernel instead of replaying a CUDA graph")
     ap.add_argument("--no-verify", action="store_true", help="skip the single-GPU stateless recompute of S and the gradient")
     return ap.parse_args()
@@ -305,7 +308,12 @@ def main():
 
     nt = args.nt
     strong = world == 1 or args.scaling == "strong"
-    if strong:
+    if args.emulate_shard:
+        assert world == 1
+        nd_total = ND
+        d0, d1 = sharding.direction_shard(ND, 0, args.emulate_shard)
+        args.no_verify = args.no_e2e = True
+    elif strong:
         nd_total = ND
         d0, d1 = sharding.direction_shard(ND, rank, world)
     else:
@@ -348,7 +356,8 @@ def main():
     note = None
     try:
         ses = DeviceSession(rays, K_ne, m_tci, i0, dobs, CdCt, forward=args.forward, adjoint=args.adjoint,
-                            order=args.order, use_graph=not args.no_graph, keep_rays=True, reducer=args.reducer)
+                            order=args.order, use_graph=not args.no_graph, keep_rays=True, reducer=args.reducer,
+                            compact=bool(args.emulate_shard))
     except _lib.IonoError as exc:           # e.g. not enough free HBM for the assembly: stay on the GPU, stateless kernels
         if world > 1:
             raise
@@ -394,41 +403,59 @@ def main():
             clocks = sampler.window(t_load0, t_wall1)
             clocks["window"] = "warm-up + timed region"
 
-    # ---- per-kernel durations: the same calls, eagerly, with CUDA events around each (separate pass) ------
-    kt = {}
+    # ---- per-component durations: each call of the step captured REP times into its own CUDA graph and one
+    # replay timed with CUDA events on the launching stream (device time without host launch gaps) ----------
+    REP = 8
+    kms = {}
 
     def timed(name, fn):
-        a, b = ev(), ev()
-        a.record()
         fn()
-        b.record()
-        kt.setdefault(name, []).append((a, b))
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(REP):
+                fn()
+        ts = []
+        for _ in range(3):
+            if world > 1:
+                dist.barrier()
+                torch.cuda.synchronize()
+            a, b = ev(), ev()
+            a.record()
+            g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / REP)
+        kms[name] = float(np.median(ts))
 
     ses.m.copy_(m_dev)
-    for it in range(3 + min(args.steps, 20)):
-        if it == 3:
-            kt.clear()
-        if ses.fp is not None:
-            timed("quads_from_m", lambda: _lib.call("iono_forwardprojector_quads_from_m_f64", ses.fp.handle,
-                                                   _lib.ptr(ses.m), K_ne / 1e13, _lib.ptr(ses.quads), _lib.stream_ptr()))
-            timed("prepared_forward", lambda: ses.fp.tec_quads(ses.quads, out=ses.tec))
-        else:
-            timed("quads_from_m", lambda: ne_quads_from_m(ses.m, K_ne, ne_out=ses.ne, quads_out=ses.quads,
-                                                          want_ne=ses.ne is not None))
-            timed("ray_sweep_forward", lambda: tec_from_quads(ses.rays, grid, ses.quads, order=args.order,
-                                                              check_bounds=False, out=ses.tec, oob=ses.oob))
-        if ses.fp is not None and ses.ne is not None:
-            _lib.call("iono_ne_from_m_f64", _lib.ptr(ses.m), ses.m.numel(), K_ne / 1e13, _lib.ptr(ses.ne), _lib.stream_ptr())
-        timed("residual", ses._enqueue_residual)
-        timed("binned_adjoint" if ses.bp is not None else "ray_sweep_adjoint_scatter", ses._enqueue_adjoint)
-        if ses.sharded:
-            if world > 1:
-                dist.barrier()          # time the collective, not the arrival skew of the ranks
-            if args.reducer == "nccl":
-                timed("allreduce_nccl", lambda: dist.all_reduce(ses.acc_c))
-            timed("peer_reduce_expand" if args.reducer == "peer" else "expand", ses._enqueue_reduce)
+    if ses.fp is not None:
+        timed("quads_from_m", lambda: _lib.call("iono_forwardprojector_quads_from_m_f64", ses.fp.handle,
+                                               _lib.ptr(ses.m), K_ne / 1e13, _lib.ptr(ses.quads), _lib.stream_ptr()))
+        timed("prepared_forward", lambda: ses.fp.tec_quads(ses.quads, out=ses.tec))
+    else:
+        timed("quads_from_m", lambda: ne_quads_from_m(ses.m, K_ne, ne_out=ses.ne, quads_out=ses.quads,
+                                                      want_ne=ses.ne is not None))
+        timed("ray_sweep_forward", lambda: tec_from_quads(ses.rays, grid, ses.quads, order=args.order,
+                                                          check_bounds=False, out=ses.tec, oob=ses.oob))
+    timed("residual", ses._enqueue_residual)
+    timed("binned_adjoint" if ses.bp is not None else "ray_sweep_adjoint_scatter", ses._enqueue_adjoint)
+    if ses.sharded:
+        if world > 1 and args.reducer == "nccl":
+            ts = []
+            for _ in range(5):
+                dist.barrier()
+                torch.cuda.synchronize()
+                a, b = ev(), ev()
+                a.record()
+                dist.all_reduce(ses.acc_c)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            kms["allreduce_nccl"] = float(np.median(ts))
+        timed("peer_reduce_expand" if (world > 1 and args.reducer == "peer") else "expand", ses._enqueue_reduce)
+    ses.misfit_and_gradient(m_dev)          # leave the session's buffers in the state of a whole step
     torch.cuda.synchronize()
-    kms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in kt.items()}
 
     # ---- verification: S and the gradient against a single-GPU recompute with the STATELESS kernels ----------
     verify = None
@@ -560,8 +587,8 @@ def main():
                      "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_note,
                      "peak_source": peak_src},
         "kernels": kernels,
-        "kernel_timing": "separate eager pass of the same calls with CUDA events around each (the timed region "
-                         "replays them as one CUDA graph)",
+        "kernel_timing": "separate pass: each call of the step captured 8x into its own CUDA graph, one replay timed "
+                         "with CUDA events (the timed region replays the whole step as one CUDA graph)",
         "pass_frac_of_hbm_roofline": (bytes_fwd + bytes_adj) / ms / 1e6 / hbm,     # per GPU: this rank's rays
         "setup_once_per_geometry": {"ray_generation_ms": cast_ms, "operators_build_s": build_s,
                                     "amortised_ms_per_step_over_50_iterations": ms + (build_s * 1e3 + cast_ms) / 50.0},

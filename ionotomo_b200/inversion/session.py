@@ -35,7 +35,7 @@ from .gradient import BackProjector, backproject, residual
 
 class DeviceSession(object):
     def __init__(self, rays, K_ne, m_tci, i0, dobs, CdCt, forward="prepared", adjoint="binned", order="time",
-                 use_graph=True, keep_rays=None, check_bounds=True, group=None, reducer="peer"):
+                 use_graph=True, keep_rays=None, check_bounds=True, group=None, reducer="peer", compact=None):
         lib = _lib.load()
         self.rays = _lib.to_device(rays)
         Na, Nt, Nd, four, Ns = self.rays.shape
@@ -54,7 +54,10 @@ class DeviceSession(object):
         assert forward in ("prepared", "sweep") and adjoint in ("binned", "scatter")
         self.group = group
         self.rank, self.world = sharding.world() if group is None else (dist.get_rank(group), dist.get_world_size(group))
-        self.sharded = self.world > 1
+        # compact=True on a single process: the sharded step without the link (what one rank does; profiling)
+        self.sharded = self.world > 1 or bool(compact)
+        if self.world == 1 and self.sharded:
+            reducer = "nccl"
         if self.sharded:
             assert adjoint == "binned", "sharded rays: the compact accumulator is written by the binned adjoint"
             assert reducer in ("peer", "nccl")
@@ -187,7 +190,8 @@ class DeviceSession(object):
         self._run("forward", fn)
         if self.sharded:
             self.S.copy_(self.S_local)
-            dist.all_reduce(self.S, group=self.group)
+            if self.world > 1:
+                dist.all_reduce(self.S, group=self.group)
         return self.dtec, self.S[0]
 
     def misfit_and_gradient(self, m=None):
@@ -202,7 +206,8 @@ class DeviceSession(object):
                 self._enqueue_residual()
                 self._enqueue_adjoint()
             self._run("step_a", fa)
-            dist.all_reduce(self.acc_c, group=self.group)
+            if self.world > 1:
+                dist.all_reduce(self.acc_c, group=self.group)
             self._run("step_b", self._enqueue_reduce)
         else:
             def fn():
@@ -219,7 +224,8 @@ class DeviceSession(object):
         self.n_gradient += 1
         if self.sharded and self.reducer_kind == "nccl":
             self._run("adjoint_a", self._enqueue_adjoint)
-            dist.all_reduce(self.acc_c, group=self.group)
+            if self.world > 1:
+                dist.all_reduce(self.acc_c, group=self.group)
             self._run("step_b", self._enqueue_reduce)
         else:
             def fn():
