@@ -134,8 +134,8 @@ int iono_adjoint_coef_f64(const double *g, const double *dobs, const double *CdC
  * (forward_equation.py:50), misfit_out[0] = sum((dtec-dobs)^2/(CdCt+1e-15))/2 (line_search.py:48-49),
  * coef_out as iono_adjoint_coef_f64 (may be NULL), coef_perm_out = the same coefficients in the
  * back-projector's internal order (antenna, direction, time) for iono_backprojector_apply_permuted_f64
- * (may be NULL).  scratch: iono_residual_scratch_elems() doubles.  Deterministic. */
-int64_t iono_residual_scratch_elems(void);
+ * (may be NULL).  scratch: iono_residual_scratch_elems(Na, Nt, Nd) doubles.  Deterministic. */
+int64_t iono_residual_scratch_elems(int Na, int Nt, int Nd);
 int iono_residual_f64(const double *tec, const double *dobs, const double *CdCt, int Na, int Nt, int Nd,
                       int i0, double *dtec_out, double *coef_out, double *coef_perm_out, double *scratch,
                       double *misfit_out, void *stream);

@@ -39,7 +39,7 @@ SIGNATURES = {
     "iono_quads_from_ne_f64": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "iono_ne_quads_from_m_f64": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp]),
     "iono_tec_forward_quads_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "iono_residual_scratch_elems": (_i64, []),
+    "iono_residual_scratch_elems": (_i64, [_i, _i, _i]),
     "iono_residual_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "iono_dtec_f64": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "iono_adjoint_coef_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -284,13 +284,18 @@ __global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *
             while (true) {
                 const int nb = min(n_rows - r0, 31);
                 double mysum = 0.0;
-                for (int q = 0; q < nb; ++q) {
-                    const long long b = __shfl_sync(0xffffffffu, myptr, q), e = __shfl_sync(0xffffffffu, myptr, q + 1);
-                    const int lo = (int)(max(b, k0) - k0), hi = (int)(min(e, k1) - k0);
+                for (int q0 = 0; q0 < nb; q0 += 4) {   // as in backproject_wruns_kernel: four rows at a time
+                    const int q = q0 + (lane >> 3);
+                    const long long b = __shfl_sync(0xffffffffu, myptr, min(q, 31)),
+                                    e = __shfl_sync(0xffffffffu, myptr, min(q + 1, 31));
+                    const int lo = (int)(max(b, k0) - k0), hi = (q < nb) ? (int)(min(e, k1) - k0) : lo;
                     double s = 0.0;
-                    for (int j = lo + lane; j < hi; j += 32) s += prod[j];
-                    s = warp_sum(s);
-                    if (lane == q) mysum = s;
+                    for (int j = lo + (lane & 7); j < hi; j += 8) s += prod[j];
+                    s += __shfl_xor_sync(0xffffffffu, s, 4);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    const double t = __shfl_sync(0xffffffffu, s, ((lane - q0) & 3) << 3);
+                    if (lane >= q0 && lane < q0 + 4) mysum = t;
                 }
                 const long long mye = __shfl_down_sync(0xffffffffu, myptr, 1);
                 if (lane < nb) {
@@ -479,13 +484,19 @@ __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__re
             while (true) {
                 const int nb = min(n_rows - r0, 31);
                 double mysum = 0.0;
-                for (int q = 0; q < nb; ++q) {
-                    const int b = __shfl_sync(0xffffffffu, pb, q), e = __shfl_sync(0xffffffffu, pb, q + 1);
-                    const int lo = max(b, 0), hi = min(e, kend);
+                // four rows at a time, one per group of 8 lanes (rows of a multi-row segment are short: a whole
+                // warp per row spent most of its time in the shuffle tree)
+                for (int q0 = 0; q0 < nb; q0 += 4) {
+                    const int q = q0 + (lane >> 3);
+                    const int b = __shfl_sync(0xffffffffu, pb, min(q, 31)), e = __shfl_sync(0xffffffffu, pb, min(q + 1, 31));
+                    const int lo = max(b, 0), hi = (q < nb) ? min(e, kend) : lo;
                     double s = 0.0;
-                    for (int j = lo + lane; j < hi; j += 32) s += prod[j];
-                    s = warp_sum(s);
-                    if (lane == q) mysum = s;
+                    for (int j = lo + (lane & 7); j < hi; j += 8) s += prod[j];
+                    s += __shfl_xor_sync(0xffffffffu, s, 4);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    const double t = __shfl_sync(0xffffffffu, s, ((lane - q0) & 3) << 3);   // row q0+i sits in group i
+                    if (lane >= q0 && lane < q0 + 4) mysum = t;
                 }
                 const int mye = __shfl_down_sync(0xffffffffu, pb, 1);
                 if (lane < nb) {
@@ -526,7 +537,9 @@ __global__ void __launch_bounds__(256) backproject_combine_short_kernel(const in
     }
 }
 
-// One warp per straddling row: add its partials in segment order.
+// One warp per straddling row with partials in more than 8 segments (the heaviest voxels sit under the array core
+// and collect ~1e6 entries = thousands of segments): every lane keeps 8 independent loads in flight, fixed
+// reduction tree.
 __global__ void __launch_bounds__(256) backproject_combine_kernel(const int *__restrict__ rows, int n_rows,
                                                                    int BP_SEG,
                                                                    const long long *__restrict__ ptr,
@@ -542,11 +555,16 @@ __global__ void __launch_bounds__(256) backproject_combine_kernel(const int *__r
         const long long v = row_voxel[row];
         const long long b = ptr[row], e = ptr[row + 1];
         const long long s_first = b / BP_SEG, s_last = (e - 1) / BP_SEG;
-        double s = 0.0;
-        for (long long sg = s_first + lane; sg <= s_last; sg += 32) {
-            const int slot = (sg == s_first && b > sg * BP_SEG) ? 1 : 0;
-            s += partial[2 * sg + slot];
+        const int first_slot = (b > s_first * BP_SEG) ? 1 : 0;
+        double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        for (long long sg = s_first + lane; sg <= s_last; sg += 256) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const long long q = sg + 32 * u;
+                if (q <= s_last) a[u] += partial[2 * q + (q == s_first ? first_slot : 0)];
+            }
         }
+        double s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
         s = warp_sum(s);
         if (lane == 0) out[v] = s * row_scale(scale, (unsigned int)v);
     }

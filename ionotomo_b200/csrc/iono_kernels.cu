@@ -562,99 +562,131 @@ extern "C" int iono_misfit_f64(const double *g, const double *dobs, const double
 // order).  A CTA owns 8 times x 32 directions and walks the antennas, so the coefficients can also be written
 // in the back-projector's internal (antenna, direction, time) order through a shared-memory transpose.
 // ---------------------------------------------------------------------------
-constexpr int RES_TT = 8, RES_TD = 32, RES_AG = 8;   // tile of 8 times x 32 directions, 8 antennas per round
+constexpr int RES_TT = 8, RES_TD = 32, RES_AG = 8;   // tile of 8 times x 32 directions, 8 antennas per work item
+constexpr int RES_MAX_CTAS = 2048;
+
+// Work item = (tile, antenna group): items are independent except for the sum over antennas in the reference
+// antenna's coefficient, which the LAST item of a tile to finish forms from the per-group partial sums in group
+// order (fixed order => reproducible).  With one item per CTA the kernel is one memory round trip deep instead
+// of Na/8 (it was latency-bound: 44 us at the LOFAR case whatever the number of rays).
+struct ResidualScratch {
+    double *partial;          // [RES_MAX_CTAS] misfit partials
+    double *psum;             // [groups][tiles][256] sum of dd over the group's antennas
+    double *ddref;            // [tiles][256] dd of the reference antenna
+    unsigned int *tile_count; // [tiles] arrivals per tile
+    unsigned int *counter;    // arrivals of CTAs
+};
 
 __global__ void __launch_bounds__(256) residual_kernel(const double *__restrict__ tec, const double *__restrict__ dobs,
                                                         const double *__restrict__ CdCt, int Na, int Nt, int Nd, int i0,
                                                         double *__restrict__ dtec, double *__restrict__ coef,
-                                                        double *__restrict__ coef_perm, double *__restrict__ scratch,
-                                                        unsigned int *counter, double *__restrict__ out_S) {
+                                                        double *__restrict__ coef_perm, ResidualScratch sc,
+                                                        double *__restrict__ out_S) {
     __shared__ double tile[RES_AG][RES_TT][RES_TD + 1];
-    __shared__ bool last;
+    __shared__ bool last_of_tile, last;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int dl = threadIdx.x >> 3, tl = threadIdx.x & 7;   // transposed role: direction, time within the tile
     const int tiles_d = (Nd + RES_TD - 1) / RES_TD, tiles_t = (Nt + RES_TT - 1) / RES_TT;
+    const int tiles = tiles_d * tiles_t, groups = (Na + RES_AG - 1) / RES_AG;
     const long long ntd = (long long)Nt * Nd;
     double S = 0.0;
-    for (int b = blockIdx.x; b < tiles_d * tiles_t; b += gridDim.x) {
+    for (int item = blockIdx.x; item < tiles * groups; item += gridDim.x) {
+        const int b = item / groups, grp = item - b * groups, a0 = grp * RES_AG;
         const int t0 = (b / tiles_d) * RES_TT, d0 = (b % tiles_d) * RES_TD;
         const int t = t0 + ty, d = d0 + tx;
         const bool ok = t < Nt && d < Nd;
         const bool okT = (d0 + dl < Nd) && (t0 + tl < Nt);
         const long long j = (long long)t * Nd + d;
         const double ref = ok ? tec[(long long)i0 * ntd + j] : 0.0;
-        double sum = 0.0, dd_ref = 0.0;
-        // antennas in rounds of RES_AG: the loads of a round are independent (8 x 3 in flight per thread) and
-        // one barrier pair serves the transposed stores of the whole round; the sum over antennas stays in
-        // antenna order
-        for (int a0 = 0; a0 < Na; a0 += RES_AG) {
-            double tv[RES_AG], ov[RES_AG], cv[RES_AG];
+        double tv[RES_AG], ov[RES_AG], cv[RES_AG];
 #pragma unroll
-            for (int u = 0; u < RES_AG; ++u) {
-                const bool in = ok && (a0 + u < Na);
-                const long long k = (long long)(a0 + u) * ntd + j;
-                tv[u] = in ? tec[k] : 0.0;
-                ov[u] = in ? dobs[k] : 0.0;
-                cv[u] = in ? CdCt[k] : 1.0;
+        for (int u = 0; u < RES_AG; ++u) {   // 8 x 3 independent loads in flight per thread
+            const bool in = ok && (a0 + u < Na);
+            const long long k = (long long)(a0 + u) * ntd + j;
+            tv[u] = in ? tec[k] : 0.0;
+            ov[u] = in ? dobs[k] : 0.0;
+            cv[u] = in ? CdCt[k] : 1.0;
+        }
+        double sum = 0.0, dd_ref = 0.0;
+        __syncthreads();     // the previous item's reads of `tile` are done
+#pragma unroll
+        for (int u = 0; u < RES_AG; ++u) {
+            const int a = a0 + u;
+            double dd = 0.0;
+            if (ok && a < Na) {
+                const long long k = (long long)a * ntd + j;
+                const double g = tv[u] - ref;
+                const double r = g - ov[u];
+                dd = r / (cv[u] + 1e-15);
+                S = fma(r, dd, S);
+                sum += dd;
+                dtec[k] = g;
+                if (a == i0) dd_ref = dd;
+                else if (coef) coef[k] = dd;
             }
-            if (coef_perm) __syncthreads();     // the previous round's transposed reads are done
+            tile[u][ty][tx] = dd;
+        }
+        sc.psum[((long long)grp * tiles + b) * 256 + threadIdx.x] = sum;
+        if (i0 >= a0 && i0 < a0 + RES_AG) sc.ddref[(long long)b * 256 + threadIdx.x] = dd_ref;
+        __syncthreads();
+        if (coef_perm) {
 #pragma unroll
             for (int u = 0; u < RES_AG; ++u) {
                 const int a = a0 + u;
-                double dd = 0.0;
-                if (ok && a < Na) {
-                    const long long k = (long long)a * ntd + j;
-                    const double g = tv[u] - ref;
-                    const double r = g - ov[u];
-                    const double w = cv[u] + 1e-15;
-                    dd = r / w;
-                    S += r * r / w;
-                    sum += dd;
-                    dtec[k] = g;
-                    if (a == i0) dd_ref = dd;
-                    else if (coef) coef[k] = dd;
-                }
-                if (coef_perm) tile[u][ty][tx] = dd;
-            }
-            if (coef_perm) {
-                __syncthreads();
-#pragma unroll
-                for (int u = 0; u < RES_AG; ++u) {
-                    const int a = a0 + u;
-                    if (okT && a < Na && a != i0)
-                        coef_perm[((long long)a * Nd + d0 + dl) * Nt + t0 + tl] = tile[u][tl][dl];
-                }
+                if (okT && a < Na && a != i0)
+                    coef_perm[((long long)a * Nd + d0 + dl) * Nt + t0 + tl] = tile[u][tl][dl];
             }
         }
-        // reference antenna: c = dd - sum over antennas (the -tec[i0] term of dTEC, transposed)
-        const double c_ref = dd_ref - sum;
-        if (ok && coef) coef[(long long)i0 * ntd + j] = c_ref;
-        if (coef_perm) {
-            __syncthreads();
-            tile[0][ty][tx] = c_ref;
-            __syncthreads();
-            if (okT) coef_perm[((long long)i0 * Nd + d0 + dl) * Nt + t0 + tl] = tile[0][tl][dl];
+        // reference antenna: c = dd - sum over ALL antennas (the -tec[i0] term of dTEC, transposed), formed by the
+        // last group of this tile to arrive
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last_of_tile = (atomicAdd(sc.tile_count + b, 1u) == (unsigned int)groups - 1u);
+        }
+        __syncthreads();
+        if (last_of_tile) {
+            __threadfence();
+            double total = 0.0;
+            for (int q = 0; q < groups; ++q) total += __ldcg(sc.psum + ((long long)q * tiles + b) * 256 + threadIdx.x);
+            const double c_ref = __ldcg(sc.ddref + (long long)b * 256 + threadIdx.x) - total;
+            if (ok && coef) coef[(long long)i0 * ntd + j] = c_ref;
+            if (coef_perm) {
+                tile[0][ty][tx] = c_ref;
+                __syncthreads();
+                if (okT) coef_perm[((long long)i0 * Nd + d0 + dl) * Nt + t0 + tl] = tile[0][tl][dl];
+            }
+            if (threadIdx.x == 0) sc.tile_count[b] = 0u;
         }
     }
     // misfit: per-CTA partial, the last CTA to arrive adds the partials in CTA order
     __syncthreads();
     S = block_sum_256(S);
     if (threadIdx.x == 0) {
-        scratch[blockIdx.x] = S;
+        sc.partial[blockIdx.x] = S;
         __threadfence();
-        last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+        last = (atomicAdd(sc.counter, 1u) == gridDim.x - 1);
     }
     __syncthreads();
     if (last) {
         __threadfence();
         double s = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(scratch + i);
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(sc.partial + i);
         s = block_sum_256(s);
-        if (threadIdx.x == 0) { out_S[0] = 0.5 * s; *counter = 0u; }
+        if (threadIdx.x == 0) { out_S[0] = 0.5 * s; *sc.counter = 0u; }
     }
 }
 
-extern "C" int64_t iono_residual_scratch_elems(void) { return MISFIT_BLOCKS + 1; }
+static void residual_layout(int Na, int Nt, int Nd, long long &tiles, long long &groups, long long &elems) {
+    tiles = (long long)((Nd + RES_TD - 1) / RES_TD) * ((Nt + RES_TT - 1) / RES_TT);
+    groups = (Na + RES_AG - 1) / RES_AG;
+    elems = RES_MAX_CTAS + (groups + 1) * tiles * 256 + (tiles + 2 + 1) / 2 + 1;
+}
+
+extern "C" int64_t iono_residual_scratch_elems(int Na, int Nt, int Nd) {
+    long long tiles, groups, elems;
+    residual_layout(Na < 1 ? 1 : Na, Nt < 1 ? 1 : Nt, Nd < 1 ? 1 : Nd, tiles, groups, elems);
+    return elems;
+}
 
 extern "C" int iono_residual_f64(const double *tec, const double *dobs, const double *CdCt, int Na, int Nt, int Nd,
                                  int i0, double *dtec_out, double *coef_out, double *coef_perm_out, double *scratch,
@@ -668,12 +700,20 @@ extern "C" int iono_residual_f64(const double *tec, const double *dobs, const do
     }
     if (!tec || !dobs || !CdCt || !dtec_out || i0 < 0 || i0 >= Na)
         return fail(IONO_EBADARG, "iono_residual_f64: bad argument");
-    const int tiles = ((Nd + RES_TD - 1) / RES_TD) * ((Nt + RES_TT - 1) / RES_TT);
-    const int blocks = tiles < MISFIT_BLOCKS ? tiles : MISFIT_BLOCKS;
-    unsigned int *counter = reinterpret_cast<unsigned int *>(scratch + MISFIT_BLOCKS);
-    CU_CHECK(cudaMemsetAsync(counter, 0, sizeof(double), st));
-    residual_kernel<<<blocks, 256, 0, st>>>(tec, dobs, CdCt, Na, Nt, Nd, i0, dtec_out, coef_out, coef_perm_out, scratch,
-                                            counter, misfit_out);
+    long long tiles, groups, elems;
+    residual_layout(Na, Nt, Nd, tiles, groups, elems);
+    if (tiles * groups > 0x7fffffffLL) return fail(IONO_EBADARG, "iono_residual_f64: too many rays");
+    ResidualScratch sc;
+    sc.partial = scratch;
+    sc.psum = scratch + RES_MAX_CTAS;
+    sc.ddref = sc.psum + groups * tiles * 256;
+    sc.tile_count = reinterpret_cast<unsigned int *>(sc.ddref + tiles * 256);
+    sc.counter = sc.tile_count + tiles;
+    CU_CHECK(cudaMemsetAsync(sc.tile_count, 0, (size_t)(tiles + 1) * sizeof(unsigned int), st));
+    const long long items = tiles * groups;
+    const int blocks = (int)(items < RES_MAX_CTAS ? items : RES_MAX_CTAS);
+    residual_kernel<<<blocks, 256, 0, st>>>(tec, dobs, CdCt, Na, Nt, Nd, i0, dtec_out, coef_out, coef_perm_out, sc,
+                                            misfit_out);
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
 }

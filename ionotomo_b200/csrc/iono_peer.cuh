@@ -38,15 +38,17 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-// peer data: system-scope relaxed (volatile) loads -- never from a stale L1 line -- and plain stores
+// Peer data: relaxed system-scope loads (never served from a stale L1 line).  `asm volatile` keeps them below the
+// flag wait (which ends in __syncthreads()) and in program order; there is no memory clobber and the callers
+// issue all loads of a step before the first use, so 2N requests per thread are in flight over the link.
 __device__ __forceinline__ double2 ld_peer_v2(const double *p) {
     double2 v;
-    asm volatile("ld.volatile.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
     return v;
 }
 __device__ __forceinline__ double ld_peer(const double *p) {
     double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
     return v;
 }
 
@@ -82,21 +84,33 @@ __global__ void __launch_bounds__(256) peer_reduce_expand_kernel(PeerTable T, in
     const long long pairs = L / 2;
     const long long p0 = pairs * me / N, p1 = pairs * (me + 1) / N;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += stride) {
-        double2 s = make_double2(0.0, 0.0);
-#pragma unroll 4
-        for (int r = 0; r < N; ++r) {
-            const double2 v = ld_peer_v2(T.acc[r] + 2 * p);
-            s.x += v.x;
-            s.y += v.y;
-        }
-#pragma unroll 4
-        for (int r = 0; r < N; ++r) *reinterpret_cast<double2 *>(T.res[r] + 2 * p) = s;
+    for (long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += 2 * stride) {
+        const bool two = p + stride < p1;
+        double2 v[IONO_MAX_PEERS], u[IONO_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < IONO_MAX_PEERS; ++r)     // all loads of both elements first: 2N requests in flight per thread
+            if (r < N) {
+                v[r] = ld_peer_v2(T.acc[r] + 2 * p);
+                u[r] = two ? ld_peer_v2(T.acc[r] + 2 * (p + stride)) : make_double2(0.0, 0.0);
+            }
+        double2 s = make_double2(0.0, 0.0), w = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r < IONO_MAX_PEERS; ++r)     // rank order: the same bits on every rank
+            if (r < N) { s.x += v[r].x; s.y += v[r].y; w.x += u[r].x; w.y += u[r].y; }
+#pragma unroll
+        for (int r = 0; r < IONO_MAX_PEERS; ++r)
+            if (r < N) {
+                *reinterpret_cast<double2 *>(T.res[r] + 2 * p) = s;
+                if (two) *reinterpret_cast<double2 *>(T.res[r] + 2 * (p + stride)) = w;
+            }
     }
-    // every CTA's peer stores must be out before the slice is announced: last CTA to arrive signals
-    __threadfence_system();
+    // every CTA's peer stores must be out before the slice is announced: the CTA barrier orders the threads'
+    // stores before thread 0's system-scope fence (cumulative), the last CTA to arrive signals
     __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(arrivals, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = (atomicAdd(arrivals, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (last) {
         if ((int)threadIdx.x < N) {
@@ -109,8 +123,9 @@ __global__ void __launch_bounds__(256) peer_reduce_expand_kernel(PeerTable T, in
     if (blockIdx.x == 0 && threadIdx.x == 0) *calls = epoch;
     // 4. expansion with the chain-rule factor; the last element of the vector is the summed misfit
     const double *res = T.res[me];
+#pragma unroll 4
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_union; i += stride) {
-        const int v = voxel[i];
+        const int v = __ldg(voxel + i);
         grad[v] = k * exp(__ldg(m + v)) * ld_peer(res + i);
     }
     if (misfit_out && blockIdx.x == 0 && threadIdx.x == 0) misfit_out[0] = ld_peer(res + n_union);

@@ -46,7 +46,7 @@ def residual(tec, dobs, CdCt, i0, want_coef=True, want_perm=False, out=None):
             else torch.empty(Na * Nt * Nd, dtype=torch.float64, device=dev)) if want_perm else None
     scratch = out.get("scratch")
     if scratch is None:
-        scratch = torch.empty(int(lib.iono_residual_scratch_elems()), dtype=torch.float64, device=dev)
+        scratch = torch.empty(int(lib.iono_residual_scratch_elems(Na, Nt, Nd)), dtype=torch.float64, device=dev)
     S = out.get("S") if out.get("S") is not None else torch.empty(1, dtype=torch.float64, device=dev)
     _lib.call("iono_residual_f64", _lib.ptr(tec), _lib.ptr(dobs), _lib.ptr(CdCt), Na, Nt, Nd, int(i0), _lib.ptr(dtec),
               _lib.ptr(coef) if coef is not None else None, _lib.ptr(perm) if perm is not None else None,

@@ -77,7 +77,7 @@ class DeviceSession(object):
         self.dtec = torch.empty(self.ray_shape, **f64)
         self.coef = torch.empty(self.ray_shape, **f64) if self.bp is None else None
         self.coef_perm = torch.empty(Na * Nt * Nd, **f64) if self.bp is not None else None
-        self.scratch = torch.empty(int(lib.iono_residual_scratch_elems()), **f64)
+        self.scratch = torch.empty(int(lib.iono_residual_scratch_elems(Na, Nt, Nd)), **f64)
         self.S = torch.zeros(1, **f64)
         self.S_local = self.S
         self.grad = torch.zeros(self.shape, **f64)     # voxels no ray touches stay zero for the whole session

@@ -845,8 +845,12 @@ def test_fused_residual_kernel(ib, shape, i0):
     coef0 = adjoint_coefficients(g0, dobs, C, i0)
     S0 = float(misfit(g0, dobs, C))
     g1, S1, coef1, perm1 = residual(tec, dobs, C, i0, want_coef=True, want_perm=True)
-    assert torch.equal(g1, g0) and torch.equal(coef1, coef0)
-    assert torch.equal(perm1.reshape(Na, Nd, Nt), coef0.permute(0, 2, 1).contiguous())
+    assert torch.equal(g1, g0)
+    # the reference antenna's coefficient sums dd over the antennas in groups of 8: last-bit differences there
+    others = [a for a in range(Na) if a != i0]
+    assert torch.equal(coef1[others], coef0[others])
+    assert float((coef1 - coef0).abs().max()) <= 1e-13 * float(coef0.abs().max())
+    assert torch.equal(perm1.reshape(Na, Nd, Nt), coef1.permute(0, 2, 1).contiguous())
     assert abs(float(S1) - S0) <= 1e-13 * abs(S0)
     tn = tec.cpu().numpy()
     gn = tn - tn[i0]
