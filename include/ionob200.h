@@ -198,6 +198,13 @@ int iono_gaussian_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int 
 int iono_phase_integrals_f64(iono_grid_t grid, const double *ne, const double *dmu, const double *rays,
                              int Na, int Nt, int Nd, int Ns, const double *freqs_host, int Nf, int order,
                              double *out, unsigned long long *oob_count, void *stream);
+/* Simpson integration (old scipy even='avg') of integrands tabulated at the ray samples along the rays' s rows:
+ * out[ray*out_stride] = simps(f(y[ray,:]), s[ray,:]);  mode 0: f = y;  mode 1: f = 1 - sqrt(1 + y*c);
+ * mode 2: f = y/sqrt(1 + y*c) * y2.  y, y2: (nrays,Ns); rays: (nrays,4,Ns).  The integrate-after-interpolate
+ * order of the reference's generation B (iterative_newton.py:108-119, :157-179), used for its bit-compatible
+ * reproduction including the axis scramble of TriCubic.interp on 4-D inputs (geometry/tri_cubic.py:69-70). */
+int iono_simps_rows_f64(const double *y, const double *y2, const double *rays, int64_t nrays, int Ns, int mode,
+                        double c, double *out, int out_stride, void *stream);
 /* penalty == 0: out = const[a] + 2 pi nu clock[a,t] - (2 pi nu/c)(I - I[i0])   (iterative_newton.py:107-123)
  * penalty != 0: out = -(2 pi nu/(2 n_p c))(I - I[i0])                          (iterative_newton.py:166-183) */
 int iono_phase_assemble_f64(const double *integrals, int Na, int Nt, int Nd, int Nf, int i0,

@@ -51,6 +51,7 @@ SIGNATURES = {
     "iono_chord_adjoint_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "iono_gaussian_adjoint_f64": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _d, _d, _i, _i, _vp, _vp]),
     "iono_phase_integrals_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "iono_simps_rows_f64": (_i, [_vp, _vp, _vp, _i64, _i, _i, _d, _vp, _i, _vp]),
     "iono_phase_assemble_f64": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "iono_backprojector_create": (_i, [_vp, _vp, _i, _i, _i, _i, ctypes.POINTER(_vp), _vp, _vp]),
     "iono_backprojector_apply_f64": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -86,7 +87,7 @@ KERNEL_LAUNCHES = {
     "iono_cast_rays_frames_f64": 1, "iono_ne_to_refractive_index_f64": 1, "iono_optical_path_f64": 1,
     "iono_tci_interp_f64": 1, "iono_tec_forward_f64": 1, "iono_dtec_f64": 1, "iono_adjoint_coef_f64": 1,
     "iono_tec_adjoint_f64": 1, "iono_misfit_f64": 2, "iono_convolve3d_nearest_f64": 1,
-    "iono_phase_integrals_f64": 1, "iono_phase_assemble_f64": 1, "iono_chord_adjoint_f64": 1,
+    "iono_phase_integrals_f64": 1, "iono_simps_rows_f64": 1, "iono_phase_assemble_f64": 1, "iono_chord_adjoint_f64": 1,
     "iono_gaussian_adjoint_f64": 1,
     "iono_backprojector_apply_f64": 4, "iono_backprojector_apply_chunks_f64": 3,
     "iono_backprojector_apply_permuted_f64": 3, "iono_backprojector_apply_gradient_f64": 3,

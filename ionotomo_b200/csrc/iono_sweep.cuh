@@ -653,3 +653,53 @@ extern "C" int iono_phase_assemble_f64(const double *integrals, int Na, int Nt, 
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Simpson integration of tabulated integrands along the rays' s rows: out[ray*out_stride] =
+// simps(f(y[ray,:]), s[ray,:]) with scipy's old even='avg' rule (the per-sample weights of the sweep).
+//   mode 0: f = y;   mode 1: f = 1 - sqrt(1 + y * c)   (phase integrand, c = -1/n_p);
+//   mode 2: f = y / sqrt(1 + y * c) * y2               (prior-penalty integrand)
+// Used by the reference-compatible phase operators, which interpolate first (TriCubic.interp on 4-D inputs,
+// with the reference's axis scramble, geometry/tri_cubic.py:69-70) and integrate afterwards
+// (iterative_newton.py:108-119, :157-179).  Warp per ray.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) simps_rows_kernel(const double *__restrict__ y, const double *__restrict__ y2,
+                                                         const double *__restrict__ rays, long long R, int Ns,
+                                                         int mode, double c, double *__restrict__ out,
+                                                         int out_stride) {
+    const int lane = threadIdx.x & 31;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const bool n_odd = Ns & 1;
+    for (long long ray = warp_global; ray < R; ray += n_warps) {
+        const double *sp = rays + ray * 4 * Ns + 3 * (long long)Ns;
+        const double *yp = y + ray * Ns;
+        double acc = 0.0;
+        for (int i = lane; i < Ns; i += 32) {
+            const double w = simpson_weight(i, Ns, n_odd, sp[max(i - 2, 0)], sp[max(i - 1, 0)], sp[i],
+                                            sp[min(i + 1, Ns - 1)], sp[min(i + 2, Ns - 1)]);
+            double f = yp[i];
+            if (mode == 1) f = 1.0 - sqrt(fma(f, c, 1.0));
+            else if (mode == 2) f = f / sqrt(fma(f, c, 1.0)) * y2[ray * Ns + i];
+            acc = fma(w, f, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[ray * out_stride] = acc;
+    }
+}
+
+extern "C" int iono_simps_rows_f64(const double *y, const double *y2, const double *rays, int64_t nrays, int Ns,
+                                   int mode, double c, double *out, int out_stride, void *stream) {
+    if (nrays < 0 || Ns < 1 || mode < 0 || mode > 2 || out_stride < 1)
+        return fail(IONO_EBADARG, "iono_simps_rows_f64: bad argument");
+    if (nrays == 0) return IONO_OK;
+    if (!y || !rays || !out || (mode == 2 && !y2)) return fail(IONO_EBADARG, "iono_simps_rows_f64: NULL pointer");
+    if (Ns < 2) {   // simps of a single sample is 0
+        CU_CHECK(cudaMemset2DAsync(out, (size_t)out_stride * 8, 0, 8, (size_t)nrays, (cudaStream_t)stream));
+        return IONO_OK;
+    }
+    simps_rows_kernel<<<ew_grid(nrays * 32), 256, 0, (cudaStream_t)stream>>>(y, y2, rays, nrays, Ns, mode, c, out,
+                                                                            out_stride);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}

@@ -7,9 +7,11 @@ frequencies in one pass over the rays (``iono_phase_integrals_f64``).
 
 Note on parity: the reference calls ``tci.interp`` on 4-D coordinate arrays, where
 ``np.array([x,y,z]).T`` reverses all axes (geometry/tri_cubic.py:69-70) and scrambles which
-sample belongs to which ray.  This implementation integrates each ray over its own samples
-(the evident intent); the oracle can reproduce the reference's scrambled values for pinning
-(``reference_axis_scramble=True``), see DESIGN.md.
+sample belongs to which ray.  By default each ray is integrated over its own samples (the evident
+intent, one fused sweep); ``reference_axis_scramble=True`` reproduces the reference's own output:
+point-wise interpolation of all samples (``iono_tci_interp_f64``, SciPy's arithmetic), the same
+transpose-and-reshape, then Simpson along each ray's ``s`` (``iono_simps_rows_f64``) -- pinned to
+``tests/golden/forward_*.npz['phase', 'penalty']``, which the reference's module produced.
 """
 import ctypes
 
@@ -46,9 +48,43 @@ def _ne_from_mu(mu, K, shape, device):
     return mu_d, ne
 
 
-def forward_equation(model, tci, rays, freqs, K=1e11, i0=0, order="time", check_bounds=True):
+def _scrambled_samples(tci, field_dev, rays_d, check_bounds):
+    """``tci.interp(rays[...,0,:], rays[...,1,:], rays[...,2,:])`` exactly as the reference evaluates it on 4-D
+    inputs (geometry/tri_cubic.py:69-70): values in the order of the fully transposed coordinate array, reshaped
+    to ``(Na,Nt,Nd,Ns)`` without undoing the transpose."""
+    Na, Nt, Nd, _, Ns = rays_d.shape
+    x = rays_d[:, :, :, 0, :].contiguous().reshape(-1)
+    y = rays_d[:, :, :, 1, :].contiguous().reshape(-1)
+    z = rays_d[:, :, :, 2, :].contiguous().reshape(-1)
+    v = torch.empty_like(x)
+    oob = torch.zeros(1, dtype=torch.int64, device=rays_d.device)
+    _lib.call("iono_tci_interp_f64", tci.grid().handle, _lib.ptr(field_dev), _lib.ptr(x), _lib.ptr(y), _lib.ptr(z),
+              x.numel(), 0, _lib.ptr(v), ctypes.c_void_p(oob.data_ptr()), _lib.stream_ptr())
+    if check_bounds and int(oob.item()) != 0:
+        raise ValueError("One of the requested xi is out of bounds in dimension 0")
+    return v.reshape(Na, Nt, Nd, Ns).permute(3, 2, 1, 0).contiguous().reshape(Na, Nt, Nd, Ns)
+
+
+def _integrals_scrambled(tci, ne_dev, dmu_dev, rays_d, freqs, check_bounds):
+    Na, Nt, Nd, _, Ns = rays_d.shape
+    f_h = np.ascontiguousarray(_lib.host_f64(freqs), dtype=np.float64).reshape(-1)
+    Nf = f_h.size
+    ne_rays = _scrambled_samples(tci, ne_dev, rays_d, check_bounds)
+    dmu_rays = _scrambled_samples(tci, dmu_dev, rays_d, check_bounds) if dmu_dev is not None else None
+    out = torch.empty((Na, Nt, Nd, Nf), dtype=torch.float64, device=rays_d.device)
+    for l in range(Nf):
+        c = -1.0 / (1.2404e-2 * f_h[l] ** 2)
+        _lib.call("iono_simps_rows_f64", _lib.ptr(ne_rays), _lib.ptr(dmu_rays) if dmu_rays is not None else None,
+                  _lib.ptr(rays_d), Na * Nt * Nd, Ns, 2 if dmu_rays is not None else 1, float(c),
+                  ctypes.c_void_p(out.data_ptr() + 8 * l), Nf, _lib.stream_ptr())
+    return out, f_h
+
+
+def forward_equation(model, tci, rays, freqs, K=1e11, i0=0, order="time", check_bounds=True,
+                     reference_axis_scramble=False):
     """Phase ``(Na, Nt, Nd, Nf)`` from ``model = (mu, clock, const)`` (iterative_newton.py:86-127).
-    Like the reference this leaves ``tci.M = K*exp(mu)``."""
+    Like the reference this leaves ``tci.M = K*exp(mu)``.  ``reference_axis_scramble=True``: the reference's
+    own output, sample scramble included (module docstring)."""
     want_numpy = not isinstance(rays, torch.Tensor)
     rays_d = _lib.to_device(rays)
     Na, Nt, Nd, _, Ns = rays_d.shape
@@ -56,7 +92,10 @@ def forward_equation(model, tci, rays, freqs, K=1e11, i0=0, order="time", check_
     shape = (tci.nx, tci.ny, tci.nz)
     _, ne = _ne_from_mu(mu, K, shape, rays_d.device)
     tci.M = ne if isinstance(tci.M, torch.Tensor) else ne.cpu().numpy()      # iterative_newton.py:106
-    I, f_h = _integrals(tci, ne, None, rays_d, freqs, order, check_bounds)
+    if reference_axis_scramble:
+        I, f_h = _integrals_scrambled(tci, ne, None, rays_d, freqs, check_bounds)
+    else:
+        I, f_h = _integrals(tci, ne, None, rays_d, freqs, order, check_bounds)
     clock_d = _lib.to_device(clock).reshape(Na, Nt)
     const_d = _lib.to_device(const).reshape(Na)
     g = torch.empty_like(I)
@@ -65,7 +104,8 @@ def forward_equation(model, tci, rays, freqs, K=1e11, i0=0, order="time", check_
     return g.cpu().numpy() if want_numpy else g
 
 
-def prior_penalty_mu(model, model_prior, tci, rays, freqs, K=1e11, i0=0, order="time", check_bounds=True):
+def prior_penalty_mu(model, model_prior, tci, rays, freqs, K=1e11, i0=0, order="time", check_bounds=True,
+                     reference_axis_scramble=False):
     """First-order prior penalty ``(Na, Nt, Nd, Nf)`` (iterative_newton.py:138-184).
     Leaves ``tci.M = mu_prior - mu`` like the reference (:159)."""
     want_numpy = not isinstance(rays, torch.Tensor)
@@ -77,7 +117,10 @@ def prior_penalty_mu(model, model_prior, tci, rays, freqs, K=1e11, i0=0, order="
     mu_d, ne = _ne_from_mu(mu, K, shape, rays_d.device)
     dmu = (_lib.to_device(mu_prior, rays_d.device).reshape(shape) - mu_d).contiguous()
     tci.M = dmu if isinstance(tci.M, torch.Tensor) else dmu.cpu().numpy()
-    J, f_h = _integrals(tci, ne, dmu, rays_d, freqs, order, check_bounds)
+    if reference_axis_scramble:
+        J, f_h = _integrals_scrambled(tci, ne, dmu, rays_d, freqs, check_bounds)
+    else:
+        J, f_h = _integrals(tci, ne, dmu, rays_d, freqs, order, check_bounds)
     r = torch.empty_like(J)
     _lib.call("iono_phase_assemble_f64", _lib.ptr(J), Na, Nt, Nd, f_h.size, int(i0), f_h.ctypes.data,
               None, None, 1, _lib.ptr(r), _lib.stream_ptr())

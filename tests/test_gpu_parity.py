@@ -362,6 +362,14 @@ def test_phase_forward_and_penalty_vs_oracle(ib, golden, tag):
     refs = O.phase_forward_equation(g["mu"], g["clock"], g["const"], xv, yv, zv, rays, g["freqs"], K=1e11,
                                     i0=i0, reference_axis_scramble=True)
     np.testing.assert_allclose(refs, g["phase"], rtol=1e-10, atol=1e-10 * np.abs(g["phase"]).max())
+    # ... and so is the product: with the same switch the CUDA path reproduces the REFERENCE's own output
+    # (phase and prior penalty written by the reference's iterative_newton.py, tests/golden/make_golden.py)
+    ph_s = newton.forward_equation((g["mu"], g["clock"], g["const"]), tci, rays, g["freqs"], K=1e11, i0=i0,
+                                   reference_axis_scramble=True)
+    assert np.abs(ph_s - g["phase"]).max() < 1e-9 * ion_scale + 1e-13 * np.abs(g["phase"]).max()
+    pen_s = newton.prior_penalty_mu((g["mu"], g["clock"], g["const"]), (g["mu_prior"], g["clock"], g["const"]),
+                                    tci, rays, g["freqs"], K=1e11, i0=i0, reference_axis_scramble=True)
+    assert np.abs(pen_s - g["penalty"]).max() < 1e-10 * np.abs(g["penalty"]).max()
 
 
 def test_phase_forward_many_freqs_device(ib):
