@@ -277,6 +277,26 @@ int iono_peer_reduce_expand_f64(void *const *acc, void *const *res, void *const 
                                 int64_t L, const int *union_voxels, int64_t n_union, const double *m,
                                 double k_scale, double *grad, double *misfit_out, void *stream);
 
+/* ---- vector algebra of the device-resident inversion driver -------------------------------------
+ * The reference's BFGS recursion evaluates one scalar product (a triple Simpson integral over the grid,
+ * bfgs_dask.py:165-167) and one axpy per dask task (bfgs_dask.py:34-56, :165-194).  Here the history is ONE
+ * matrix H (rows of length n, leading dimension ld >= n) and an iteration needs a constant number of passes:
+ *   iono_multi_dot_f64 : out[r] = sum_i w[i] H[r][i] x[i], r < rows <= 32, one pass over x (w may be NULL;
+ *                        with the grid's Simpson weights it is the reference's inner product); scratch:
+ *                        iono_multi_dot_scratch_elems() doubles; deterministic
+ *   iono_lincomb_f64   : out[i] = coef[0] x[i] + sum_r coef[r+1] H[r][i]; coef (rows+1 doubles) in DEVICE
+ *                        memory, x may be NULL
+ *   iono_gather_f64    : out[i] = src[idx[i]]                       (grid -> active voxels)
+ *   iono_scatter_axpy_f64 : dst[idx[i]] = base[idx[i]] + alpha_dev[0] * x[i]   (active voxels -> grid) */
+int64_t iono_multi_dot_scratch_elems(void);
+int iono_multi_dot_f64(const double *H, int64_t ld, int rows, const double *x, const double *w, int64_t n,
+                       double *scratch, double *out, void *stream);
+int iono_lincomb_f64(const double *H, int64_t ld, int rows, const double *coef_dev, const double *x, int64_t n,
+                     double *out, void *stream);
+int iono_gather_f64(const double *src, const int *idx, int64_t n, double *out, void *stream);
+int iono_scatter_axpy_f64(const double *base, const double *alpha_dev, const double *x, const int *idx, int64_t n,
+                          double *dst, void *stream);
+
 /* ---- misfit ---------------------------------------------------------------
  * out[0] = sum((g-dobs)^2/(CdCt+1e-15))/2 (inversion/line_search.py:48-49).
  * Deterministic two-stage reduction; `scratch` needs iono_misfit_scratch_elems()

@@ -1,0 +1,157 @@
+// Vector algebra of the device-resident inversion driver (L-BFGS in compact form): every product an
+// iteration needs in a constant number of passes over the history, no host round trip per dot.
+// Included by iono_kernels.cu.
+//
+// The reference builds its BFGS recursion as a chain of dask tasks, one scalar product (a triple Simpson
+// integral over the grid, bfgs_dask.py:165-167 `scalarProduct`) and one axpy at a time
+// (bfgs_dask.py:34-56, :165-194).  Here the history lives in ONE matrix H of `rows` vectors of length n
+// (rows 0..k-1 = s_i, rows k..2k-1 = y_i), and
+//   iono_multi_dot_f64   : out[r] = sum_i w[i] * H[r][i] * x[i]   for all rows in one pass over x
+//                          (w optional: the Simpson quadrature weights of the grid make this the reference's
+//                          inner product, TriCubic.inner / scalarProduct; NULL = Euclidean)
+//   iono_lincomb_f64     : out[i] = c0 * x[i] + sum_r c[r] * H[r][i]     (coefficients read from device memory)
+//   iono_gather_f64 / iono_scatter_axpy_f64 : between the grid and the ACTIVE voxels -- the ones some ray
+//                          touches; the gradient is identically zero elsewhere, so the optimiser's vectors
+//                          only need those entries (a fifth of the grid at the LOFAR case).
+// All reductions are two-stage with a fixed tree: bit-reproducible.
+#pragma once
+
+constexpr int OPT_MAX_ROWS = 32;
+constexpr int OPT_BLOCKS = 592;    // 4 x 148
+
+template <int ROWS>
+__global__ void __launch_bounds__(256) multi_dot_kernel(const double *__restrict__ H, long long ld,
+                                                         const double *__restrict__ x, const double *__restrict__ w,
+                                                         long long n, int rows, double *__restrict__ partial) {
+    __shared__ double red[8][ROWS];
+    double acc[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[r] = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double xi = x[i];
+        if (w) xi *= w[i];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+            if (r < rows) acc[r] = fma(H[r * ld + i], xi, acc[r]);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const double t = warp_sum(acc[r]);
+        if (lane == 0) red[warp][r] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < ROWS && (int)threadIdx.x < rows) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+        partial[(long long)blockIdx.x * OPT_MAX_ROWS + threadIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) multi_dot_final_kernel(const double *__restrict__ partial, int blocks, int rows,
+                                                               double *__restrict__ out) {
+    // one warp per row: lanes stride over the per-CTA partials in a fixed order
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < rows; r += 8) {
+        double t = 0.0;
+        for (int b = lane; b < blocks; b += 32) t += partial[(long long)b * OPT_MAX_ROWS + r];
+        t = warp_sum(t);
+        if (lane == 0) out[r] = t;
+    }
+}
+
+extern "C" int64_t iono_multi_dot_scratch_elems(void) { return (int64_t)OPT_BLOCKS * OPT_MAX_ROWS; }
+
+extern "C" int iono_multi_dot_f64(const double *H, int64_t ld, int rows, const double *x, const double *w, int64_t n,
+                                  double *scratch, double *out, void *stream) {
+    if (rows < 0 || rows > OPT_MAX_ROWS || n < 0 || ld < n || !out || !scratch)
+        return fail(IONO_EBADARG, "iono_multi_dot_f64: bad argument (rows <= 32)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0) return IONO_OK;
+    if (n == 0) {
+        CU_CHECK(cudaMemsetAsync(out, 0, rows * sizeof(double), st));
+        return IONO_OK;
+    }
+    if (!H || !x) return fail(IONO_EBADARG, "iono_multi_dot_f64: NULL pointer");
+    long long want = (n + 255) / 256;
+    const int blocks = (int)(want < OPT_BLOCKS ? want : OPT_BLOCKS);
+    if (rows <= 4) multi_dot_kernel<4><<<blocks, 256, 0, st>>>(H, ld, x, w, n, rows, scratch);
+    else if (rows <= 12) multi_dot_kernel<12><<<blocks, 256, 0, st>>>(H, ld, x, w, n, rows, scratch);
+    else if (rows <= 22) multi_dot_kernel<22><<<blocks, 256, 0, st>>>(H, ld, x, w, n, rows, scratch);
+    else multi_dot_kernel<32><<<blocks, 256, 0, st>>>(H, ld, x, w, n, rows, scratch);
+    CU_CHECK(cudaGetLastError());
+    multi_dot_final_kernel<<<1, 256, 0, st>>>(scratch, blocks, rows, out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(256) lincomb_kernel(const double *__restrict__ H, long long ld, int rows,
+                                                       const double *__restrict__ coef, const double *__restrict__ x,
+                                                       long long n, double *__restrict__ out) {
+    __shared__ double c[ROWS + 1];
+    if (threadIdx.x <= ROWS && (int)threadIdx.x <= rows) c[threadIdx.x] = coef[threadIdx.x];   // c[0] scales x
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double v = x ? c[0] * x[i] : 0.0;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+            if (r < rows) v = fma(c[r + 1], H[r * ld + i], v);
+        out[i] = v;
+    }
+}
+
+// out[i] = coef[0] * x[i] + sum_{r < rows} coef[r + 1] * H[r][i]; coef: rows + 1 doubles in DEVICE memory.
+extern "C" int iono_lincomb_f64(const double *H, int64_t ld, int rows, const double *coef, const double *x, int64_t n,
+                                double *out, void *stream) {
+    if (rows < 0 || rows > OPT_MAX_ROWS || n < 0 || ld < n || !coef || (rows > 0 && !H))
+        return fail(IONO_EBADARG, "iono_lincomb_f64: bad argument (rows <= 32)");
+    if (n == 0) return IONO_OK;
+    if (!out) return fail(IONO_EBADARG, "iono_lincomb_f64: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = ew_grid(n);
+    if (rows <= 4) lincomb_kernel<4><<<blocks, 256, 0, st>>>(H, ld, rows, coef, x, n, out);
+    else if (rows <= 12) lincomb_kernel<12><<<blocks, 256, 0, st>>>(H, ld, rows, coef, x, n, out);
+    else if (rows <= 22) lincomb_kernel<22><<<blocks, 256, 0, st>>>(H, ld, rows, coef, x, n, out);
+    else lincomb_kernel<32><<<blocks, 256, 0, st>>>(H, ld, rows, coef, x, n, out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const double *__restrict__ src, const int *__restrict__ idx,
+                                                      long long n, double *__restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = src[idx[i]];
+}
+
+// dst[idx[i]] = base[idx[i]] + (*alpha) * x[i]   (alpha in device memory; dst may alias base)
+__global__ void __launch_bounds__(256) scatter_axpy_kernel(const double *__restrict__ base, const double *alpha,
+                                                            const double *__restrict__ x, const int *__restrict__ idx,
+                                                            long long n, double *__restrict__ dst) {
+    const double a = *alpha;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int v = idx[i];
+        dst[v] = fma(a, x[i], base[v]);
+    }
+}
+
+extern "C" int iono_gather_f64(const double *src, const int *idx, int64_t n, double *out, void *stream) {
+    if (n < 0 || (n > 0 && (!src || !idx || !out))) return fail(IONO_EBADARG, "iono_gather_f64: bad argument");
+    if (n == 0) return IONO_OK;
+    gather_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(src, idx, n, out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
+extern "C" int iono_scatter_axpy_f64(const double *base, const double *alpha_dev, const double *x, const int *idx,
+                                     int64_t n, double *dst, void *stream) {
+    if (n < 0 || (n > 0 && (!base || !alpha_dev || !x || !idx || !dst)))
+        return fail(IONO_EBADARG, "iono_scatter_axpy_f64: bad argument");
+    if (n == 0) return IONO_OK;
+    scatter_axpy_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(base, alpha_dev, x, idx, n, dst);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}

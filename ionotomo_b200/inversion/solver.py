@@ -1,24 +1,40 @@
 """Device-resident inversion driver: L-BFGS on the log-density model ``m`` with the misfit
 ``S(m) = sum((g(m) - dobs)^2 / (CdCt + 1e-15)) / 2`` -- the loop the reference sketches in
 ``tests/test_inversion.py:30-39`` (``fmin_l_bfgs_b(func_and_gradient, m0, ...)``) and builds as a
-dask graph in ``inversion/bfgs_dask.py:207-340``; every forward and every gradient runs on the
-GPU and nothing but scalars returns to the host between iterations.
+dask graph in ``inversion/bfgs_dask.py:207-340``.
 
-The first step length comes from the reference's secant probe (``line_search.py:55-66``: one
-extra forward at ``ep = 1e-3``); later iterations start from the L-BFGS-scaled unit step with
-Armijo backtracking.  With sharded rays pass ``reduce_fn`` / ``reduce_scalar`` (see
-``ionotomo_b200.sharding``): the search direction is then identical on every rank.
+Every forward and every gradient is one CUDA-graph replay of a ``DeviceSession``; the optimiser's own
+algebra runs in the library's vector kernels on the ACTIVE voxels only (the ones some ray touches --
+the gradient is identically zero elsewhere), with the history kept as one matrix:
+
+* L-BFGS in the compact form of Byrd, Nocedal & Schnabel (1994): ``H g = gamma g + S u + gamma Y v`` with
+  ``u, v`` from the small matrices ``S^T Y``, ``Y^T Y`` and the products ``S^T g``, ``Y^T g`` -- all
+  products of an iteration come from three ``iono_multi_dot_f64`` passes over the history and return to
+  the host in ONE copy per iteration; the direction is one ``iono_lincomb_f64`` pass.  (The reference
+  evaluates the same recursion one scalar product and one axpy per dask task, bfgs_dask.py:165-194.)
+* ``metric="simpson"`` makes every product the reference's inner product (``scalarProduct`` =
+  triple Simpson integral over the grid, bfgs_dask.py:165-167 / ``TriCubic.inner``); default Euclidean.
+* The first step length comes from the reference's secant probe (``line_search.py:55-66``: one extra
+  forward at ``ep = 1e-3``); later iterations start from the unit step with Armijo backtracking.
+
+With sharded rays (``DeviceSession`` under ``torch.distributed``) misfit and gradient are global on every
+rank, so every rank takes identical steps.
 """
+import ctypes
+
+import numpy as np
 import torch
 
 from .. import _lib
 from ..geometry.tri_cubic import TriCubic
 from .forward_equation import ForwardProjector, forward_equation
 from .gradient import BackProjector, adjoint_coefficients, backproject, misfit, _ne_from_m
+from .session import DeviceSession
 
 
 class InversionProblem(object):
-    """Fixed geometry + data; evaluates misfit and gradient for a model array on the device."""
+    """Fixed geometry + data; evaluates misfit and gradient for a model array on the device.
+    (Kernel-by-kernel form kept for callers of round 1's API; ``lbfgs_solve`` drives a ``DeviceSession``.)"""
 
     def __init__(self, rays, K_ne, m_tci, i0, dobs, CdCt, order="time", binned=True, reduce_fn=None,
                  reduce_scalar=None, prepared=False):
@@ -71,78 +87,244 @@ class InversionProblem(object):
         return grad
 
 
-def lbfgs_solve(problem, m0, n_iter=50, history=10, c1=1e-4, max_backtracks=20, callback=None):
-    """Minimise the misfit from ``m0`` (float64 CUDA tensor ``(nx, ny, nz)``).
+def simpson_grid_weights(xvec, yvec, zvec):
+    """Weights ``w`` with ``sum(w * a * b) == TriCubic.inner``-style triple ``simps`` of ``a*b`` over the grid
+    (geometry/tri_cubic.py:61-67, bfgs_dask.py:165-167): outer product of the 1-D old-SciPy ``even='avg'``
+    weights of the three axes."""
+    def w1(x):
+        x = np.asarray(x, dtype=np.float64)
+        n = x.size
+        eye = np.eye(n)
+        return np.array([_simps_avg_1d(eye[i], x) for i in range(n)])
+    return np.einsum("i,j,k->ijk", w1(xvec), w1(yvec), w1(zvec))
 
+
+def _simps_avg_1d(y, x):
+    """Old ``scipy.integrate.simps(y, x, even='avg')`` for one 1-D array (tomography/integrate.py:50-153)."""
+    def basic(y, x, start, stop):
+        s = 0.0
+        for a in range(start, stop, 2):
+            h0, h1 = x[a + 1] - x[a], x[a + 2] - x[a + 1]
+            s += (h0 + h1) / 6. * (y[a] * (2 - h1 / h0) + y[a + 1] * (h0 + h1) ** 2 / (h0 * h1) + y[a + 2] * (2 - h0 / h1))
+        return s
+    n = len(y)
+    if n < 2:
+        return 0.0
+    if n % 2 == 1:
+        return basic(y, x, 0, n - 2)
+    first = basic(y, x, 0, n - 3) + 0.5 * (x[-1] - x[-2]) * (y[-1] + y[-2])
+    last = basic(y, x, 1, n - 2) + 0.5 * (x[1] - x[0]) * (y[1] + y[0])
+    return 0.5 * (first + last)
+
+
+class _Vectors(object):
+    """History matrix + work rows on the active voxels, and the kernels that act on them."""
+
+    def __init__(self, n, history, device, weights=None):
+        lib = _lib.load()
+        self.n, self.k = int(n), int(history)
+        self.ld = (self.n + 3) // 4 * 4
+        # rows: s_0..s_{k-1}, y_0..y_{k-1}, G (current gradient), D (direction), T (new gradient)
+        self.H = torch.zeros((2 * self.k + 3, self.ld), dtype=torch.float64, device=device)
+        self.G, self.D, self.T = 2 * self.k, 2 * self.k + 1, 2 * self.k + 2
+        self.scratch = torch.empty(int(lib.iono_multi_dot_scratch_elems()), dtype=torch.float64, device=device)
+        self.dots = torch.zeros((3, 32), dtype=torch.float64, device=device)
+        self.dots_h = torch.zeros((3, 32), dtype=torch.float64).pin_memory()
+        self.coef_h = torch.zeros(40, dtype=torch.float64).pin_memory()
+        self.coef = torch.zeros(40, dtype=torch.float64, device=device)
+        self.w = weights
+
+    def row(self, r):
+        return self.H[r]
+
+    def multi_dot(self, rows, x_row, slot, weighted=True):
+        """dots[slot, r] = <H[r], H[x_row]> for r < rows."""
+        _lib.call("iono_multi_dot_f64", _lib.ptr(self.H), self.ld, int(rows), _lib.ptr(self.H[x_row]),
+                  _lib.ptr(self.w) if (self.w is not None and weighted) else None, self.n, _lib.ptr(self.scratch),
+                  _lib.ptr(self.dots[slot]), _lib.stream_ptr())
+
+    def fetch_dots(self):
+        self.dots_h.copy_(self.dots, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.dots_h.numpy()
+
+    def lincomb(self, coefs, x_row, out_row, rows=None, first_row=0):
+        """H[out_row] = coefs[0] * H[x_row] + sum_r coefs[r+1] * H[first_row + r]."""
+        c = np.asarray(coefs, dtype=np.float64)
+        rows = len(c) - 1 if rows is None else rows
+        self.coef_h[:len(c)] = torch.from_numpy(c)
+        self.coef.copy_(self.coef_h, non_blocking=True)
+        _lib.call("iono_lincomb_f64", _lib.ptr(self.H[first_row]) if rows > 0 else None, self.ld, int(rows),
+                  _lib.ptr(self.coef), _lib.ptr(self.H[x_row]) if x_row is not None else None, self.n,
+                  _lib.ptr(self.H[out_row]), _lib.stream_ptr())
+
+
+def lbfgs_solve(problem, m0, n_iter=50, history=10, c1=1e-4, max_backtracks=20, callback=None, metric=None):
+    """Minimise the misfit from ``m0`` (float64 ``(nx, ny, nz)``, NumPy or CUDA tensor).
+
+    ``problem``: a ``DeviceSession`` (or an ``InversionProblem`` of round 1's API, which is wrapped).
     Returns ``(m, info)`` with ``info['S']`` the misfit history (``n_iter + 1`` values at most),
-    ``info['n_forward']``, ``info['n_gradient']``.
+    ``info['n_forward']``, ``info['n_gradient']``, ``info['host_syncs_per_iteration']``.
+    ``metric``: ``None`` (Euclidean) or ``"simpson"`` (the reference's grid inner product).
     """
-    m = _lib.to_device(m0).clone()
-    g = problem.forward(m)
-    S = problem.misfit(g)
-    grad = problem.gradient(m, g)
-    hist_s, hist_y, hist_rho = [], [], []
+    ses = problem if isinstance(problem, DeviceSession) else _session_from_problem(problem)
+    dev = ses.device
+    m = _lib.to_device(m0).reshape(ses.shape).clone()
+    # active voxels: rows of the operator (union over ranks when sharded)
+    if ses.sharded:
+        idx = ses.union_voxels
+    elif ses.bp is not None:
+        lib = _lib.load()
+        nr = int(lib.iono_backprojector_n_rows(ses.bp.handle))
+        idx = torch.empty(max(nr, 1), dtype=torch.int32, device=dev)
+        _lib.call("iono_backprojector_row_voxels", ses.bp.handle, ctypes.c_void_p(idx.data_ptr()), _lib.stream_ptr())
+        idx = idx[:nr].contiguous()
+    else:
+        idx = torch.arange(m.numel(), dtype=torch.int32, device=dev)
+    n = int(idx.numel())
+    w = None
+    if metric == "simpson":
+        xv, yv, zv = ses.grid.xvec, ses.grid.yvec, ses.grid.zvec
+        w = torch.as_tensor(simpson_grid_weights(xv, yv, zv)).to(dev).reshape(-1)[idx.long()].contiguous()
+    elif metric is not None:
+        raise ValueError("metric must be None or 'simpson'")
+    V = _Vectors(n, history, dev, w)
+    k = history
+    step_dev = torch.zeros(1, dtype=torch.float64, device=dev)
+    step_pin = torch.zeros(1, dtype=torch.float64).pin_memory()
+    m_trial = m.clone()
+
+    def gather(src, row):
+        _lib.call("iono_gather_f64", _lib.ptr(src), ctypes.c_void_p(idx.data_ptr()), n, _lib.ptr(V.row(row)),
+                  _lib.stream_ptr())
+
+    def trial(step):
+        step_pin[0] = step
+        step_dev.copy_(step_pin, non_blocking=True)
+        _lib.call("iono_scatter_axpy_f64", _lib.ptr(m), _lib.ptr(step_dev), _lib.ptr(V.row(V.D)),
+                  ctypes.c_void_p(idx.data_ptr()), n, _lib.ptr(m_trial), _lib.stream_ptr())
+        dtec, S_t = ses.forward(m_trial)
+        return float(S_t)                       # the one host sync of a trial
+
+    S, grad = ses.misfit_and_gradient(m)
+    S = float(S)
+    gather(grad, V.G)
     S_hist = [S]
+    count = 0                  # pairs stored (chronological order in rows 0..count-1 / k..k+count-1)
+    SY = np.zeros((k, k))
+    YY = np.zeros((k, k))
     step0 = None
+    syncs = []
+    # products of the current gradient with the history and with itself
+    V.multi_dot(2 * k + 1, V.G, 0)
     for it in range(n_iter):
-        # two-loop recursion
-        q = grad.clone()
-        alphas = []
-        for s, y, rho in zip(reversed(hist_s), reversed(hist_y), reversed(hist_rho)):
-            a = rho * float(torch.sum(s * q))
-            alphas.append(a)
-            q.add_(y, alpha=-a)
-        if hist_s:
-            gamma = float(torch.sum(hist_s[-1] * hist_y[-1]) / torch.sum(hist_y[-1] * hist_y[-1]))
-            q.mul_(gamma)
-        for (s, y, rho), a in zip(zip(hist_s, hist_y, hist_rho), reversed(alphas)):
-            b = rho * float(torch.sum(y * q))
-            q.add_(s, alpha=a - b)
-        d = -q
-        gd = float(torch.sum(grad * d))
-        if not gd < 0:          # not a descent direction: restart with steepest descent
-            hist_s, hist_y, hist_rho = [], [], []
-            d = -grad
-            gd = float(torch.sum(grad * d))
-        if not hist_s:
-            # secant estimate of the step along -grad from one probe (reference line_search.py:55-66)
-            if step0 is None:
-                ep = 1e-3 / max(float(grad.abs().max()), 1e-300)
-                g_probe = problem.forward(m + ep * d)
-                Gm = (g_probe - g) / ep
-                dd = (g - problem.dobs) / (problem.CdCt + 1e-15)
-                num = float(torch.sum(dd * Gm))
-                den = float(torch.sum(Gm * Gm / (problem.CdCt + 1e-15)))
-                if problem.reduce_scalar is not None:
-                    num = problem.reduce_scalar(torch.tensor(num, dtype=torch.float64, device=m.device))
-                    den = problem.reduce_scalar(torch.tensor(den, dtype=torch.float64, device=m.device))
-                step0 = abs(num / den) if den > 0 else 1.0
-            step = step0
-        else:
+        n_sync = 1
+        d = V.fetch_dots()
+        p1, p2, gg = d[0, :count].copy(), d[0, k:k + count].copy(), float(d[0, V.G])
+        use_history = count > 0
+        if use_history:
+            R = np.triu(SY[:count, :count])
+            Dg = np.diag(np.diag(SY[:count, :count]))
+            gamma = SY[count - 1, count - 1] / YY[count - 1, count - 1]
+            try:
+                Rinv_p1 = np.linalg.solve(R, p1)
+                u = np.linalg.solve(R.T, (Dg + gamma * YY[:count, :count]) @ Rinv_p1 - gamma * p2)
+                v = -Rinv_p1
+                gd = -(gamma * gg + u @ p1 + gamma * (v @ p2))
+            except np.linalg.LinAlgError:
+                use_history = False
+            if use_history and not (gd < 0 and np.isfinite(gd)):
+                use_history = False            # not a descent direction: restart with steepest descent
+        if use_history:
+            coefs = np.zeros(2 * k + 1)
+            coefs[0] = -gamma
+            coefs[1:1 + count] = -u
+            coefs[1 + k:1 + k + count] = -gamma * v
+            V.lincomb(coefs, V.G, V.D, rows=2 * k)
+            if w is not None:                   # the Armijo test needs the Euclidean directional derivative
+                V.multi_dot_rows = None
+                _lib.call("iono_multi_dot_f64", _lib.ptr(V.H[V.D]), V.ld, 1, _lib.ptr(V.H[V.G]), None, n,
+                          _lib.ptr(V.scratch), _lib.ptr(V.dots[1]), _lib.stream_ptr())
+                gd = float(V.fetch_dots()[1, 0])
+                n_sync += 1
             step = 1.0
+        else:
+            count = 0
+            V.lincomb([-1.0], V.G, V.D, rows=0)
+            if w is not None:
+                _lib.call("iono_multi_dot_f64", _lib.ptr(V.H[V.G]), V.ld, 1, _lib.ptr(V.H[V.G]), None, n,
+                          _lib.ptr(V.scratch), _lib.ptr(V.dots[1]), _lib.stream_ptr())
+                gd = -float(V.fetch_dots()[1, 0])
+                n_sync += 1
+            else:
+                gd = -gg
+            if step0 is None:
+                # secant estimate of the step along -grad from one probe (reference line_search.py:55-66)
+                gmax = float(V.row(V.G)[:n].abs().max())
+                ep = 1e-3 / max(gmax, 1e-300)
+                g0 = ses.dtec.clone()
+                trial(ep)
+                Gm = (ses.dtec - g0) / ep
+                dd = (g0 - ses.dobs) / (ses.CdCt + 1e-15)
+                nd = torch.stack([torch.sum(dd * Gm), torch.sum(Gm * Gm / (ses.CdCt + 1e-15))])
+                if ses.sharded and ses.world > 1:
+                    torch.distributed.all_reduce(nd, group=ses.group)
+                num, den = float(nd[0]), float(nd[1])
+                step0 = abs(num / den) if den > 0 else 1.0
+                n_sync += 3
+            step = step0
         accepted = False
         for _ in range(max_backtracks):
-            m_new = m + step * d
-            g_new = problem.forward(m_new)
-            S_new = problem.misfit(g_new)
+            S_new = trial(step)
+            n_sync += 1
             if S_new == S_new and S_new <= S + c1 * step * gd:
                 accepted = True
                 break
             step *= 0.5
         if not accepted:
             break
-        grad_new = problem.gradient(m_new, g_new)
-        s_vec = m_new - m
-        y_vec = grad_new - grad
-        sy = float(torch.sum(s_vec * y_vec))
-        if sy > 1e-12 * float(torch.sum(y_vec * y_vec)):
-            hist_s.append(s_vec)
-            hist_y.append(y_vec)
-            hist_rho.append(1.0 / sy)
-            if len(hist_s) > history:
-                hist_s.pop(0); hist_y.pop(0); hist_rho.pop(0)
-        m, g, S, grad = m_new, g_new, S_new, grad_new
+        grad = ses.gradient_after_forward()
+        gather(grad, V.T)
+        # new pair: s = step * d, y = g_new - g; drop the oldest pair when the history is full
+        if count == k:
+            V.H[0:k - 1].copy_(V.H[1:k].clone())
+            V.H[k:2 * k - 1].copy_(V.H[k + 1:2 * k].clone())
+            SY[:k - 1, :k - 1] = SY[1:, 1:]
+            YY[:k - 1, :k - 1] = YY[1:, 1:]
+            count = k - 1
+        V.lincomb([step], V.D, count, rows=0)
+        V.lincomb([1.0, -1.0], V.T, k + count, rows=1, first_row=V.G)
+        V.H[V.G].copy_(V.H[V.T])
+        m, m_trial = m_trial, m
+        S = S_new
         S_hist.append(S)
+        # all products the next iteration needs, one copy to the host at its start:
+        #   slot 0: <rows, g_new>   slot 1: <rows, y_new>   slot 2: <rows, s_new>
+        V.multi_dot(2 * k + 1, V.G, 0)
+        V.multi_dot(2 * k, k + count, 1)
+        V.multi_dot(2 * k, count, 2)
+        d = V.fetch_dots()
+        n_sync += 1
+        sy = d[1, count]
+        yy = d[1, k + count]
+        if sy > 1e-12 * yy:
+            SY[:count + 1, count] = d[1, :count + 1]            # s_i . y_new
+            SY[count, :count + 1] = d[2, k:k + count + 1]       # s_new . y_j
+            YY[:count + 1, count] = d[1, k:k + count + 1]
+            YY[count, :count + 1] = d[1, k:k + count + 1]
+            count += 1
+        syncs.append(n_sync)
         if callback is not None:
             callback(it, m, S)
-    return m, {"S": S_hist, "n_forward": problem.n_forward, "n_gradient": problem.n_gradient}
+    return m, {"S": S_hist, "n_forward": ses.n_forward, "n_gradient": ses.n_gradient, "active_voxels": n,
+               "host_syncs_per_iteration": float(np.mean(syncs)) if syncs else 0.0}
+
+
+def _session_from_problem(problem):
+    """Round 1's ``InversionProblem`` -> session on the same rays and data."""
+    tci = problem._tci(torch.zeros((len(problem.xvec), len(problem.yvec), len(problem.zvec)), dtype=torch.float64,
+                                   device=problem.rays.device))
+    ses = DeviceSession(problem.rays, problem.K_ne, tci, problem.i0, problem.dobs, problem.CdCt,
+                        forward="prepared" if problem.fp is not None else "sweep",
+                        adjoint="binned" if problem.bp is not None else "scatter", order=problem.order)
+    return ses
