@@ -488,39 +488,49 @@ def main():
         del grad_dev
 
     # ---- end to end through the host-level session API ------------------------------------------
-    e2e, e2e_cold = None, None
+    e2e, e2e_active, e2e_cold = None, None, None
     if not args.no_e2e:
         ses.close()
         del ses
         torch.cuda.empty_cache()
         dobs_h, C_h = dobs.cpu().numpy(), CdCt.cpu().numpy()
-        hs = HostSession(None, K_ne, m_tci, i0, dobs_h, C_h, origins=origins_h, directions=directions_h,
-                         tmax=w["tmax"], Ns=w["Ns"], forward=args.forward, adjoint=args.adjoint, order=args.order,
-                         use_graph=not args.no_graph, reducer=args.reducer)
-        hs.m_host.copy_(m_dev)
-        e2e_steps = max(3, min(args.steps, 20))
-        for _ in range(3):
-            hs.misfit_and_gradient()
-        fence()
-        t0 = time.time()
-        for _ in range(e2e_steps):
-            g_h, S_h, grad_h = hs.misfit_and_gradient()
-        fence()
-        dt = (time.time() - t0) / e2e_steps
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt[0])
-        e2e = {"value": R_total / dt, "unit": "rays/s", "h2d_bytes_per_step": int(hs.h2d_bytes_per_call),
-               "d2h_bytes_per_step": int(hs.d2h_bytes_per_call), "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "misfit": S_h,
-               "api": "ionotomo_b200.inversion.host_stream.HostSession(...).misfit_and_gradient(m_host): the model comes "
+
+        def time_host_session(active):
+            hs = HostSession(None, K_ne, m_tci, i0, dobs_h, C_h, origins=origins_h, directions=directions_h,
+                             tmax=w["tmax"], Ns=w["Ns"], forward=args.forward, adjoint=args.adjoint, order=args.order,
+                             use_graph=not args.no_graph, reducer=args.reducer, active_only=active)
+            if not active:
+                hs.m_host.copy_(m_dev)
+            n_steps = max(3, min(args.steps, 20))
+            for _ in range(3):
+                hs.misfit_and_gradient()
+            fence()
+            t0 = time.time()
+            for _ in range(n_steps):
+                g_h, S_h, grad_h = hs.misfit_and_gradient()
+            fence()
+            dt = (time.time() - t0) / n_steps
+            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt[0])
+            res = {"value": R_total / dt, "unit": "rays/s", "h2d_bytes_per_step": int(hs.h2d_bytes_per_call),
+                   "d2h_bytes_per_step": int(hs.d2h_bytes_per_call), "ms_per_step": dt * 1e3, "steps": n_steps,
+                   "misfit": S_h}
+            hs.close()
+            del hs
+            torch.cuda.empty_cache()
+            return res
+
+        e2e = time_host_session(False)
+        e2e["api"] = ("ionotomo_b200.inversion.host_stream.HostSession(...).misfit_and_gradient(m_host): the model comes "
                       "from pinned host memory, dTEC (local rays), misfit and gradient return to pinned host memory; "
-                      "geometry, data and operators stay resident (the reference computes its rays once per solve)",
-               "per_rank": "every rank uploads the model and downloads the full gradient over its own PCIe link"}
-        hs.close()
-        del hs
-        torch.cuda.empty_cache()
+                      "geometry, data and operators stay resident (the reference computes its rays once per solve)")
+        e2e["multi_gpu"] = ("the host program is rank 0's: its model is broadcast to the other GPUs over NVLink, the "
+                            "gradient returns on rank 0 only; byte counts are rank 0's")
+        e2e_active = time_host_session(True)
+        e2e_active["api"] = ("HostSession(..., active_only=True): model and gradient as vectors over the voxels some ray "
+                             "touches (the gradient is zero elsewhere)")
         if world == 1:
             # cold call: the materialised 5 GB ray array itself comes from the host, time block by time block
             rays_h = torch.empty(rays.shape, dtype=torch.float64, pin_memory=True)
@@ -592,7 +602,7 @@ def main():
         "pass_frac_of_hbm_roofline": (bytes_fwd + bytes_adj) / ms / 1e6 / hbm,     # per GPU: this rank's rays
         "setup_once_per_geometry": {"ray_generation_ms": cast_ms, "operators_build_s": build_s,
                                     "amortised_ms_per_step_over_50_iterations": ms + (build_s * 1e3 + cast_ms) / 50.0},
-        "cpu_baseline": cpu, "e2e": e2e, "e2e_cold": e2e_cold, "gpu_launches": launches, "clocks": clocks,
+        "cpu_baseline": cpu, "e2e": e2e, "e2e_active_voxels": e2e_active, "e2e_cold": e2e_cold, "gpu_launches": launches, "clocks": clocks,
         "misfit": S_val, "verify": verify,
     }
     if note:

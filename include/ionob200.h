@@ -294,6 +294,7 @@ int iono_multi_dot_f64(const double *H, int64_t ld, int rows, const double *x, c
 int iono_lincomb_f64(const double *H, int64_t ld, int rows, const double *coef_dev, const double *x, int64_t n,
                      double *out, void *stream);
 int iono_gather_f64(const double *src, const int *idx, int64_t n, double *out, void *stream);
+int iono_scatter_set_f64(const double *x, const int *idx, int64_t n, double *dst, void *stream);   /* dst[idx[i]] = x[i] */
 int iono_scatter_axpy_f64(const double *base, const double *alpha_dev, const double *x, const int *idx, int64_t n,
                           double *dst, void *stream);
 

@@ -70,6 +70,7 @@ SIGNATURES = {
     "iono_multi_dot_f64": (_i, [_vp, _i64, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "iono_lincomb_f64": (_i, [_vp, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
     "iono_gather_f64": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "iono_scatter_set_f64": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "iono_scatter_axpy_f64": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     "iono_peer_alloc": (_i, [_i64, ctypes.POINTER(_vp), _vp]),
     "iono_peer_open": (_i, [_vp, ctypes.POINTER(_vp)]),
@@ -98,7 +99,7 @@ KERNEL_LAUNCHES = {
     "iono_backprojector_apply_permuted_f64": 3, "iono_backprojector_apply_gradient_f64": 3,
     "iono_backprojector_apply_compact_f64": 3, "iono_backprojector_ne_rows_f64": 1, "iono_forwardprojector_quads_from_m_f64": 1,
     "iono_forwardprojector_create": 1, "iono_forwardprojector_apply_f64": 2, "iono_forwardprojector_apply_quads_f64": 1,
-    "iono_peer_reduce_expand_f64": 1, "iono_multi_dot_f64": 2, "iono_lincomb_f64": 1, "iono_gather_f64": 1,
+    "iono_peer_reduce_expand_f64": 1, "iono_multi_dot_f64": 2, "iono_lincomb_f64": 1, "iono_gather_f64": 1, "iono_scatter_set_f64": 1,
     "iono_scatter_axpy_f64": 1,
     "iono_quads_from_ne_f64": 1, "iono_ne_quads_from_m_f64": 1, "iono_tec_forward_quads_f64": 1, "iono_residual_f64": 1,
 }

@@ -138,6 +138,21 @@ __global__ void __launch_bounds__(256) scatter_axpy_kernel(const double *__restr
     }
 }
 
+__global__ void __launch_bounds__(256) scatter_set_kernel(const double *__restrict__ x, const int *__restrict__ idx,
+                                                           long long n, double *__restrict__ dst) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[idx[i]] = x[i];
+}
+
+// dst[idx[i]] = x[i]
+extern "C" int iono_scatter_set_f64(const double *x, const int *idx, int64_t n, double *dst, void *stream) {
+    if (n < 0 || (n > 0 && (!x || !idx || !dst))) return fail(IONO_EBADARG, "iono_scatter_set_f64: bad argument");
+    if (n == 0) return IONO_OK;
+    scatter_set_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, idx, n, dst);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
 extern "C" int iono_gather_f64(const double *src, const int *idx, int64_t n, double *out, void *stream) {
     if (n < 0 || (n > 0 && (!src || !idx || !out))) return fail(IONO_EBADARG, "iono_gather_f64: bad argument");
     if (n == 0) return IONO_OK;

@@ -162,12 +162,22 @@ class HostSession(object):
     instead of 5 GB.  All arrays returned are views of pinned host buffers owned by the session, valid until
     the next call; ``m_host`` is a pinned buffer the caller may fill in place (pass ``m=None`` then).
 
-    With ``torch.distributed`` initialised and the rays sharded over the ranks (direction or time blocks)
-    every rank returns the global ``S`` and gradient and the ``dtec`` of its own rays.
+    ``active_only=True``: the model and the gradient travel as vectors over the ACTIVE voxels
+    (``self.active_voxels``, flat indices of the voxels some ray touches; the gradient is identically zero
+    elsewhere, so an optimiser only ever changes those entries of ``m``): a fifth of the bytes at the LOFAR case.
+    The session keeps the full model on the device, initialised from ``m_tci.M``.
+
+    With ``torch.distributed`` initialised and the rays sharded over the ranks (direction or time blocks) the
+    HOST program is rank ``root``'s: its model is broadcast to the other GPUs over NVLink, every rank returns the
+    ``dtec`` of its own rays, and ``S`` and the gradient (global) are copied to the host on ``root`` only (the other
+    ranks return ``None`` for the gradient) -- one model upload and one gradient download per step for the whole
+    job, whatever the number of GPUs.
     """
 
     def __init__(self, rays, K_ne, m_tci, i0, dobs, CdCt, origins=None, directions=None, tmax=1000., Ns=None,
-                 **session_kw):
+                 active_only=False, root=0, **session_kw):
+        import ctypes
+        import torch.distributed as dist
         from ..geometry.calc_rays import cast_ray
         from .fermat import Fermat
         from .session import DeviceSession
@@ -178,37 +188,82 @@ class HostSession(object):
                             Ns if Ns is not None else m_tci.nz)
         self.session = DeviceSession(rays, K_ne, m_tci, i0, dobs, CdCt, **session_kw)
         s = self.session
-        self.m_host = torch.empty(s.shape, dtype=torch.float64, pin_memory=True)
+        self.root = int(root)
+        self.is_root = (not s.sharded) or s.world == 1 or s.rank == self.root
+        self._dist = dist if (s.sharded and s.world > 1) else None
+        self.active_only = bool(active_only)
+        self.active_voxels = None
+        if self.active_only:
+            if s.sharded:
+                idx = s.union_voxels
+            else:
+                assert s.bp is not None, "active_only needs the binned adjoint (its rows are the active voxels)"
+                nr = int(_lib.load().iono_backprojector_n_rows(s.bp.handle))
+                idx = torch.empty(max(nr, 1), dtype=torch.int32, device=s.device)
+                _lib.call("iono_backprojector_row_voxels", s.bp.handle, ctypes.c_void_p(idx.data_ptr()),
+                          _lib.stream_ptr())
+                idx = idx[:nr].contiguous()
+            self._idx = idx
+            self.active_voxels = idx.cpu().numpy().astype(np.int64)
+            n = int(idx.numel())
+            s.m.copy_(m_tci.device_M())
+            self._m_act = torch.empty(n, dtype=torch.float64, device=s.device)
+            self._g_act = torch.empty(n, dtype=torch.float64, device=s.device)
+            self._one = torch.ones(1, dtype=torch.float64, device=s.device)
+            self._zero_grid = None
+            self.m_host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+            self.m_host.copy_(s.m.reshape(-1)[idx.long()])
+            self.grad_host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+        else:
+            self.m_host = torch.empty(s.shape, dtype=torch.float64, pin_memory=True)
+            self.grad_host = torch.empty(s.shape, dtype=torch.float64, pin_memory=True)
         self.dtec_host = torch.empty(s.ray_shape, dtype=torch.float64, pin_memory=True)
-        self.grad_host = torch.empty(s.shape, dtype=torch.float64, pin_memory=True)
         self.S_host = torch.empty(1, dtype=torch.float64, pin_memory=True)
-        self.h2d_bytes_per_call = self.m_host.numel() * 8
-        self.d2h_bytes_per_call = (self.dtec_host.numel() + self.grad_host.numel() + 1) * 8
+        self.h2d_bytes_per_call = self.m_host.numel() * 8 if self.is_root else 0
+        self.d2h_bytes_per_call = (self.dtec_host.numel() + (self.grad_host.numel() + 1 if self.is_root else 0)) * 8
+
+    def _upload(self, m):
+        import ctypes
+        s = self.session
+        if self.is_root:
+            if m is not None:
+                src = torch.as_tensor(m, dtype=torch.float64).reshape(self.m_host.shape)
+                if src.data_ptr() != self.m_host.data_ptr():
+                    self.m_host.copy_(src)
+            if self.active_only:
+                self._m_act.copy_(self.m_host, non_blocking=True)
+            else:
+                s.m.copy_(self.m_host, non_blocking=True)
+        if self._dist is not None:                       # the root's model reaches the other GPUs over NVLink
+            self._dist.broadcast(self._m_act if self.active_only else s.m, src=self.root, group=s.group)
+        if self.active_only:
+            # m[active] = m_act
+            _lib.call("iono_scatter_set_f64", _lib.ptr(self._m_act), ctypes.c_void_p(self._idx.data_ptr()),
+                          self._m_act.numel(), _lib.ptr(s.m), _lib.stream_ptr())
 
     def misfit_and_gradient(self, m=None):
-        """``(dtec, S, gradient)`` for the model ``m`` (NumPy ``(nx,ny,nz)``; ``None``: ``self.m_host`` as filled by
-        the caller)."""
+        """``(dtec, S, gradient)`` for the model ``m`` (NumPy ``(nx,ny,nz)``, or the vector over
+        ``active_voxels`` with ``active_only``; ``None``: ``self.m_host`` as filled by the caller)."""
+        import ctypes
         s = self.session
-        if m is not None:
-            src = torch.as_tensor(m, dtype=torch.float64).reshape(s.shape)
-            if src.data_ptr() != self.m_host.data_ptr():
-                self.m_host.copy_(src)
-        s.m.copy_(self.m_host, non_blocking=True)
+        self._upload(m)
         s.misfit_and_gradient(None)
         self.dtec_host.copy_(s.dtec, non_blocking=True)
-        self.grad_host.copy_(s.grad, non_blocking=True)
+        if self.is_root:
+            if self.active_only:
+                _lib.call("iono_gather_f64", _lib.ptr(s.grad), ctypes.c_void_p(self._idx.data_ptr()),
+                          self._g_act.numel(), _lib.ptr(self._g_act), _lib.stream_ptr())
+                self.grad_host.copy_(self._g_act, non_blocking=True)
+            else:
+                self.grad_host.copy_(s.grad, non_blocking=True)
         self.S_host.copy_(s.S, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self.dtec_host.numpy(), float(self.S_host[0]), self.grad_host.numpy()
+        return self.dtec_host.numpy(), float(self.S_host[0]), (self.grad_host.numpy() if self.is_root else None)
 
     def forward(self, m=None):
         """``(dtec, S)`` only (line searches)."""
         s = self.session
-        if m is not None:
-            src = torch.as_tensor(m, dtype=torch.float64).reshape(s.shape)
-            if src.data_ptr() != self.m_host.data_ptr():
-                self.m_host.copy_(src)
-        s.m.copy_(self.m_host, non_blocking=True)
+        self._upload(m)
         s.forward(None)
         self.dtec_host.copy_(s.dtec, non_blocking=True)
         self.S_host.copy_(s.S, non_blocking=True)

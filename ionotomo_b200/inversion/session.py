@@ -72,7 +72,15 @@ class DeviceSession(object):
         self.m = torch.empty(self.shape, **f64)                 # static input of the graph
         self.ne = torch.empty(self.shape, **f64) if self.bp is None else None
         self.ne_rows = torch.empty(self.shape, **f64) if (self.bp is not None and not self.sharded) else None
-        self.quads = quads_alloc(self.shape, dev)
+        # quad records (4 x the grid) pay while their hot part stays in L2; beyond 2^24 voxels the plain layout is used
+        V = self.shape[0] * self.shape[1] * self.shape[2]
+        self.use_quads = V <= (1 << 24)
+        self.quads = quads_alloc(self.shape, dev) if self.use_quads else None
+        if not self.use_quads:
+            if self.ne is None:
+                self.ne = self.ne_rows if self.ne_rows is not None else torch.zeros(self.shape, **f64)
+            elif self.ne_rows is not None:
+                self.ne_rows = self.ne      # one buffer: the forward fills it, the apply scales with it
         self.tec = torch.empty(self.ray_shape, **f64)
         self.dtec = torch.empty(self.ray_shape, **f64)
         self.coef = torch.empty(self.ray_shape, **f64) if self.bp is None else None
@@ -114,6 +122,21 @@ class DeviceSession(object):
 
     # ---- the step, as enqueued work on the current stream ------------------------------------
     def _enqueue_forward(self):
+        if not self.use_quads:
+            # large grids: plain layout (IONO_FWD_LAYOUT policy of the C side keeps it plain beyond 2^24 voxels)
+            from .forward_equation import tec_from_ne
+            if self.fp is not None and self.bp is not None:
+                _lib.call("iono_backprojector_ne_rows_f64", self.bp.handle, _lib.ptr(self.m), self.K_ne / TECU,
+                          _lib.ptr(self.ne), _lib.stream_ptr())      # the operator's rows = every corner the rays read
+                self.fp.tec(self.ne, out=self.tec)
+            else:
+                _lib.call("iono_ne_from_m_f64", _lib.ptr(self.m), self.m.numel(), self.K_ne / TECU, _lib.ptr(self.ne),
+                          _lib.stream_ptr())
+                if self.fp is not None:
+                    self.fp.tec(self.ne, out=self.tec)
+                else:
+                    self.tec.copy_(tec_from_ne(self.rays, self.grid, self.ne, order=self.order, check_bounds=False))
+            return
         if self.fp is not None:
             _lib.call("iono_forwardprojector_quads_from_m_f64", self.fp.handle, _lib.ptr(self.m), self.K_ne / TECU,
                       _lib.ptr(self.quads), _lib.stream_ptr())
@@ -140,8 +163,9 @@ class DeviceSession(object):
         elif self.bp is not None:
             # chain-rule factor for the touched rows only, then the apply with `scale` (evaluating exp inside the
             # apply kernel costs 0.2 ms at the LOFAR case: it runs once per segment, not once per row)
-            _lib.call("iono_backprojector_ne_rows_f64", self.bp.handle, _lib.ptr(self.m), self.K_ne / TECU,
-                      _lib.ptr(self.ne_rows), _lib.stream_ptr())
+            if self.use_quads:              # (plain layout: the forward has just filled ne for these rows)
+                _lib.call("iono_backprojector_ne_rows_f64", self.bp.handle, _lib.ptr(self.m), self.K_ne / TECU,
+                          _lib.ptr(self.ne_rows), _lib.stream_ptr())
             self.bp.apply_permuted(self.coef_perm, scale=self.ne_rows, out=self.grad)
         else:
             backproject(self.rays, self.grid, self.coef, self.shape, order=self.order, check_bounds=False,

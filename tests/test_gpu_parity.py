@@ -426,7 +426,126 @@ def test_lbfgs_inversion_reduces_misfit(ib, binned):
     assert S[-1] < 0.05 * S[0]
     # the driver's first evaluation equals the oracle's misfit
     g0 = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], m0, 0)
-    np.testing.assert_allclose(S[0], O.misfit(g0, dobs, CdCt), rtol=1e-10)
+    np.testing.assert_allclose(S[0], O.misfit(g0, dobs, CdCt), rtol=1e-8)
+    # voxels no ray touches never move
+    untouched = (O.backproject(rays, P["xvec"], P["yvec"], P["zvec"], np.ones(dobs.shape)) == 0)
+    assert np.array_equal(m.cpu().numpy()[untouched], m0[untouched])
+
+
+def test_optimiser_vector_kernels(ib):
+    """iono_multi_dot / iono_lincomb / iono_gather / iono_scatter_*: the algebra of the L-BFGS driver."""
+    import ctypes
+    import torch
+    from ionotomo_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.RandomState(11)
+    for rows, n in ((1, 5), (3, 1000), (7, 70001), (21, 12345), (32, 4097)):
+        ld = (n + 3) // 4 * 4 + 8
+        Hn = rng.normal(size=(rows, ld))
+        xn, wn = rng.normal(size=n), rng.uniform(0.5, 2., size=n)
+        H, x, w = torch.as_tensor(Hn).cuda(), torch.as_tensor(xn).cuda(), torch.as_tensor(wn).cuda()
+        scratch = torch.empty(int(lib.iono_multi_dot_scratch_elems()), dtype=torch.float64, device="cuda")
+        out = torch.full((32,), float("nan"), dtype=torch.float64, device="cuda")
+        for wt, ref in ((None, Hn[:, :n] @ xn), (w, Hn[:, :n] @ (wn * xn))):
+            _lib.call("iono_multi_dot_f64", _lib.ptr(H), ld, rows, _lib.ptr(x), _lib.ptr(wt) if wt is not None else None, n,
+                      _lib.ptr(scratch), _lib.ptr(out), _lib.stream_ptr())
+            got = out.cpu().numpy()[:rows]
+            assert np.abs(got - ref).max() <= 1e-12 * np.abs(Hn).max() * np.abs(xn).max() * n
+            first = got.copy()
+            _lib.call("iono_multi_dot_f64", _lib.ptr(H), ld, rows, _lib.ptr(x), _lib.ptr(wt) if wt is not None else None, n,
+                      _lib.ptr(scratch), _lib.ptr(out), _lib.stream_ptr())
+            assert np.array_equal(out.cpu().numpy()[:rows], first)          # fixed reduction tree
+        cn = rng.normal(size=rows + 1)
+        c = torch.as_tensor(cn).cuda()
+        y = torch.empty(n, dtype=torch.float64, device="cuda")
+        _lib.call("iono_lincomb_f64", _lib.ptr(H), ld, rows, _lib.ptr(c), _lib.ptr(x), n, _lib.ptr(y), _lib.stream_ptr())
+        np.testing.assert_allclose(y.cpu().numpy(), cn[0] * xn + cn[1:] @ Hn[:, :n], rtol=0, atol=1e-12 * rows)
+        _lib.call("iono_lincomb_f64", _lib.ptr(H), ld, rows, _lib.ptr(c), None, n, _lib.ptr(y), _lib.stream_ptr())
+        np.testing.assert_allclose(y.cpu().numpy(), cn[1:] @ Hn[:, :n], rtol=0, atol=1e-12 * rows)
+    # gather / scatter between a grid and its active entries
+    big = rng.normal(size=5000)
+    idx = np.sort(rng.choice(5000, 700, replace=False)).astype(np.int32)
+    b, i_d = torch.as_tensor(big).cuda(), torch.as_tensor(idx).cuda()
+    act = torch.empty(700, dtype=torch.float64, device="cuda")
+    _lib.call("iono_gather_f64", _lib.ptr(b), ctypes.c_void_p(i_d.data_ptr()), 700, _lib.ptr(act), _lib.stream_ptr())
+    assert np.array_equal(act.cpu().numpy(), big[idx])
+    alpha = torch.as_tensor([0.25]).cuda()
+    dst = b.clone()
+    _lib.call("iono_scatter_axpy_f64", _lib.ptr(b), _lib.ptr(alpha), _lib.ptr(act), ctypes.c_void_p(i_d.data_ptr()), 700,
+              _lib.ptr(dst), _lib.stream_ptr())
+    ref = big.copy()
+    ref[idx] = big[idx] + 0.25 * big[idx]
+    np.testing.assert_allclose(dst.cpu().numpy(), ref, rtol=1e-15)
+    _lib.call("iono_scatter_set_f64", _lib.ptr(act), ctypes.c_void_p(i_d.data_ptr()), 700, _lib.ptr(dst), _lib.stream_ptr())
+    assert np.array_equal(dst.cpu().numpy(), big)
+
+
+@pytest.mark.parametrize("metric", [None, "simpson"])
+def test_lbfgs_matches_scipy_lbfgsb(ib, metric):
+    """The reference's driver sketch is scipy.optimize.fmin_l_bfgs_b(func_and_gradient, m0) (tests/test_inversion.py:
+    30-39): the device-resident L-BFGS must reach the same misfit (within 1 %% of the drop) in the same number of
+    iterations, function and gradient coming from the same session through the host API."""
+    import torch
+    from scipy.optimize import fmin_l_bfgs_b
+    from ionotomo_b200.inversion.host_stream import HostSession
+    from ionotomo_b200.inversion.session import DeviceSession
+    from ionotomo_b200.inversion.solver import lbfgs_solve, simpson_grid_weights
+    P = small_problem(6, 8, 3, 12, 32, 24, 24, 32)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 32)
+    dobs = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], 0)
+    dobs = dobs + 0.001 * P["rng"].normal(size=dobs.shape)
+    CdCt = np.full(dobs.shape, 0.001 ** 2)
+    X, Y, Z = np.meshgrid(P["xvec"], P["yvec"], P["zvec"], indexing="ij")
+    m0 = np.log((1e11 * np.exp(-((Z - 300.) / 150.) ** 2) + 1e9) / P["K_ne"])
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], m0)
+    n_iter = 30
+    ses = DeviceSession(rays, P["K_ne"], tci, 0, dobs, CdCt)
+    m, info = lbfgs_solve(ses, torch.as_tensor(m0).cuda(), n_iter=n_iter, metric=metric)
+    assert info["active_voxels"] < m0.size and info["host_syncs_per_iteration"] <= 6
+    hs = HostSession(rays, P["K_ne"], tci, 0, dobs, CdCt)
+
+    def func_and_gradient(mflat):
+        g, S, grad = hs.misfit_and_gradient(mflat.reshape(m0.shape))
+        return S, grad.reshape(-1).copy()
+    S0 = func_and_gradient(m0.reshape(-1))[0]
+    np.testing.assert_allclose(info["S"][0], S0, rtol=1e-9)
+    _, S_scipy, d = fmin_l_bfgs_b(func_and_gradient, m0.reshape(-1), m=10, maxiter=n_iter, factr=10., pgtol=1e-30)
+    S_ours = info["S"][-1]
+    assert S_ours < 0.05 * S0 and S_scipy < 0.05 * S0
+    assert abs(S_ours - S_scipy) <= 0.01 * (S0 - min(S_ours, S_scipy)), (S0, S_ours, S_scipy, d["nit"], len(info["S"]))
+    if metric == "simpson":       # the weights reproduce TriCubic.inner (triple simps over the grid)
+        a, b = P["rng"].normal(size=m0.shape), P["rng"].normal(size=m0.shape)
+        w = simpson_grid_weights(P["xvec"], P["yvec"], P["zvec"])
+        np.testing.assert_allclose((w * a * b).sum(), O.tci_inner(P["xvec"], P["yvec"], P["zvec"], a, b), rtol=1e-12)
+
+
+def test_host_session_api(ib):
+    """HostSession: full-grid and active-only calls agree with the oracle and with each other; rays generated on
+    the device from origins/directions give the same numbers as the materialised host array."""
+    from ionotomo_b200.inversion.host_stream import HostSession
+    P = small_problem(902, 5, 4, 6, 30, 14, 13, 16)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 30)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    g_true = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], 1)
+    dobs = g_true + 0.01 * P["rng"].normal(size=g_true.shape)
+    CdCt = np.full(g_true.shape, 1e-4)
+    hs = HostSession(None, P["K_ne"], tci, 1, dobs, CdCt, origins=P["origins"], directions=P["directions"],
+                     tmax=P["tmax"], Ns=30)
+    ha = HostSession(rays, P["K_ne"], tci, 1, dobs, CdCt, active_only=True)
+    assert ha.active_voxels.size < P["m"].size and np.all(np.diff(ha.active_voxels) > 0)
+    for k in range(3):
+        m = P["m"] + 0.04 * k * np.sin(np.arange(P["m"].size)).reshape(P["m"].shape)
+        g_ref = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], m, 1)
+        grad_ref = O.gradient_exact(rays, g_ref, dobs, 1, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], m, CdCt)
+        S_ref = O.misfit(g_ref, dobs, CdCt)
+        dtec, S, grad = hs.misfit_and_gradient(m)
+        assert abs(S - S_ref) <= 1e-7 * S_ref and np.abs(grad - grad_ref).max() <= 1e-7 * np.abs(grad_ref).max()
+        assert np.abs(dtec - g_ref).max() <= 1e-9 * np.abs(g_ref).max()
+        dtec_a, S_a, grad_a = ha.misfit_and_gradient(m.reshape(-1)[ha.active_voxels])
+        assert S_a == S and np.array_equal(grad_a, grad.reshape(-1)[ha.active_voxels]) and np.array_equal(dtec_a, dtec)
+        assert np.abs(grad.reshape(-1)).sum() == np.abs(grad_a).sum()          # nothing outside the active set
+        d2, S2 = hs.forward(m)
+        assert np.array_equal(d2, dtec) and S2 == S
 
 
 # ---------------------------------------------------------------- host-array streaming API
