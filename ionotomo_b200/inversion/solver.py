@@ -130,8 +130,11 @@ class _Vectors(object):
         self.scratch = torch.empty(int(lib.iono_multi_dot_scratch_elems()), dtype=torch.float64, device=device)
         self.dots = torch.zeros((3, 32), dtype=torch.float64, device=device)
         self.dots_h = torch.zeros((3, 32), dtype=torch.float64).pin_memory()
-        self.coef_h = torch.zeros(40, dtype=torch.float64).pin_memory()
-        self.coef = torch.zeros(40, dtype=torch.float64, device=device)
+        # coefficient vectors go up asynchronously from pinned slots; a ring, so that a slot is not rewritten while its
+        # copy may still be in flight (an iteration issues <= 4 of them between two host synchronisations)
+        self.coef_h = torch.zeros((8, 40), dtype=torch.float64).pin_memory()
+        self.coef = torch.zeros((8, 40), dtype=torch.float64, device=device)
+        self._slot = 0
         self.w = weights
 
     def row(self, r):
@@ -152,10 +155,12 @@ class _Vectors(object):
         """H[out_row] = coefs[0] * H[x_row] + sum_r coefs[r+1] * H[first_row + r]."""
         c = np.asarray(coefs, dtype=np.float64)
         rows = len(c) - 1 if rows is None else rows
-        self.coef_h[:len(c)] = torch.from_numpy(c)
-        self.coef.copy_(self.coef_h, non_blocking=True)
+        k = self._slot
+        self._slot = (k + 1) % 8
+        self.coef_h[k, :len(c)] = torch.from_numpy(c)
+        self.coef[k].copy_(self.coef_h[k], non_blocking=True)
         _lib.call("iono_lincomb_f64", _lib.ptr(self.H[first_row]) if rows > 0 else None, self.ld, int(rows),
-                  _lib.ptr(self.coef), _lib.ptr(self.H[x_row]) if x_row is not None else None, self.n,
+                  _lib.ptr(self.coef[k]), _lib.ptr(self.H[x_row]) if x_row is not None else None, self.n,
                   _lib.ptr(self.H[out_row]), _lib.stream_ptr())
 
 
@@ -164,7 +169,8 @@ def lbfgs_solve(problem, m0, n_iter=50, history=10, c1=1e-4, max_backtracks=20, 
 
     ``problem``: a ``DeviceSession`` (or an ``InversionProblem`` of round 1's API, which is wrapped).
     Returns ``(m, info)`` with ``info['S']`` the misfit history (``n_iter + 1`` values at most),
-    ``info['n_forward']``, ``info['n_gradient']``, ``info['host_syncs_per_iteration']``.
+    ``info['n_forward']``, ``info['n_gradient']``, ``info['host_syncs_per_iteration']``, ``info['iter_seconds']``
+    (wall time of every iteration; the first ones include the one-off CUDA-graph captures of the session).
     ``metric``: ``None`` (Euclidean) or ``"simpson"`` (the reference's grid inner product).
     """
     ses = problem if isinstance(problem, DeviceSession) else _session_from_problem(problem)
@@ -215,6 +221,9 @@ def lbfgs_solve(problem, m0, n_iter=50, history=10, c1=1e-4, max_backtracks=20, 
     YY = np.zeros((k, k))
     step0 = None
     syncs = []
+    import time as _time
+    iter_seconds = []
+    _t_prev = _time.time()
     # products of the current gradient with the history and with itself
     V.multi_dot(2 * k + 1, V.G, 0)
     for it in range(n_iter):
@@ -314,10 +323,13 @@ def lbfgs_solve(problem, m0, n_iter=50, history=10, c1=1e-4, max_backtracks=20, 
             YY[count, :count + 1] = d[1, k:k + count + 1]
             count += 1
         syncs.append(n_sync)
+        _t_now = _time.time()                   # (fetch_dots above synchronised the stream)
+        iter_seconds.append(_t_now - _t_prev)
+        _t_prev = _t_now
         if callback is not None:
             callback(it, m, S)
     return m, {"S": S_hist, "n_forward": ses.n_forward, "n_gradient": ses.n_gradient, "active_voxels": n,
-               "host_syncs_per_iteration": float(np.mean(syncs)) if syncs else 0.0}
+               "host_syncs_per_iteration": float(np.mean(syncs)) if syncs else 0.0, "iter_seconds": iter_seconds}
 
 
 def _session_from_problem(problem):

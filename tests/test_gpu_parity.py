@@ -469,7 +469,7 @@ def test_optimiser_vector_kernels(ib):
     act = torch.empty(700, dtype=torch.float64, device="cuda")
     _lib.call("iono_gather_f64", _lib.ptr(b), ctypes.c_void_p(i_d.data_ptr()), 700, _lib.ptr(act), _lib.stream_ptr())
     assert np.array_equal(act.cpu().numpy(), big[idx])
-    alpha = torch.as_tensor([0.25]).cuda()
+    alpha = torch.as_tensor([0.25], dtype=torch.float64).cuda()
     dst = b.clone()
     _lib.call("iono_scatter_axpy_f64", _lib.ptr(b), _lib.ptr(alpha), _lib.ptr(act), ctypes.c_void_p(i_d.data_ptr()), 700,
               _lib.ptr(dst), _lib.stream_ptr())

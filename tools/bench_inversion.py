@@ -63,7 +63,11 @@ for _ in range(10):
     prob.gradient_after_forward()
 torch.cuda.synchronize()
 t_adj = (time.time() - t1) / 10
-ray_share = (nf * t_fwd + ng * t_adj) / dt
+import numpy as np
+it_s = np.array(info["iter_seconds"])
+steady = float(np.median(it_s[3:])) if len(it_s) > 6 else float(np.median(it_s))     # past the one-off graph captures
+evals_f, evals_g = (nf - 2) / max(1, len(it_s)), (ng - 1) / max(1, len(it_s))
+ray_share = (evals_f * t_fwd + evals_g * t_adj) / steady
 err0 = float((w["m_prior"] - w["m_true"]).abs().mean())
 err1 = float((m - w["m_true"]).abs().mean())
 print(json.dumps({
@@ -71,6 +75,7 @@ print(json.dumps({
     "forward_ms": t_fwd * 1e3, "adjoint_ms": t_adj * 1e3, "share_of_time_in_forward_and_adjoint": ray_share,
     "active_voxels": info["active_voxels"], "host_syncs_per_iteration": info["host_syncs_per_iteration"],
     "iterations": len(info["S"]) - 1, "seconds": dt, "s_per_iteration": dt / max(1, len(info["S"]) - 1),
+    "steady_ms_per_iteration": steady * 1e3, "forwards_per_iteration": evals_f, "gradients_per_iteration": evals_g,
     "n_forward": info["n_forward"], "n_gradient": info["n_gradient"], "operator_build_s": t_build,
     "operator_gb": (prob.bp.nbytes / 1e9) if prob.bp else 0.0, "adjoint": "scatter" if args.scatter else "binned",
     "forward": "sweep" if args.sweep else "prepared", "forward_operator_gb": (prob.fp.nbytes / 1e9) if prob.fp else 0.0,
