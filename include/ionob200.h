@@ -72,6 +72,11 @@ int iono_mul_f64(const double *a, const double *b, int64_t n, double *out, void 
 int iono_cast_rays_straight_f64(const double *origins, const double *directions, int64_t nrays,
                                 double tmax, int Ns, double *rays_out, void *stream);
 
+/* Arc length as the independent variable: Fermat(type='s') (inversion/fermat.py:74-82, :163-166) for
+ * straight rays: s = linspace(0, smax, Ns), (x,y,z) = origin + unit(direction) * s. */
+int iono_cast_rays_arclength_f64(const double *origins, const double *directions, int64_t nrays,
+                                 double smax, int Ns, double *rays_out, void *stream);
+
 /* Frame-aware variant: ITRS inputs, the reference's Pointing frame applied per ray on the fly
  * (astro/frames/pointing_frame.py:140-190 and the per-time loop of calc_rays, calc_rays.py:125-139):
  *   origin[a,t,k]    = R[t] . (ants_itrs_m[a] - p0_itrs_m) / 1000   (km)

@@ -31,6 +31,7 @@ SIGNATURES = {
     "iono_ne_from_m_f64": (_i, [_vp, _i64, _d, _vp, _vp]),
     "iono_mul_f64": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "iono_cast_rays_straight_f64": (_i, [_vp, _vp, _i64, _d, _i, _vp, _vp]),
+    "iono_cast_rays_arclength_f64": (_i, [_vp, _vp, _i64, _d, _i, _vp, _vp]),
     "iono_cast_rays_frames_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _vp, _vp]),
     "iono_ne_to_refractive_index_f64": (_i, [_vp, _i64, _d, _vp, _vp]),
     "iono_optical_path_f64": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp]),
@@ -90,7 +91,7 @@ SIGNATURES = {
 # kernels launched per C call (for bench.py's ``gpu_launches``; memsets are not counted)
 KERNEL_LAUNCHES = {
     "iono_ne_from_m_f64": 1, "iono_mul_f64": 1, "iono_cast_rays_straight_f64": 1,
-    "iono_cast_rays_frames_f64": 1, "iono_ne_to_refractive_index_f64": 1, "iono_optical_path_f64": 1,
+    "iono_cast_rays_frames_f64": 1, "iono_cast_rays_arclength_f64": 1, "iono_ne_to_refractive_index_f64": 1, "iono_optical_path_f64": 1,
     "iono_tci_interp_f64": 1, "iono_tec_forward_f64": 1, "iono_dtec_f64": 1, "iono_adjoint_coef_f64": 1,
     "iono_tec_adjoint_f64": 1, "iono_misfit_f64": 2, "iono_convolve3d_nearest_f64": 1,
     "iono_phase_integrals_f64": 1, "iono_simps_rows_f64": 1, "iono_phase_assemble_f64": 1, "iono_chord_adjoint_f64": 1,

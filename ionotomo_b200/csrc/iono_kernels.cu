@@ -246,6 +246,9 @@ struct RayConst {
 
 constexpr int CAST_RAYS_PER_CTA = 64;
 
+// ARC: arc length as the independent variable (Fermat(type='s'), fermat.py:74-82,163-166):
+// s = linspace(0, tmax, N), (x,y,z) = origin + p s.
+template <bool ARC>
 __global__ void __launch_bounds__(256) cast_rays_kernel(const double *__restrict__ origins,
                                                          const double *__restrict__ directions, int64_t nrays,
                                                          double tmax, int Ns, double *__restrict__ rays) {
@@ -262,10 +265,10 @@ __global__ void __launch_bounds__(256) cast_rays_kernel(const double *__restrict
             double px = __ddiv_rn(xd, sdot), py = __ddiv_rn(yd, sdot), pz = __ddiv_rn(zd, sdot);
             RayConst c;
             c.x0 = o[0]; c.y0 = o[1]; c.z0 = o[2];
-            c.kx = __ddiv_rn(px, pz);
-            c.ky = __ddiv_rn(py, pz);
+            c.kx = ARC ? px : __ddiv_rn(px, pz);
+            c.ky = ARC ? py : __ddiv_rn(py, pz);
             c.pz = pz;
-            c.step = __ddiv_rn(__dadd_rn(tmax, -c.z0), (double)(Ns - 1));
+            c.step = ARC ? __ddiv_rn(tmax, (double)(Ns - 1)) : __ddiv_rn(__dadd_rn(tmax, -c.z0), (double)(Ns - 1));
             rc[threadIdx.x] = c;
         }
         __syncthreads();
@@ -273,6 +276,14 @@ __global__ void __launch_bounds__(256) cast_rays_kernel(const double *__restrict
             const RayConst c = rc[r];
             double *out = rays + (base + r) * 4 * (int64_t)Ns;
             for (int i = lane; i < Ns; i += 32) {
+                if (ARC) {
+                    const double sv = (i == Ns - 1 && Ns > 1) ? tmax : __dmul_rn((double)i, c.step);
+                    __stcs(out + i, __dadd_rn(c.x0, __dmul_rn(c.kx, sv)));
+                    __stcs(out + Ns + i, __dadd_rn(c.y0, __dmul_rn(c.ky, sv)));
+                    __stcs(out + 2 * (int64_t)Ns + i, __dadd_rn(c.z0, __dmul_rn(c.pz, sv)));
+                    __stcs(out + 3 * (int64_t)Ns + i, sv);
+                    continue;
+                }
                 double z = (i == Ns - 1 && Ns > 1) ? tmax : __dadd_rn(__dmul_rn((double)i, c.step), c.z0);
                 double dz = __dadd_rn(z, -c.z0);
                 __stcs(out + i, __dadd_rn(c.x0, __dmul_rn(c.kx, dz)));
@@ -368,8 +379,22 @@ extern "C" int iono_cast_rays_straight_f64(const double *origins, const double *
     if (nrays == 0) return IONO_OK;
     int64_t ctas = (nrays + CAST_RAYS_PER_CTA - 1) / CAST_RAYS_PER_CTA;
     int64_t cap = (int64_t)sm_count() * 8;
-    cast_rays_kernel<<<(int)(ctas < cap ? ctas : cap), 256, 0, (cudaStream_t)stream>>>(origins, directions, nrays,
-                                                                                       tmax, Ns, rays_out);
+    cast_rays_kernel<false><<<(int)(ctas < cap ? ctas : cap), 256, 0, (cudaStream_t)stream>>>(origins, directions,
+                                                                                              nrays, tmax, Ns, rays_out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
+
+// Fermat(type='s') with straight rays: s = linspace(0, smax, Ns), position = origin + unit direction * s.
+extern "C" int iono_cast_rays_arclength_f64(const double *origins, const double *directions, int64_t nrays,
+                                            double smax, int Ns, double *rays_out, void *stream) {
+    if (!origins || !directions || !rays_out || nrays < 0 || Ns < 1)
+        return fail(IONO_EBADARG, "iono_cast_rays_arclength_f64: bad argument");
+    if (nrays == 0) return IONO_OK;
+    int64_t ctas = (nrays + CAST_RAYS_PER_CTA - 1) / CAST_RAYS_PER_CTA;
+    int64_t cap = (int64_t)sm_count() * 8;
+    cast_rays_kernel<true><<<(int)(ctas < cap ? ctas : cap), 256, 0, (cudaStream_t)stream>>>(origins, directions,
+                                                                                             nrays, smax, Ns, rays_out);
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
 }

@@ -5,7 +5,9 @@ straight-ray in effect (``euler_ode`` hard-codes grad n = 0, ``fermat.py:53-55``
 every production caller passes ``straight_line_approx=True``), with the
 z coordinate as independent variable (``type='z'``): the closed form
 ``x = x0 + (px/pz)(z - z0)``, ``s = (z - z0)/pz`` on ``z = linspace(z0, tmax, N)``
-is evaluated on the GPU by ``iono_cast_rays_straight_f64``.
+is evaluated on the GPU by ``iono_cast_rays_straight_f64``.  ``type='s'`` (arc length as the independent
+variable, ``fermat.py:74-82``): ``s = linspace(0, tmax, N)``, position ``= origin + p s``
+(``iono_cast_rays_arclength_f64``).
 """
 import numpy as np
 import torch
@@ -15,9 +17,12 @@ from .. import _lib
 
 class Fermat(object):
     def __init__(self, ne_tci=None, frequency=120e6, type='z', straight_line_approx=True):
-        if type != 'z':
-            raise NotImplementedError("only type='z' (z as independent variable) is built; "
-                                      "it is the only mode calc_rays uses (calc_rays.py:142)")
+        if type not in ('z', 's'):
+            raise ValueError("type must be 'z' (z as the independent variable) or 's' (arc length)")
+        if type == 's' and not straight_line_approx:
+            # fermat.py:74-82 with the interpolated index: dx/ds = p/n along a fixed direction; no caller of the
+            # reference uses it (calc_rays.py:142 always passes type='z')
+            raise NotImplementedError("type='s' is built for straight_line_approx=True")
         self.type = type
         self.frequency = frequency  # Hz
         self.straight_line_approx = straight_line_approx
@@ -33,8 +38,8 @@ class Fermat(object):
         lead = tuple(o.shape[:-1])
         nrays = int(np.prod(lead)) if lead else 1
         rays = torch.empty(lead + (4, int(N)), dtype=torch.float64, device=o.device)
-        _lib.call("iono_cast_rays_straight_f64", _lib.ptr(o), _lib.ptr(d), nrays, float(tmax), int(N),
-                  _lib.ptr(rays), _lib.stream_ptr())
+        _lib.call("iono_cast_rays_straight_f64" if self.type == 'z' else "iono_cast_rays_arclength_f64", _lib.ptr(o),
+                  _lib.ptr(d), nrays, float(tmax), int(N), _lib.ptr(rays), _lib.stream_ptr())
         if not self.straight_line_approx:
             # the shipped "curved" mode: same geometry, s becomes the optical path int n dz/pz
             # (euler_ode with grad n == 0, fermat.py:53-55,57-66)

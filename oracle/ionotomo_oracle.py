@@ -233,6 +233,16 @@ def integrate_ray_straight(origin, direction, tmax, N):
     return x, y, z, s
 
 
+def integrate_ray_arclength(origin, direction, smax, N):
+    """``Fermat(type='s').integrate_ray`` for straight rays (inversion/fermat.py:74-82, :163-166): the
+    independent variable is the arc length, ``s = linspace(0, smax, N)``, position ``= origin + p s``."""
+    o = np.asarray(origin, dtype=np.float64)
+    d = np.asarray(direction, dtype=np.float64)
+    p = d / np.sqrt(d[0] ** 2 + d[1] ** 2 + d[2] ** 2)
+    s = np.linspace(0., smax, N)
+    return o[0] + p[0] * s, o[1] + p[1] * s, o[2] + p[2] * s, s
+
+
 def cast_ray(origins, directions, tmax, N):
     """Vectorised ``cast_ray`` (geometry/calc_rays.py:61-96): (Na,Nt,Nd,3) ->
     rays (Na,Nt,Nd,4,N), rows x,y,z,s.  Same formulas as `integrate_ray_straight`."""

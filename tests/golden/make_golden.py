@@ -80,26 +80,10 @@ class _StubFinder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
         pass
 
 
-def _simps(y, x=None, dx=1, axis=-1, even='avg'):
-    """Old ``scipy.integrate.simps`` from installed-SciPy pieces only."""
-    assert even == 'avg'
-    y = np.asarray(y)
-    N = y.shape[axis]
-    if N % 2 == 1:
-        return scipy.integrate.simpson(y, x=x, dx=dx, axis=axis)
-    y = np.moveaxis(y, axis, -1)
-    if x is None:
-        x = np.arange(N) * dx
-    x = np.asarray(x)
-    if x.ndim > 1:
-        x = np.moveaxis(x, axis, -1)
-    else:
-        x = np.broadcast_to(x, y.shape)
-    first = scipy.integrate.simpson(y[..., :-1], x=x[..., :-1], axis=-1) \
-        + 0.5 * (x[..., -1] - x[..., -2]) * (y[..., -1] + y[..., -2])
-    last = scipy.integrate.simpson(y[..., 1:], x=x[..., 1:], axis=-1) \
-        + 0.5 * (x[..., 1] - x[..., 0]) * (y[..., 1] + y[..., 0])
-    return 0.5 * (first + last)
+# scipy.integrate.simps is gone from the installed SciPy: the reference's modules get the routine they were
+# written against, transcribed from the SciPy releases of their time (old_scipy_simps.py)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from old_scipy_simps import simps as _simps  # noqa: E402
 
 
 def install():
@@ -328,8 +312,48 @@ def main():
     np.savez(os.path.join(OUT, "synthetic.npz"), xvec=xvec, yvec=yvec, zvec=zvec, dm=dm, h=h,
              chap45=chap45, chap80=chap80)
     golden_gauss()
+    golden_simps_even()
+    golden_fermat_s()
     print("golden vectors written to", OUT)
 
 
+def golden_simps_even():
+    """Old SciPy's simps on NON-uniform abscissae, even and odd N, all three `even` modes: pins the oracle's and the
+    kernels' Simpson weights beyond the uniform-x numbers of the old docstring."""
+    rng = np.random.RandomState(77)
+    out = {}
+    for N in (2, 3, 4, 5, 6, 9, 10, 30, 31, 64, 128, 129, 256):
+        x = np.cumsum(rng.uniform(0.3, 2.5, size=(5, N)), axis=1)
+        y = rng.normal(size=(5, N)) + np.sin(x / 7.)
+        out["x%d" % N], out["y%d" % N] = x, y
+        out["avg%d" % N] = _simps(y, x, axis=1, even='avg')
+        if N % 2 == 0:
+            out["first%d" % N] = _simps(y, x, axis=1, even='first')
+            out["last%d" % N] = _simps(y, x, axis=1, even='last')
+    x10 = np.arange(0, 10)
+    out["doc_avg"], out["doc_first"] = _simps(np.power(x10, 3), x10), _simps(np.power(x10, 3), x10, even='first')
+    np.savez(os.path.join(OUT, "simps_even.npz"), **out)
+
+
+def golden_fermat_s():
+    """Fermat(type='s'): arc length as the independent variable (inversion/fermat.py:74-82,163-166), straight rays."""
+    from ionotomo.geometry.tri_cubic import TriCubic
+    from ionotomo.inversion.fermat import Fermat
+    xvec, yvec, zvec, ne, origins, directions, rng = small_problem(21, 3, 2, 4, 15, 10, 9, 11)
+    ne_tci = TriCubic(xvec, yvec, zvec, ne)
+    fermat = Fermat(ne_tci=ne_tci, frequency=120e6, type='s', straight_line_approx=True)
+    rays = np.zeros(origins.shape[:3] + (4, 15))
+    for i in range(origins.shape[0]):
+        for j in range(origins.shape[1]):
+            for k in range(origins.shape[2]):
+                rays[i, j, k] = np.stack(fermat.integrate_ray(origins[i, j, k], directions[i, j, k], 950., N=15))
+    np.savez(os.path.join(OUT, "fermat_s.npz"), origins=origins, directions=directions, rays=rays, tmax=950., Ns=15)
+
+
 if __name__ == "__main__":
-    main()
+    install()
+    if len(sys.argv) > 1 and sys.argv[1] == "--extra-only":     # the two fixtures added in round 2
+        golden_simps_even()
+        golden_fermat_s()
+    else:
+        main()

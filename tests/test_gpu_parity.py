@@ -1011,3 +1011,35 @@ def test_device_session_matches_separate_calls(ib, forward, adjoint, graph):
         assert np.abs(grad.cpu().numpy() - grad_ref).max() < 1e-7 * np.abs(grad_ref).max()
     dtec, S2 = ses.forward(torch.as_tensor(P["m"]).cuda())
     assert np.abs(dtec.cpu().numpy() - g_true).max() < TOL * tec_scale
+
+
+def test_fermat_arclength_mode(ib, golden):
+    """Fermat(type='s'): bit-identical to the oracle's closed form, equal to the reference's odeint output."""
+    g = golden("fermat_s")
+    f = ib.Fermat(None, type='s')
+    rays = f.cast(g["origins"], g["directions"], float(g["tmax"]), int(g["Ns"]))
+    np.testing.assert_allclose(rays, g["rays"], rtol=0, atol=1e-9)
+    o, d = g["origins"], g["directions"]
+    for idx in [(0, 0, 0), (2, 1, 3)]:
+        ref = np.stack(O.integrate_ray_arclength(o[idx], d[idx], float(g["tmax"]), int(g["Ns"])))
+        assert np.array_equal(rays[idx], ref)
+    x, y, z, s = f.integrate_ray(o[1, 0, 2], d[1, 0, 2], 500., N=7)
+    assert np.array_equal(s, np.linspace(0., 500., 7)) and x.shape == (7,)
+    with pytest.raises(NotImplementedError):
+        ib.Fermat(None, type='s', straight_line_approx=False)
+
+
+def test_simps_rows_kernel_against_old_scipy(ib, golden):
+    """iono_simps_rows_f64 (the sweep's per-sample Simpson weights applied to tabulated integrands) on the
+    non-uniform even/odd-N fixture written by the old SciPy routine."""
+    import torch
+    from ionotomo_b200 import _lib
+    g = golden("simps_even")
+    for N in (2, 3, 4, 5, 6, 9, 10, 30, 31, 64, 128, 129, 256):
+        x, y, ref = g["x%d" % N], g["y%d" % N], g["avg%d" % N]
+        rays = np.zeros((x.shape[0], 4, N))
+        rays[:, 3, :] = x
+        out = torch.empty(x.shape[0], dtype=torch.float64, device="cuda")
+        _lib.call("iono_simps_rows_f64", _lib.ptr(torch.as_tensor(y).cuda()), None, _lib.ptr(torch.as_tensor(rays).cuda()),
+                  x.shape[0], N, 0, 0.0, _lib.ptr(out), 1, _lib.stream_ptr())
+        np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-12, atol=1e-12 * np.abs(y).max() * np.ptp(x))

@@ -290,3 +290,28 @@ def test_gaussian_adjoint_matches_reference(golden):
     raw = O.gaussian_adjoint(g["rays"], dd, i0, K, xv, yv, zv, g["m"], sig, Nk, cell)
     assert np.all(raw[-1] == 0) and np.all(raw[:, -1] == 0) and np.all(raw[:, :, -1] == 0)
     assert np.abs(raw).max() > 0
+
+
+def test_simps_nonuniform_even_n_against_old_scipy(golden):
+    """tests/golden/simps_even.npz comes from the old SciPy routine itself (tests/golden/old_scipy_simps.py, a
+    transcription of scipy/integrate/quadrature.py of SciPy 0.19-1.5) on NON-uniform abscissae: the oracle's
+    even='avg' rule and its per-sample weights must reproduce it for even and odd N."""
+    g = golden("simps_even")
+    assert float(g["doc_avg"]) == 1642.5 and float(g["doc_first"]) == 1644.5      # the old docstring's answers
+    for N in (2, 3, 4, 5, 6, 9, 10, 30, 31, 64, 128, 129, 256):
+        x, y, ref = g["x%d" % N], g["y%d" % N], g["avg%d" % N]
+        np.testing.assert_allclose(O.simps_avg(y, x), ref, rtol=1e-13, atol=1e-13 * np.abs(y).max() * np.ptp(x))
+        w = np.stack([O.simps_weights(xi) for xi in x])
+        np.testing.assert_allclose((w * y).sum(1), ref, rtol=1e-12, atol=1e-12 * np.abs(y).max() * np.ptp(x))
+        if N % 2 == 0 and N > 2:
+            # 'avg' is the mean of the two one-sided rules
+            np.testing.assert_allclose(0.5 * (g["first%d" % N] + g["last%d" % N]), ref, rtol=1e-13)
+
+
+def test_fermat_arclength_golden(golden):
+    """Fermat(type='s') of the reference (odeint on the straight ODE) against the closed form."""
+    g = golden("fermat_s")
+    o, d = g["origins"], g["directions"]
+    for idx in np.ndindex(*o.shape[:3]):
+        x, y, z, s = O.integrate_ray_arclength(o[idx], d[idx], float(g["tmax"]), int(g["Ns"]))
+        np.testing.assert_allclose(np.stack([x, y, z, s]), g["rays"][idx], rtol=0, atol=1e-9)
