@@ -296,6 +296,10 @@ int iono_peer_reduce_expand_f64(void *const *acc, void *const *res, void *const 
 int64_t iono_multi_dot_scratch_elems(void);
 int iono_multi_dot_f64(const double *H, int64_t ld, int rows, const double *x, const double *w, int64_t n,
                        double *scratch, double *out, void *stream);
+/* three right-hand sides that are rows of H themselves, one pass over the history:
+ * out[j*32 + r] = sum_i w[i] H[r][i] H[x_row_j][i], j < 3 (out: 96 doubles) */
+int iono_multi_dot3_f64(const double *H, int64_t ld, int rows, int x_row0, int x_row1, int x_row2, const double *w,
+                        int64_t n, double *scratch, double *out, void *stream);
 int iono_lincomb_f64(const double *H, int64_t ld, int rows, const double *coef_dev, const double *x, int64_t n,
                      double *out, void *stream);
 int iono_gather_f64(const double *src, const int *idx, int64_t n, double *out, void *stream);

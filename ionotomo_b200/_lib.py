@@ -69,6 +69,7 @@ SIGNATURES = {
     "iono_backprojector_destroy": (_i, [_vp]),
     "iono_multi_dot_scratch_elems": (_i64, []),
     "iono_multi_dot_f64": (_i, [_vp, _i64, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "iono_multi_dot3_f64": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "iono_lincomb_f64": (_i, [_vp, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
     "iono_gather_f64": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "iono_scatter_set_f64": (_i, [_vp, _vp, _i64, _vp, _vp]),
@@ -100,7 +101,7 @@ KERNEL_LAUNCHES = {
     "iono_backprojector_apply_permuted_f64": 3, "iono_backprojector_apply_gradient_f64": 3,
     "iono_backprojector_apply_compact_f64": 3, "iono_backprojector_ne_rows_f64": 1, "iono_forwardprojector_quads_from_m_f64": 1,
     "iono_forwardprojector_create": 1, "iono_forwardprojector_apply_f64": 2, "iono_forwardprojector_apply_quads_f64": 1,
-    "iono_peer_reduce_expand_f64": 1, "iono_multi_dot_f64": 2, "iono_lincomb_f64": 1, "iono_gather_f64": 1, "iono_scatter_set_f64": 1,
+    "iono_peer_reduce_expand_f64": 1, "iono_multi_dot_f64": 2, "iono_multi_dot3_f64": 4, "iono_lincomb_f64": 1, "iono_gather_f64": 1, "iono_scatter_set_f64": 1,
     "iono_scatter_axpy_f64": 1,
     "iono_quads_from_ne_f64": 1, "iono_ne_quads_from_m_f64": 1, "iono_tec_forward_quads_f64": 1, "iono_residual_f64": 1,
 }

@@ -61,7 +61,84 @@ __global__ void __launch_bounds__(256) multi_dot_final_kernel(const double *__re
     }
 }
 
-extern "C" int64_t iono_multi_dot_scratch_elems(void) { return (int64_t)OPT_BLOCKS * OPT_MAX_ROWS; }
+// Three right-hand sides at once: out[j][r] = sum_i w[i] H[r][i] H[xr[j]][i] for rows r0 <= r < r0 + ROWS -- the
+// products of the whole history with the new gradient, the new y and the new s in ONE pass over the history.
+template <int ROWS>
+__global__ void __launch_bounds__(256) multi_dot3_kernel(const double *__restrict__ H, long long ld, int r0, int rows,
+                                                          int x0, int x1, int x2, const double *__restrict__ w,
+                                                          long long n, double *__restrict__ partial) {
+    __shared__ double red[8][3 * ROWS];
+    double acc[3][ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) acc[0][r] = acc[1][r] = acc[2][r] = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double a = H[x0 * ld + i], b = H[x1 * ld + i], c = H[x2 * ld + i];
+        if (w) { const double wi = w[i]; a *= wi; b *= wi; c *= wi; }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+            if (r0 + r < rows) {
+                const double h = H[(r0 + r) * ld + i];
+                acc[0][r] = fma(h, a, acc[0][r]);
+                acc[1][r] = fma(h, b, acc[1][r]);
+                acc[2][r] = fma(h, c, acc[2][r]);
+            }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const double t = warp_sum(acc[j][r]);
+            if (lane == 0) red[warp][j * ROWS + r] = t;
+        }
+    __syncthreads();
+    if (threadIdx.x < 3 * ROWS) {
+        const int j = threadIdx.x / ROWS, r = threadIdx.x % ROWS;
+        if (r0 + r < rows) {
+            double t = 0.0;
+            for (int q = 0; q < 8; ++q) t += red[q][threadIdx.x];
+            partial[((long long)blockIdx.x * 3 + j) * OPT_MAX_ROWS + r0 + r] = t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) multi_dot3_final_kernel(const double *__restrict__ partial, int blocks, int rows,
+                                                                double *__restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = warp; q < 3 * rows; q += 8) {
+        const int j = q / rows, r = q % rows;
+        double t = 0.0;
+        for (int b = lane; b < blocks; b += 32) t += partial[((long long)b * 3 + j) * OPT_MAX_ROWS + r];
+        t = warp_sum(t);
+        if (lane == 0) out[j * OPT_MAX_ROWS + r] = t;
+    }
+}
+
+extern "C" int64_t iono_multi_dot_scratch_elems(void) { return (int64_t)OPT_BLOCKS * OPT_MAX_ROWS * 3; }
+
+// out[j*32 + r] = sum_i w[i] H[r][i] H[x_rows[j]][i], j < 3, r < rows <= 32: the history is read once (in groups of
+// 8 rows) for all three right-hand sides, which are rows of H themselves.
+extern "C" int iono_multi_dot3_f64(const double *H, int64_t ld, int rows, int x_row0, int x_row1, int x_row2,
+                                   const double *w, int64_t n, double *scratch, double *out, void *stream) {
+    if (rows < 0 || rows > OPT_MAX_ROWS || n < 0 || ld < n || !out || !scratch || x_row0 < 0 || x_row1 < 0 || x_row2 < 0)
+        return fail(IONO_EBADARG, "iono_multi_dot3_f64: bad argument (rows <= 32)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 0) return IONO_OK;
+    if (n == 0) {
+        CU_CHECK(cudaMemsetAsync(out, 0, 3 * OPT_MAX_ROWS * sizeof(double), st));
+        return IONO_OK;
+    }
+    if (!H) return fail(IONO_EBADARG, "iono_multi_dot3_f64: NULL pointer");
+    long long want = (n + 255) / 256;
+    const int blocks = (int)(want < OPT_BLOCKS ? want : OPT_BLOCKS);
+    for (int r0 = 0; r0 < rows; r0 += 8)
+        multi_dot3_kernel<8><<<blocks, 256, 0, st>>>(H, ld, r0, rows, x_row0, x_row1, x_row2, w, n, scratch);
+    CU_CHECK(cudaGetLastError());
+    multi_dot3_final_kernel<<<1, 256, 0, st>>>(scratch, blocks, rows, out);
+    CU_CHECK(cudaGetLastError());
+    return IONO_OK;
+}
 
 extern "C" int iono_multi_dot_f64(const double *H, int64_t ld, int rows, const double *x, const double *w, int64_t n,
                                   double *scratch, double *out, void *stream) {

@@ -118,13 +118,15 @@ def _simps_avg_1d(y, x):
 
 
 class _Vectors(object):
-    """History matrix + work rows on the active voxels, and the kernels that act on them."""
+    """History matrix + work rows on the active voxels, and the kernels that act on them.
+    Rows: s in slots 0..k-1, y in slots k..2k-1 (a pair occupies physical slot p and k+p; pairs are kept in a ring,
+    ``order`` lists the slots from oldest to newest), then G (current gradient), D (direction), T (new gradient)."""
 
     def __init__(self, n, history, device, weights=None):
         lib = _lib.load()
         self.n, self.k = int(n), int(history)
+        assert 2 * self.k + 3 <= 32, "history <= 14"
         self.ld = (self.n + 3) // 4 * 4
-        # rows: s_0..s_{k-1}, y_0..y_{k-1}, G (current gradient), D (direction), T (new gradient)
         self.H = torch.zeros((2 * self.k + 3, self.ld), dtype=torch.float64, device=device)
         self.G, self.D, self.T = 2 * self.k, 2 * self.k + 1, 2 * self.k + 2
         self.scratch = torch.empty(int(lib.iono_multi_dot_scratch_elems()), dtype=torch.float64, device=device)
@@ -140,11 +142,18 @@ class _Vectors(object):
     def row(self, r):
         return self.H[r]
 
+    def _w(self, weighted=True):
+        return _lib.ptr(self.w) if (self.w is not None and weighted) else None
+
     def multi_dot(self, rows, x_row, slot, weighted=True):
         """dots[slot, r] = <H[r], H[x_row]> for r < rows."""
         _lib.call("iono_multi_dot_f64", _lib.ptr(self.H), self.ld, int(rows), _lib.ptr(self.H[x_row]),
-                  _lib.ptr(self.w) if (self.w is not None and weighted) else None, self.n, _lib.ptr(self.scratch),
-                  _lib.ptr(self.dots[slot]), _lib.stream_ptr())
+                  self._w(weighted), self.n, _lib.ptr(self.scratch), _lib.ptr(self.dots[slot]), _lib.stream_ptr())
+
+    def multi_dot3(self, rows, x0, x1, x2):
+        """dots[j, r] = <H[r], H[x_j]> for r < rows, j = 0, 1, 2: one pass over the history."""
+        _lib.call("iono_multi_dot3_f64", _lib.ptr(self.H), self.ld, int(rows), int(x0), int(x1), int(x2), self._w(),
+                  self.n, _lib.ptr(self.scratch), _lib.ptr(self.dots), _lib.stream_ptr())
 
     def fetch_dots(self):
         self.dots_h.copy_(self.dots, non_blocking=True)
@@ -173,6 +182,7 @@ def lbfgs_solve(problem, m0, n_iter=50, history=10, c1=1e-4, max_backtracks=20, 
     (wall time of every iteration; the first ones include the one-off CUDA-graph captures of the session).
     ``metric``: ``None`` (Euclidean) or ``"simpson"`` (the reference's grid inner product).
     """
+    import time as _time
     ses = problem if isinstance(problem, DeviceSession) else _session_from_problem(problem)
     dev = ses.device
     m = _lib.to_device(m0).reshape(ses.shape).clone()
@@ -198,46 +208,48 @@ def lbfgs_solve(problem, m0, n_iter=50, history=10, c1=1e-4, max_backtracks=20, 
     k = history
     step_dev = torch.zeros(1, dtype=torch.float64, device=dev)
     step_pin = torch.zeros(1, dtype=torch.float64).pin_memory()
-    m_trial = m.clone()
+    ses.m.copy_(m)
 
     def gather(src, row):
         _lib.call("iono_gather_f64", _lib.ptr(src), ctypes.c_void_p(idx.data_ptr()), n, _lib.ptr(V.row(row)),
                   _lib.stream_ptr())
 
     def trial(step):
+        """Forward at m + step * d, written straight into the session's model buffer; returns the misfit
+        (the one host synchronisation of a trial)."""
         step_pin[0] = step
         step_dev.copy_(step_pin, non_blocking=True)
         _lib.call("iono_scatter_axpy_f64", _lib.ptr(m), _lib.ptr(step_dev), _lib.ptr(V.row(V.D)),
-                  ctypes.c_void_p(idx.data_ptr()), n, _lib.ptr(m_trial), _lib.stream_ptr())
-        dtec, S_t = ses.forward(m_trial)
-        return float(S_t)                       # the one host sync of a trial
+                  ctypes.c_void_p(idx.data_ptr()), n, _lib.ptr(ses.m), _lib.stream_ptr())
+        dtec, S_t = ses.forward(None)
+        return float(S_t)
 
-    S, grad = ses.misfit_and_gradient(m)
+    S, grad = ses.misfit_and_gradient(None)
     S = float(S)
     gather(grad, V.G)
     S_hist = [S]
-    count = 0                  # pairs stored (chronological order in rows 0..count-1 / k..k+count-1)
-    SY = np.zeros((k, k))
+    order = []                 # physical slots of the stored pairs, oldest first
+    SY = np.zeros((k, k))      # SY[p, q] = <s_p, y_q>, YY[p, q] = <y_p, y_q>  (physical slots)
     YY = np.zeros((k, k))
     step0 = None
-    syncs = []
-    import time as _time
-    iter_seconds = []
-    _t_prev = _time.time()
-    # products of the current gradient with the history and with itself
-    V.multi_dot(2 * k + 1, V.G, 0)
+    syncs, iter_seconds = [], []
+    t_prev = _time.time()
+    V.multi_dot(2 * k + 1, V.G, 0)       # <every row, g> incl. <g, g>
+    d = V.fetch_dots()
     for it in range(n_iter):
-        n_sync = 1
-        d = V.fetch_dots()
-        p1, p2, gg = d[0, :count].copy(), d[0, k:k + count].copy(), float(d[0, V.G])
-        use_history = count > 0
+        n_sync = 0
+        c = len(order)
+        o = np.array(order, dtype=int)
+        p1, p2, gg = d[0, o].copy(), d[0, k + o].copy(), float(d[0, V.G])
+        use_history = c > 0
         if use_history:
-            R = np.triu(SY[:count, :count])
-            Dg = np.diag(np.diag(SY[:count, :count]))
-            gamma = SY[count - 1, count - 1] / YY[count - 1, count - 1]
+            SYc, YYc = SY[np.ix_(o, o)], YY[np.ix_(o, o)]
+            R = np.triu(SYc)
+            Dg = np.diag(np.diag(SYc))
+            gamma = SYc[-1, -1] / YYc[-1, -1]
             try:
                 Rinv_p1 = np.linalg.solve(R, p1)
-                u = np.linalg.solve(R.T, (Dg + gamma * YY[:count, :count]) @ Rinv_p1 - gamma * p2)
+                u = np.linalg.solve(R.T, (Dg + gamma * YYc) @ Rinv_p1 - gamma * p2)
                 v = -Rinv_p1
                 gd = -(gamma * gg + u @ p1 + gamma * (v @ p2))
             except np.linalg.LinAlgError:
@@ -247,41 +259,33 @@ def lbfgs_solve(problem, m0, n_iter=50, history=10, c1=1e-4, max_backtracks=20, 
         if use_history:
             coefs = np.zeros(2 * k + 1)
             coefs[0] = -gamma
-            coefs[1:1 + count] = -u
-            coefs[1 + k:1 + k + count] = -gamma * v
+            coefs[1 + o] = -u
+            coefs[1 + k + o] = -gamma * v
             V.lincomb(coefs, V.G, V.D, rows=2 * k)
-            if w is not None:                   # the Armijo test needs the Euclidean directional derivative
-                V.multi_dot_rows = None
-                _lib.call("iono_multi_dot_f64", _lib.ptr(V.H[V.D]), V.ld, 1, _lib.ptr(V.H[V.G]), None, n,
-                          _lib.ptr(V.scratch), _lib.ptr(V.dots[1]), _lib.stream_ptr())
-                gd = float(V.fetch_dots()[1, 0])
-                n_sync += 1
             step = 1.0
         else:
-            count = 0
+            order = []
             V.lincomb([-1.0], V.G, V.D, rows=0)
-            if w is not None:
-                _lib.call("iono_multi_dot_f64", _lib.ptr(V.H[V.G]), V.ld, 1, _lib.ptr(V.H[V.G]), None, n,
-                          _lib.ptr(V.scratch), _lib.ptr(V.dots[1]), _lib.stream_ptr())
-                gd = -float(V.fetch_dots()[1, 0])
-                n_sync += 1
-            else:
-                gd = -gg
-            if step0 is None:
-                # secant estimate of the step along -grad from one probe (reference line_search.py:55-66)
-                gmax = float(V.row(V.G)[:n].abs().max())
-                ep = 1e-3 / max(gmax, 1e-300)
-                g0 = ses.dtec.clone()
-                trial(ep)
-                Gm = (ses.dtec - g0) / ep
-                dd = (g0 - ses.dobs) / (ses.CdCt + 1e-15)
-                nd = torch.stack([torch.sum(dd * Gm), torch.sum(Gm * Gm / (ses.CdCt + 1e-15))])
-                if ses.sharded and ses.world > 1:
-                    torch.distributed.all_reduce(nd, group=ses.group)
-                num, den = float(nd[0]), float(nd[1])
-                step0 = abs(num / den) if den > 0 else 1.0
-                n_sync += 3
+            gd = -gg
             step = step0
+        if w is not None:                       # the Armijo test needs the Euclidean directional derivative
+            V.multi_dot(V.G + 1, V.D, 1, weighted=False)
+            gd = float(V.fetch_dots()[1, V.G])
+            n_sync += 1
+        if step is None:
+            # secant estimate of the step along -grad from one probe (reference line_search.py:55-66)
+            gmax = float(V.row(V.G)[:n].abs().max())
+            ep = 1e-3 / max(gmax, 1e-300)
+            g0 = ses.dtec.clone()
+            trial(ep)
+            Gm = (ses.dtec - g0) / ep
+            dd = (g0 - ses.dobs) / (ses.CdCt + 1e-15)
+            nd = torch.stack([torch.sum(dd * Gm), torch.sum(Gm * Gm / (ses.CdCt + 1e-15))])
+            if ses.sharded and ses.world > 1:
+                torch.distributed.all_reduce(nd, group=ses.group)
+            num, den = float(nd[0]), float(nd[1])
+            step = step0 = abs(num / den) if den > 0 else 1.0
+            n_sync += 3
         accepted = False
         for _ in range(max_backtracks):
             S_new = trial(step)
@@ -291,41 +295,39 @@ def lbfgs_solve(problem, m0, n_iter=50, history=10, c1=1e-4, max_backtracks=20, 
                 break
             step *= 0.5
         if not accepted:
+            ses.m.copy_(m)
             break
         grad = ses.gradient_after_forward()
         gather(grad, V.T)
-        # new pair: s = step * d, y = g_new - g; drop the oldest pair when the history is full
-        if count == k:
-            V.H[0:k - 1].copy_(V.H[1:k].clone())
-            V.H[k:2 * k - 1].copy_(V.H[k + 1:2 * k].clone())
-            SY[:k - 1, :k - 1] = SY[1:, 1:]
-            YY[:k - 1, :k - 1] = YY[1:, 1:]
-            count = k - 1
-        V.lincomb([step], V.D, count, rows=0)
-        V.lincomb([1.0, -1.0], V.T, k + count, rows=1, first_row=V.G)
+        # new pair in a free slot (or in the oldest pair's): s = step * d, y = g_new - g
+        if len(order) == k:
+            p = order.pop(0)
+        else:
+            p = [q for q in range(k) if q not in order][0]
+        V.lincomb([step], V.D, p, rows=0)
+        V.lincomb([1.0, -1.0], V.T, k + p, rows=1, first_row=V.G)
         V.H[V.G].copy_(V.H[V.T])
-        m, m_trial = m_trial, m
+        # m += step * d on the active voxels (the same arithmetic that produced the accepted trial model)
+        _lib.call("iono_scatter_axpy_f64", _lib.ptr(m), _lib.ptr(step_dev), _lib.ptr(V.row(V.D)),
+                  ctypes.c_void_p(idx.data_ptr()), n, _lib.ptr(m), _lib.stream_ptr())
         S = S_new
         S_hist.append(S)
-        # all products the next iteration needs, one copy to the host at its start:
-        #   slot 0: <rows, g_new>   slot 1: <rows, y_new>   slot 2: <rows, s_new>
-        V.multi_dot(2 * k + 1, V.G, 0)
-        V.multi_dot(2 * k, k + count, 1)
-        V.multi_dot(2 * k, count, 2)
+        # every product the next iteration needs in one pass over the history and ONE copy to the host:
+        #   dots[0] = <rows, g_new>   dots[1] = <rows, y_new>   dots[2] = <rows, s_new>
+        V.multi_dot3(2 * k + 1, V.G, k + p, p)
         d = V.fetch_dots()
         n_sync += 1
-        sy = d[1, count]
-        yy = d[1, k + count]
+        sy, yy = d[1, p], d[1, k + p]
         if sy > 1e-12 * yy:
-            SY[:count + 1, count] = d[1, :count + 1]            # s_i . y_new
-            SY[count, :count + 1] = d[2, k:k + count + 1]       # s_new . y_j
-            YY[:count + 1, count] = d[1, k:k + count + 1]
-            YY[count, :count + 1] = d[1, k:k + count + 1]
-            count += 1
+            SY[:, p] = d[1, :k]                 # <s_q, y_new>
+            SY[p, :] = d[2, k:2 * k]            # <s_new, y_q>
+            YY[:, p] = d[1, k:2 * k]
+            YY[p, :] = d[1, k:2 * k]
+            order.append(p)
         syncs.append(n_sync)
-        _t_now = _time.time()                   # (fetch_dots above synchronised the stream)
-        iter_seconds.append(_t_now - _t_prev)
-        _t_prev = _t_now
+        t_now = _time.time()                    # (fetch_dots above synchronised the stream)
+        iter_seconds.append(t_now - t_prev)
+        t_prev = t_now
         if callback is not None:
             callback(it, m, S)
     return m, {"S": S_hist, "n_forward": ses.n_forward, "n_gradient": ses.n_gradient, "active_voxels": n,
