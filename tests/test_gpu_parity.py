@@ -1042,6 +1042,7 @@ def test_simps_rows_kernel_against_old_scipy(ib, golden):
         rays = np.zeros((x.shape[0], 4, N))
         rays[:, 3, :] = x
         out = torch.empty(x.shape[0], dtype=torch.float64, device="cuda")
-        _lib.call("iono_simps_rows_f64", _lib.ptr(torch.as_tensor(y).cuda()), None, _lib.ptr(torch.as_tensor(rays).cuda()),
-                  x.shape[0], N, 0, 0.0, _lib.ptr(out), 1, _lib.stream_ptr())
+        y_d, rays_d = torch.as_tensor(y).cuda(), torch.as_tensor(rays).cuda()      # keep the buffers alive over the call
+        _lib.call("iono_simps_rows_f64", _lib.ptr(y_d), None, _lib.ptr(rays_d), x.shape[0], N, 0, 0.0, _lib.ptr(out), 1,
+                  _lib.stream_ptr())
         np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-12, atol=1e-12 * np.abs(y).max() * np.ptp(x))
