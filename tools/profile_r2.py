@@ -24,10 +24,15 @@ fp = ForwardProjector(rays, m_tci)
 bp = BackProjector(rays, m_tci)
 dobs = torch.zeros(rays.shape[:3], dtype=torch.float64, device="cuda")
 C = torch.full_like(dobs, 1e-4)
+from ionotomo_b200 import _lib
 for _ in range(2):
     tec = tec_from_quads(rays, m_tci.grid(), quads, check_bounds=False)
+    _lib.call("iono_forwardprojector_quads_from_m_f64", fp.handle, _lib.ptr(m_tci.device_M()), w["K_ne"] / 1e13,
+              _lib.ptr(quads), _lib.stream_ptr())
     tec = fp.tec_quads(quads)
     g, S, coef, perm = residual(tec, dobs, C, 0, want_coef=True, want_perm=True)
+    _lib.call("iono_backprojector_ne_rows_f64", bp.handle, _lib.ptr(m_tci.device_M()), w["K_ne"] / 1e13, _lib.ptr(ne),
+              _lib.stream_ptr())
     acc = bp.apply_permuted(perm, scale=ne)
 if os.environ.get("SCATTER", "0") == "1":
     backproject(rays, m_tci.grid(), coef, tuple(ne.shape), check_bounds=False)
