@@ -302,6 +302,7 @@ int iono_multi_dot3_f64(const double *H, int64_t ld, int rows, int x_row0, int x
                         int64_t n, double *scratch, double *out, void *stream);
 int iono_lincomb_f64(const double *H, int64_t ld, int rows, const double *coef_dev, const double *x, int64_t n,
                      double *out, void *stream);
+int iono_zero_f64(double *x, int64_t n, void *stream);   /* x[0..n) = 0 (memset node, no kernel) */
 int iono_gather_f64(const double *src, const int *idx, int64_t n, double *out, void *stream);
 int iono_scatter_set_f64(const double *x, const int *idx, int64_t n, double *dst, void *stream);   /* dst[idx[i]] = x[i] */
 int iono_scatter_axpy_f64(const double *base, const double *alpha_dev, const double *x, const int *idx, int64_t n,

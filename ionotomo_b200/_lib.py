@@ -71,6 +71,7 @@ SIGNATURES = {
     "iono_multi_dot_f64": (_i, [_vp, _i64, _i, _vp, _vp, _i64, _vp, _vp, _vp]),
     "iono_multi_dot3_f64": (_i, [_vp, _i64, _i, _i, _i, _i, _vp, _i64, _vp, _vp, _vp]),
     "iono_lincomb_f64": (_i, [_vp, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
+    "iono_zero_f64": (_i, [_vp, _i64, _vp]),
     "iono_gather_f64": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "iono_scatter_set_f64": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "iono_scatter_axpy_f64": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),

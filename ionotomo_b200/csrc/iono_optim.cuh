@@ -247,3 +247,10 @@ extern "C" int iono_scatter_axpy_f64(const double *base, const double *alpha_dev
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
 }
+
+// x[0..n) = 0 (cudaMemsetAsync: a memset node in a captured graph, no kernel)
+extern "C" int iono_zero_f64(double *x, int64_t n, void *stream) {
+    if (n < 0 || (n > 0 && !x)) return fail(IONO_EBADARG, "iono_zero_f64: bad argument");
+    if (n > 0) CU_CHECK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), (cudaStream_t)stream));
+    return IONO_OK;
+}

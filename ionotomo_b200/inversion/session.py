@@ -151,7 +151,7 @@ class DeviceSession(object):
 
     def _enqueue_residual(self):
         if self.sharded:
-            self.acc_c.zero_()
+            _lib.call("iono_zero_f64", _lib.ptr(self.acc_c), self.acc_c.numel(), _lib.stream_ptr())
         residual(self.tec, self.dobs, self.CdCt, self.i0, want_coef=self.bp is None, want_perm=self.bp is not None,
                  out=dict(dtec=self.dtec, coef=self.coef, coef_perm=self.coef_perm, scratch=self.scratch,
                           S=self.S_local))
