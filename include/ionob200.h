@@ -97,6 +97,24 @@ int iono_ne_to_refractive_index_f64(const double *ne, int64_t nvox, double frequ
 int iono_optical_path_f64(iono_grid_t grid, const double *n_field, double *rays, int64_t nrays, int Ns,
                           unsigned long long *oob_count, void *stream);
 
+/* ---- true tricubic interpolation and bent rays (BASELINE config 5; the reference's notebooks only) ------
+ * notebooks/TricubicInterpolation.ipynb[cell 0]:138-299,1192-1257 + DeriveTricubic.ipynb[cell 0]:87-141: C1
+ * Lekien-Marsden interpolant from (f, fx, fy, fz, fxy, fxz, fyz, fxyz) at the 8 cell corners, derivatives by
+ * 4th-order central differences over the local spacing.  notebooks/FermatClass.ipynb[cell 0]:60-96: rays bent by
+ * grad n, independent variable z: dp/dz = grad(n) n/pz, dx/dz = px/pz, dy/dz = py/pz, ds/dz = n/pz.
+ * derivs: 8 grids of nx*ny*nz doubles in that order (iono_tricubic_derivs_f64 builds them once per field);
+ * iono_tricubic_interp_f64: out[p] = f(x,y,z), grad_out (n,3) optional, *oob_count = points outside the grid;
+ * iono_bent_rays_f64: classical RK4, `substeps` steps per sample interval, derivs of the REFRACTIVE INDEX
+ * (iono_ne_to_refractive_index_f64); rays_out (nrays,4,Ns) rows x,y,z,s at z = linspace(z0, tmax, Ns);
+ * *oob_count = rays that left the grid. */
+int iono_tricubic_derivs_f64(iono_grid_t grid, const double *f, double *derivs, void *stream);
+int iono_tricubic_interp_f64(iono_grid_t grid, const double *derivs, const double *x, const double *y,
+                             const double *z, int64_t n, double *out, double *grad_out,
+                             unsigned long long *oob_count, void *stream);
+int iono_bent_rays_f64(iono_grid_t grid, const double *derivs, const double *origins, const double *directions,
+                       int64_t nrays, double tmax, int Ns, int substeps, double *rays_out,
+                       unsigned long long *oob_count, void *stream);
+
 /* ---- point-wise interpolation -------------------------------------------
  * TriCubic.interp / .extrapolate (geometry/tri_cubic.py:69-75) == SciPy
  * RegularGridInterpolator(method='linear').  M: (nx,ny,nz).  oob_count (device,

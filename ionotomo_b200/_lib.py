@@ -35,6 +35,9 @@ SIGNATURES = {
     "iono_cast_rays_frames_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _d, _i, _vp, _vp]),
     "iono_ne_to_refractive_index_f64": (_i, [_vp, _i64, _d, _vp, _vp]),
     "iono_optical_path_f64": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "iono_tricubic_derivs_f64": (_i, [_vp, _vp, _vp, _vp]),
+    "iono_tricubic_interp_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "iono_bent_rays_f64": (_i, [_vp, _vp, _vp, _vp, _i64, _d, _i, _i, _vp, _vp, _vp]),
     "iono_tci_interp_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "iono_tec_forward_f64": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "iono_quads_from_ne_f64": (_i, [_vp, _i, _i, _i, _vp, _vp]),
@@ -94,7 +97,7 @@ SIGNATURES = {
 KERNEL_LAUNCHES = {
     "iono_ne_from_m_f64": 1, "iono_mul_f64": 1, "iono_cast_rays_straight_f64": 1,
     "iono_cast_rays_frames_f64": 1, "iono_cast_rays_arclength_f64": 1, "iono_ne_to_refractive_index_f64": 1, "iono_optical_path_f64": 1,
-    "iono_tci_interp_f64": 1, "iono_tec_forward_f64": 1, "iono_dtec_f64": 1, "iono_adjoint_coef_f64": 1,
+    "iono_tci_interp_f64": 1, "iono_tricubic_derivs_f64": 7, "iono_tricubic_interp_f64": 1, "iono_bent_rays_f64": 1, "iono_tec_forward_f64": 1, "iono_dtec_f64": 1, "iono_adjoint_coef_f64": 1,
     "iono_tec_adjoint_f64": 1, "iono_misfit_f64": 2, "iono_convolve3d_nearest_f64": 1,
     "iono_phase_integrals_f64": 1, "iono_simps_rows_f64": 1, "iono_phase_assemble_f64": 1, "iono_chord_adjoint_f64": 1,
     "iono_gaussian_adjoint_f64": 1,

@@ -472,6 +472,7 @@ extern "C" int iono_tci_interp_f64(iono_grid_t grid, const double *M, const doub
 #include "iono_optical.cuh"
 #include "iono_peer.cuh"
 #include "iono_optim.cuh"
+#include "iono_tricubic.cuh"
 
 // ---------------------------------------------------------------------------
 // small per-ray kernels

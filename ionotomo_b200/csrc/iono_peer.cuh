@@ -62,7 +62,7 @@ __device__ __forceinline__ void wait_all_ranks(const unsigned long long *my_flag
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) peer_reduce_expand_kernel(PeerTable T, int N, int me, long long L,
+__global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T, int N, int me, long long L,
                                                                   const int *__restrict__ voxel, long long n_union,
                                                                   const double *__restrict__ m, double k,
                                                                   double *__restrict__ grad,
@@ -84,25 +84,18 @@ __global__ void __launch_bounds__(256) peer_reduce_expand_kernel(PeerTable T, in
     const long long pairs = L / 2;
     const long long p0 = pairs * me / N, p1 = pairs * (me + 1) / N;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += 2 * stride) {
-        const bool two = p + stride < p1;
-        double2 v[IONO_MAX_PEERS], u[IONO_MAX_PEERS];
+    for (long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += stride) {
+        double2 s = make_double2(0.0, 0.0);
+        for (int r0 = 0; r0 < N; r0 += 8) {          // 8 peer loads in flight per thread, summed in rank order
+            double2 v[8];
 #pragma unroll
-        for (int r = 0; r < IONO_MAX_PEERS; ++r)     // all loads of both elements first: 2N requests in flight per thread
-            if (r < N) {
-                v[r] = ld_peer_v2(T.acc[r] + 2 * p);
-                u[r] = two ? ld_peer_v2(T.acc[r] + 2 * (p + stride)) : make_double2(0.0, 0.0);
-            }
-        double2 s = make_double2(0.0, 0.0), w = make_double2(0.0, 0.0);
+            for (int r = 0; r < 8; ++r)
+                if (r0 + r < N) v[r] = ld_peer_v2(T.acc[r0 + r] + 2 * p);
 #pragma unroll
-        for (int r = 0; r < IONO_MAX_PEERS; ++r)     // rank order: the same bits on every rank
-            if (r < N) { s.x += v[r].x; s.y += v[r].y; w.x += u[r].x; w.y += u[r].y; }
-#pragma unroll
-        for (int r = 0; r < IONO_MAX_PEERS; ++r)
-            if (r < N) {
-                *reinterpret_cast<double2 *>(T.res[r] + 2 * p) = s;
-                if (two) *reinterpret_cast<double2 *>(T.res[r] + 2 * (p + stride)) = w;
-            }
+            for (int r = 0; r < 8; ++r)
+                if (r0 + r < N) { s.x += v[r].x; s.y += v[r].y; }
+        }
+        for (int r = 0; r < N; ++r) *reinterpret_cast<double2 *>(T.res[r] + 2 * p) = s;
     }
     // every CTA's peer stores must be out before the slice is announced: the CTA barrier orders the threads'
     // stores before thread 0's system-scope fence (cumulative), the last CTA to arrive signals
@@ -188,10 +181,13 @@ extern "C" int iono_peer_reduce_expand_f64(void *const *acc, void *const *res, v
         T.res[r] = (double *)res[r];
         T.flags[r] = (unsigned long long *)flags[r];
     }
-    // all CTAs spin on flags: the grid must be co-resident -- one CTA per SM is
-    int ctas = sm_count();
+    // all CTAs spin on flags: the grid must be co-resident -- one CTA per SM is.  1024 threads per CTA: the loops are
+    // chains of dependent long-latency accesses (peer loads; voxel index -> model gather -> scattered store), so the
+    // kernel's time is latency / (threads in flight)
+    int ctas = sm_count(), threads = 1024;
     if (const char *e = getenv("IONO_PEER_CTAS")) { int v = atoi(e); if (v >= 1 && v <= ctas) ctas = v; }
-    peer_reduce_expand_kernel<<<ctas, 256, 0, (cudaStream_t)stream>>>(T, N, me, (long long)L, union_voxels, (long long)n_union, m, k, grad,
+    if (const char *e = getenv("IONO_PEER_THREADS")) { int v = atoi(e); if (v >= 32 && v <= 1024 && v % 32 == 0) threads = v; }
+    peer_reduce_expand_kernel<<<ctas, threads, 0, (cudaStream_t)stream>>>(T, N, me, (long long)L, union_voxels, (long long)n_union, m, k, grad,
                                                                      misfit_out);
     CU_CHECK(cudaGetLastError());
     return IONO_OK;

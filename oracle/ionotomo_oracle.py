@@ -744,3 +744,115 @@ def turbulent_realization(xvec, yvec, zvec, sigma, corr, seed):
     B[:, :, ::2] *= -1
     B *= sigma / np.std(B)
     return B
+
+
+# --------------------------------------------------------------------------
+# true tricubic interpolation and bent rays (notebook specs only):
+# notebooks/TricubicInterpolation.ipynb[cell 0]:138-299,1192-1257, notebooks/DeriveTricubic.ipynb[cell 0]:87-141,
+# notebooks/FermatClass.ipynb[cell 0]:60-96.  No reference numbers exist for these; tests validate this
+# restatement against exact tricubic polynomials and against scipy.integrate.odeint.
+# --------------------------------------------------------------------------
+def _diff_axis(f, g, axis):
+    """d f / d axis at the nodes: 4th-order central (8(f[i+1]-f[i-1]) - (f[i+2]-f[i-2]))/12 over the local spacing
+    (g[i+1]-g[i-1])/2 (DeriveTricubic.ipynb[cell 0]:87-107,124-141); 2nd-order central one node from a face and
+    one-sided on the face (extension: the notebook asserts 2 <= i <= n-3)."""
+    f = np.moveaxis(np.asarray(f, dtype=np.float64), axis, 0)
+    g = np.asarray(g, dtype=np.float64)
+    n = g.size
+    d = np.empty_like(f)
+    sh = (slice(None),) + (None,) * (f.ndim - 1)
+    if n >= 5:
+        h = 0.5 * (g[3:n - 1] - g[1:n - 3])
+        d[2:n - 2] = (8.0 * (f[3:n - 1] - f[1:n - 3]) - (f[4:n] - f[0:n - 4])) / 12.0 / h[sh]
+    for i in ([1, n - 2] if n >= 3 else []):
+        if 1 <= i <= n - 2 and not (2 <= i <= n - 3):
+            d[i] = (f[i + 1] - f[i - 1]) / (g[i + 1] - g[i - 1])
+    d[0] = (f[1] - f[0]) / (g[1] - g[0])
+    d[n - 1] = (f[n - 1] - f[n - 2]) / (g[n - 1] - g[n - 2])
+    return np.moveaxis(d, 0, axis)
+
+
+def tricubic_derivs(xvec, yvec, zvec, f):
+    """The 8 grids (f, fx, fy, fz, fxy, fxz, fyz, fxyz) the tricubic interpolant is built from."""
+    f = np.asarray(f, dtype=np.float64)
+    fx, fy, fz = _diff_axis(f, xvec, 0), _diff_axis(f, yvec, 1), _diff_axis(f, zvec, 2)
+    fxy, fxz, fyz = _diff_axis(fx, yvec, 1), _diff_axis(fx, zvec, 2), _diff_axis(fy, zvec, 2)
+    return np.stack([f, fx, fy, fz, fxy, fxz, fyz, _diff_axis(fxy, zvec, 2)])
+
+
+def _hermite(t):
+    t2, t3 = t * t, t * t * t
+    h = np.stack([2 * t3 - 3 * t2 + 1, -2 * t3 + 3 * t2, t3 - 2 * t2 + t, t3 - t2])
+    dh = np.stack([6 * t2 - 6 * t, -6 * t2 + 6 * t, 3 * t2 - 4 * t + 1, 3 * t2 - 2 * t])
+    return h, dh
+
+
+def tricubic_interp(xvec, yvec, zvec, derivs, x, y, z, grad=False):
+    """C1 tricubic (Lekien-Marsden) interpolant: the tensor product of cubic Hermite bases matching
+    (f, fx, fy, fz, fxy, fxz, fyz, fxyz) at the 8 corners of the cell -- the polynomial the notebook's 64x64 matrix
+    yields (TricubicInterpolation.ipynb[cell 0]:286-299,1192-1257), with derivatives scaled by the cell size."""
+    x, y, z = (np.asarray(v, dtype=np.float64) for v in (x, y, z))
+    shape = x.shape
+    x, y, z = x.ravel(), y.ravel(), z.ravel()
+    idx, ts, hs = [], [], []
+    for g, p in ((xvec, x), (yvec, y), (zvec, z)):
+        g = np.asarray(g, dtype=np.float64)
+        i, t = find_indices(g, p)
+        idx.append(i)
+        hs.append(g[i + 1] - g[i])
+        ts.append(t)
+    (bu, du), (bv, dv), (bw, dw) = _hermite(ts[0]), _hermite(ts[1]), _hermite(ts[2])
+    which = {(0, 0, 0): 0, (1, 0, 0): 1, (0, 1, 0): 2, (0, 0, 1): 3, (1, 1, 0): 4, (1, 0, 1): 5, (0, 1, 1): 6, (1, 1, 1): 7}
+    f = np.zeros_like(x)
+    fx, fy, fz = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
+    for i in (0, 1):
+        for j in (0, 1):
+            for k in (0, 1):
+                for a in (0, 1):
+                    for b in (0, 1):
+                        for c in (0, 1):
+                            val = derivs[which[(a, b, c)]][idx[0] + i, idx[1] + j, idx[2] + k]
+                            val = val * (hs[0] if a else 1.) * (hs[1] if b else 1.) * (hs[2] if c else 1.)
+                            Bx, By, Bz = bu[2 * a + i], bv[2 * b + j], bw[2 * c + k]
+                            f += val * Bx * By * Bz
+                            fx += val * du[2 * a + i] * By * Bz
+                            fy += val * Bx * dv[2 * b + j] * Bz
+                            fz += val * Bx * By * dw[2 * c + k]
+    if grad:
+        return f.reshape(shape), np.stack([fx / hs[0], fy / hs[1], fz / hs[2]], -1).reshape(shape + (3,))
+    return f.reshape(shape)
+
+
+def bent_ray_rhs(xvec, yvec, zvec, derivs_n, state, z):
+    """FermatClass.ipynb[cell 0]:60-96, type 'z': d[px,py,pz,x,y,s]/dz."""
+    px, py, pz, x, y, s = state
+    n, g = tricubic_interp(xvec, yvec, zvec, derivs_n, np.array([x]), np.array([y]), np.array([z]), grad=True)
+    n, g = float(n[0]), g[0]
+    return np.array([g[0] * n / pz, g[1] * n / pz, g[2] * n / pz, px / pz, py / pz, n / pz])
+
+
+def bent_ray_rk4(xvec, yvec, zvec, derivs_n, origin, direction, tmax, N, substeps=4):
+    """Classical RK4 in z with ``substeps`` steps per sample interval; returns x, y, z, s at
+    ``z = linspace(z0, tmax, N)`` (the layout of Fermat.integrate_ray)."""
+    o = np.asarray(origin, dtype=np.float64)
+    d = np.asarray(direction, dtype=np.float64)
+    p = d / np.sqrt(d[0] ** 2 + d[1] ** 2 + d[2] ** 2)
+    q = np.array([p[0], p[1], p[2], o[0], o[1], 0.0])
+    zs = np.linspace(o[2], tmax, N)
+    dzs = (tmax - o[2]) / (N - 1) if N > 1 else 0.0
+    out = np.zeros((4, N))
+    for i in range(N):
+        zi = tmax if (i == N - 1 and N > 1) else o[2] + i * dzs
+        out[:, i] = q[3], q[4], zi, q[5]
+        if i == N - 1:
+            break
+        h = dzs / substeps
+        for k in range(substeps):
+            zz = zi + k * h
+            k1 = bent_ray_rhs(xvec, yvec, zvec, derivs_n, q, zz)
+            k2 = bent_ray_rhs(xvec, yvec, zvec, derivs_n, q + 0.5 * h * k1, zz + 0.5 * h)
+            k3 = bent_ray_rhs(xvec, yvec, zvec, derivs_n, q + 0.5 * h * k2, zz + 0.5 * h)
+            k4 = bent_ray_rhs(xvec, yvec, zvec, derivs_n, q + h * k3, zz + h)
+            q = q + h / 6.0 * (k1 + 2 * k2 + 2 * k3 + k4)
+    assert np.allclose(out[2], zs)
+    return out

@@ -315,3 +315,50 @@ def test_fermat_arclength_golden(golden):
     for idx in np.ndindex(*o.shape[:3]):
         x, y, z, s = O.integrate_ray_arclength(o[idx], d[idx], float(g["tmax"]), int(g["Ns"]))
         np.testing.assert_allclose(np.stack([x, y, z, s]), g["rays"][idx], rtol=0, atol=1e-9)
+
+
+def test_tricubic_oracle_reproduces_tricubic_polynomials_and_is_c1():
+    """The 4th-order differences are exact for cubics, so the Hermite data are exact and the interpolant must
+    reproduce any polynomial of degree <= 3 per variable (uniform axes, away from the faces); across a cell face
+    value and gradient are continuous."""
+    xv, yv, zv = np.linspace(-3, 4, 12), np.linspace(0, 5, 11), np.linspace(1, 9, 13)
+    X, Y, Z = np.meshgrid(xv, yv, zv, indexing="ij")
+
+    def poly(x, y, z):
+        return (1 + 0.3 * x - 0.2 * x ** 2 + 0.05 * x ** 3) * (2 - 0.1 * y + 0.03 * y ** 3) * \
+            (0.5 + 0.2 * z - 0.01 * z ** 2 + 0.002 * z ** 3)
+    D = O.tricubic_derivs(xv, yv, zv, poly(X, Y, Z))
+    rng = np.random.RandomState(0)
+    px, py, pz = rng.uniform(xv[2], xv[-3], 300), rng.uniform(yv[2], yv[-3], 300), rng.uniform(zv[2], zv[-3], 300)
+    f, g = O.tricubic_interp(xv, yv, zv, D, px, py, pz, grad=True)
+    np.testing.assert_allclose(f, poly(px, py, pz), rtol=1e-13)
+    eps = 1e-6
+    np.testing.assert_allclose(g[:, 1], (poly(px, py + eps, pz) - poly(px, py - eps, pz)) / (2 * eps), rtol=1e-7, atol=1e-7)
+    # C1 across a face, for a non-polynomial field
+    D2 = O.tricubic_derivs(xv, yv, zv, np.sin(X) * np.cos(0.7 * Y) + 0.1 * Z ** 2)
+    x0 = xv[5]
+    fl, gl = O.tricubic_interp(xv, yv, zv, D2, np.array([x0 - 1e-9]), np.array([2.2]), np.array([4.4]), grad=True)
+    fr, gr = O.tricubic_interp(xv, yv, zv, D2, np.array([x0 + 1e-9]), np.array([2.2]), np.array([4.4]), grad=True)
+    assert abs(fl - fr) < 1e-8 and np.abs(gl - gr).max() < 1e-7
+
+
+def test_bent_ray_oracle_against_odeint():
+    """RK4 restatement of the notebook's ray equations (FermatClass.ipynb[cell 0]:60-96) against SciPy's odeint (what
+    the notebook calls), and sanity: n = 1 gives the straight ray of Fermat.integrate_ray."""
+    from scipy.integrate import odeint
+    xv, yv, zv = np.linspace(-3, 4, 12), np.linspace(0, 5, 11), np.linspace(1, 9, 13)
+    X, Y, Z = np.meshgrid(xv, yv, zv, indexing="ij")
+    ne = 1e12 * np.exp(-((Z - 5) / 2.) ** 2) * (1 + 0.3 * np.sin(X))
+    Dn = O.tricubic_derivs(xv, yv, zv, O.ne2n(ne, 30e6))
+    o, d = np.array([0.2, 2.4, 1.5]), np.array([0.05, -0.02, 1.0])
+    r = O.bent_ray_rk4(xv, yv, zv, Dn, o, d, 8.5, 12, substeps=8)
+    p = d / np.linalg.norm(d)
+    Yo = odeint(lambda q, z: O.bent_ray_rhs(xv, yv, zv, Dn, q, z), [p[0], p[1], p[2], o[0], o[1], 0.0],
+                np.linspace(o[2], 8.5, 12), rtol=1e-11, atol=1e-12)
+    assert np.abs(r[0] - Yo[:, 3]).max() < 1e-6 and np.abs(r[1] - Yo[:, 4]).max() < 1e-6
+    assert np.abs(r[3] - Yo[:, 5]).max() < 1e-5
+    assert np.abs(r[0] - (o[0] + p[0] / p[2] * (r[2] - o[2]))).max() > 0.05        # the ray really bends
+    D1 = O.tricubic_derivs(xv, yv, zv, np.ones_like(ne))
+    s = O.bent_ray_rk4(xv, yv, zv, D1, o, d, 8.5, 12, substeps=1)
+    x, y, z, sl = O.integrate_ray_straight(o, d, 8.5, 12)
+    np.testing.assert_allclose(s, np.stack([x, y, z, sl]), rtol=0, atol=1e-12)
