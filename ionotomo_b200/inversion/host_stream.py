@@ -175,7 +175,7 @@ class HostSession(object):
     """
 
     def __init__(self, rays, K_ne, m_tci, i0, dobs, CdCt, origins=None, directions=None, tmax=1000., Ns=None,
-                 active_only=False, root=0, **session_kw):
+                 active_only=False, root=0, overlap_copies=True, **session_kw):
         import ctypes
         import torch.distributed as dist
         from ..geometry.calc_rays import cast_ray
@@ -219,6 +219,16 @@ class HostSession(object):
             self.grad_host = torch.empty(s.shape, dtype=torch.float64, pin_memory=True)
         self.dtec_host = torch.empty(s.ray_shape, dtype=torch.float64, pin_memory=True)
         self.S_host = torch.empty(1, dtype=torch.float64, pin_memory=True)
+        # one GPU: copies overlapped with the kernels (see _pipelined_step)
+        self.overlap_copies = bool(overlap_copies)
+        self.n_pieces = 4
+        self._side = torch.cuda.Stream()
+        self._grad_full_host = self.grad_host
+        if self.active_only and not s.sharded and s.bp is not None:
+            # active voxels whose gradient is final after each piece of the operator
+            bounds = [0] + [s.bp.chunk_voxels(c) for c in range(16 // self.n_pieces, 16, 16 // self.n_pieces)] + \
+                [s.grad.numel()]
+            self._act_bounds = np.searchsorted(self.active_voxels, np.array(bounds), side="left")
         self.h2d_bytes_per_call = self.m_host.numel() * 8 if self.is_root else 0
         self.d2h_bytes_per_call = (self.dtec_host.numel() + (self.grad_host.numel() + 1 if self.is_root else 0)) * 8
 
@@ -247,6 +257,8 @@ class HostSession(object):
         import ctypes
         s = self.session
         self._upload(m)
+        if self.overlap_copies and not s.sharded and s.bp is not None:
+            return self._pipelined_step()
         s.misfit_and_gradient(None)
         self.dtec_host.copy_(s.dtec, non_blocking=True)
         if self.is_root:
@@ -259,6 +271,51 @@ class HostSession(object):
         self.S_host.copy_(s.S, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.dtec_host.numpy(), float(self.S_host[0]), (self.grad_host.numpy() if self.is_root else None)
+
+    def _pipelined_step(self):
+        """One GPU, binned adjoint: the device -> host copies ride behind the kernels.  dTEC and the misfit leave
+        on a side stream while the back-projection runs; the operator is applied in ``self.n_pieces`` pieces of
+        its voxel-sorted entry stream (``iono_backprojector_apply_*`` chunks) and every finished voxel range of
+        the gradient is copied out while the next piece is computed.  Same numbers as the one-shot step."""
+        import ctypes
+        s = self.session
+        main = torch.cuda.current_stream()
+        side = self._side
+        s.forward(None)                                  # quad records, forward, dTEC + misfit + coefficients (graph)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ev)
+            self.dtec_host.copy_(s.dtec, non_blocking=True)
+            self.S_host.copy_(s.S, non_blocking=True)
+        s.n_gradient += 1
+        if s.use_quads:
+            _lib.call("iono_backprojector_ne_rows_f64", s.bp.handle, _lib.ptr(s.m), s.K_ne / 1e13, _lib.ptr(s.ne_rows),
+                      _lib.stream_ptr())
+        V = s.grad.numel()
+        flat_d, flat_h = s.grad.view(-1), self._grad_full_host.view(-1)
+        step = 16 // self.n_pieces
+        done = 0
+        for c0 in range(0, 16, step):
+            s.bp.apply_permuted(s.coef_perm, scale=s.ne_rows, out=s.grad, c0=c0, c1=c0 + step)
+            upto = V if c0 + step == 16 else s.bp.chunk_voxels(c0 + step)
+            if upto > done:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    if self.active_only:
+                        a, b = int(self._act_bounds[c0 // step]), int(self._act_bounds[c0 // step + 1])
+                        if b > a:
+                            _lib.call("iono_gather_f64", _lib.ptr(s.grad), ctypes.c_void_p(self._idx[a:b].data_ptr()),
+                                      b - a, _lib.ptr(self._g_act[a:b]), ctypes.c_void_p(side.cuda_stream))
+                            self.grad_host[a:b].copy_(self._g_act[a:b], non_blocking=True)
+                    else:
+                        flat_h[done:upto].copy_(flat_d[done:upto], non_blocking=True)
+                done = upto
+        side.synchronize()
+        main.synchronize()
+        return self.dtec_host.numpy(), float(self.S_host[0]), self.grad_host.numpy()
 
     def forward(self, m=None):
         """``(dtec, S)`` only (line searches)."""
