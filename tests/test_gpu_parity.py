@@ -1084,3 +1084,18 @@ def test_tricubic_interpolation_and_bent_rays(ib):
     # n == 1 (ne = 0): the straight rays of cast_ray
     straight = bent_rays(ib.TriCubic(xv, yv, zv, np.zeros_like(ne)), o, d, 1000., 25, frequency=15e6, substeps=1)
     np.testing.assert_allclose(straight, O.cast_ray(o, d, 1000., 25), rtol=0, atol=1e-9)
+
+
+def test_get_ray_dirac_callable(ib, golden):
+    """geometry/ray_dirac.py:5-34 as a callable (toy sizes): dense chord lengths per ray, against the dense array the
+    reference's own get_ray_dirac produced (tests/golden/chord.npz['dirac'])."""
+    from ionotomo_b200.geometry.ray_dirac import get_ray_dirac
+    g = golden("chord")
+    tci = ib.TriCubic(g["xvec"], g["yvec"], g["zvec"], g["ne"])
+    rays = g["rays"][:, 0]                     # (N1, N2, 4, Ns) chunk, as the reference passes it
+    dirac, mid = get_ray_dirac(rays, tci)
+    assert mid is None and dirac.shape == g["dirac"].shape
+    np.testing.assert_allclose(dirac, g["dirac"], rtol=0, atol=1e-11 * g["dirac"].max())
+    # the contraction of inversion/gradient.py:19 gives the reference's gradient
+    G = np.einsum("ijklm,klm,ij->klm", dirac, g["ne"], g["dd"])
+    np.testing.assert_allclose(G, g["G"], rtol=0, atol=1e-11 * np.abs(g["G"]).max())
