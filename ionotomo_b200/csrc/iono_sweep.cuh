@@ -565,6 +565,9 @@ extern "C" int iono_tec_forward_f64(iono_grid_t grid, const double *ne, const do
                               "iono_tec_forward_f64");
 }
 
+static int launch_adjoint_runs(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns, const double *coef,
+                               double *acc, unsigned long long *oob_count, cudaStream_t st);
+
 extern "C" int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
                                     const double *coef, int order, int zero_first, double *acc,
                                     unsigned long long *oob_count, void *stream) {
@@ -577,6 +580,10 @@ extern "C" int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na
     if (zero_first)
         CU_CHECK(cudaMemsetAsync(acc, 0, (size_t)grid->nx * grid->ny * grid->nz * sizeof(double), st));
     if (R == 0 || Ns < 2) return IONO_OK;
+    if (device_check(grid->device, "iono_tec_adjoint_f64")) return IONO_EBADARG;
+    // time-bundled scatter with run aggregation (iono_adjoint_runs.cuh) whenever there is a time axis to walk
+    const int rc = launch_adjoint_runs(grid, rays, Na, Nt, Nd, Ns, coef, acc, oob_count, st);
+    if (rc != -1) return rc;
     SweepParams p;
     memset(&p, 0, sizeof(p));
     p.g = grid->dev; p.acc = acc; p.rays = rays; p.coef = coef; p.oob_count = oob_count;

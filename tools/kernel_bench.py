@@ -134,9 +134,19 @@ def main():
         del bp
     os.environ.pop("IONO_BP_RUNS", None)
     if "scatter" not in skip:
-        out["scatter_adjoint"] = timeit(lambda: backproject(rays, grid, coef, (nx, ny, nz), check_bounds=False, out=acc),
-                                        max(3, args.reps // 4))
-        out["scatter_vs_binned_relerr"] = float(((acc * ne - ref).abs().max() / ref.abs().max()).item())
+        os.environ["IONO_ADJOINT_RUNS"] = "0"
+        out["scatter_adjoint_plain"] = timeit(lambda: backproject(rays, grid, coef, (nx, ny, nz), check_bounds=False, out=acc),
+                                              max(3, args.reps // 4))
+        plain = acc.clone()
+        del os.environ["IONO_ADJOINT_RUNS"]
+        for wv in ("16", "12", "8"):
+            os.environ["IONO_ADJOINT_RUNS_WARPS"] = wv
+            out["scatter_adjoint_runs_w" + wv] = timeit(lambda: backproject(rays, grid, coef, (nx, ny, nz), check_bounds=False,
+                                                                            out=acc), max(3, args.reps // 2))
+        del os.environ["IONO_ADJOINT_RUNS_WARPS"]
+        out["scatter_runs_vs_plain_relerr"] = float(((acc - plain).abs().max() / plain.abs().max()).item())
+        if "runs1" not in skip:
+            out["scatter_vs_binned_relerr"] = float(((acc * ne - ref).abs().max() / ref.abs().max()).item())
     if "session" not in skip:
         del fp
         for graph in (True, False):
@@ -150,7 +160,7 @@ def main():
         if isinstance(out[k], dict) and "ms" in out[k]:
             if k.startswith(("sweep", "prepared")):
                 out[k]["frac"] = bf / out[k]["ms"] / 1e6 / hbm
-            elif k.startswith(("apply", "scatter")):
+            elif k.startswith(("apply", "scatter_adjoint")):
                 out[k]["frac"] = ba / out[k]["ms"] / 1e6 / hbm
             elif k.startswith("session"):
                 out[k]["frac"] = (bf + ba) / out[k]["ms"] / 1e6 / hbm
