@@ -29,8 +29,8 @@ struct AdjRunsParams {
     int Na, Nt, Nd, Ns;
 };
 
-template <int AXK, bool BULK>
-__global__ void __launch_bounds__(512, 1) adjoint_runs_kernel(const AdjRunsParams p) {
+template <int AXK, bool BULK, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) adjoint_runs_kernel(const AdjRunsParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int nx = p.g.ax[0].n, ny = p.g.ax[1].n, nz = p.g.ax[2].n;
@@ -179,13 +179,20 @@ __global__ void __launch_bounds__(512, 1) adjoint_runs_kernel(const AdjRunsParam
     if (n_oob) atomicAdd(p.oob_count, (unsigned long long)n_oob);
 }
 
-template <int AXK, bool BULK>
-static int launch_adjoint_runs_t(const AdjRunsParams &p, int warps, size_t smem, int ctas, cudaStream_t st) {
-    auto kern = adjoint_runs_kernel<AXK, BULK>;
+template <int AXK, bool BULK, int MAXT>
+static int launch_adjoint_runs_m(const AdjRunsParams &p, int warps, size_t smem, int ctas, cudaStream_t st) {
+    auto kern = adjoint_runs_kernel<AXK, BULK, MAXT>;
     CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctas, warps * 32, smem, st>>>(p);
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
+}
+template <int AXK, bool BULK>
+static int launch_adjoint_runs_t(const AdjRunsParams &p, int warps, size_t smem, int ctas, cudaStream_t st) {
+    // the kernel waits on its row stream and its reductions: more warps per SM win (2.15 ms with 16, 3.45 ms with 8 at
+    // the LOFAR case); beyond 16 warps the register budget is 80 per thread
+    if (warps > 16) return launch_adjoint_runs_m<AXK, BULK, 768>(p, warps, smem, ctas, st);
+    return launch_adjoint_runs_m<AXK, BULK, 512>(p, warps, smem, ctas, st);
 }
 
 // returns IONO_OK, an error, or -1 for "not applicable, use the plain scatter kernel"
@@ -198,8 +205,8 @@ static int launch_adjoint_runs(iono_grid_t grid, const double *rays, int Na, int
     const int axk = grid->exact ? 2 : (grid->uniform ? 1 : 0);
     const size_t table_bytes =
         (axk == 2) ? 0 : (((size_t)(grid->nx + grid->ny + grid->nz) * sizeof(double2)) + 127) / 128 * 128;
-    int warps = 16;
-    if (const char *e = getenv("IONO_ADJOINT_RUNS_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 16) warps = v; }
+    int warps = 24;
+    if (const char *e = getenv("IONO_ADJOINT_RUNS_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 24) warps = v; }
     auto smem_for = [&](int w) {
         return table_bytes + (((size_t)w * AR_STAGES * sizeof(uint64_t)) + 127) / 128 * 128 +
                (size_t)w * AR_STAGES * StageLayout<AR_C>::BYTES + (size_t)w * AR_QCAP * (8 * 8 + 4);

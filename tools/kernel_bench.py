@@ -139,7 +139,7 @@ def main():
                                               max(3, args.reps // 4))
         plain = acc.clone()
         del os.environ["IONO_ADJOINT_RUNS"]
-        for wv in ("16", "12", "8"):
+        for wv in ("16", "20", "24"):
             os.environ["IONO_ADJOINT_RUNS_WARPS"] = wv
             out["scatter_adjoint_runs_w" + wv] = timeit(lambda: backproject(rays, grid, coef, (nx, ny, nz), check_bounds=False,
                                                                             out=acc), max(3, args.reps // 2))
