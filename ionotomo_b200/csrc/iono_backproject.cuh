@@ -524,9 +524,7 @@ __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__re
 }
 
 // ---------------------------------------------------------------------------------------------
-// Blocked apply (the default): the segment stream is cut into blocks of `segs_per_block` CONTIGUOUS segments, dealt
-// round-robin to the warps (a first version gave every warp ONE contiguous range: the cost per segment varies with the
-// number of rows in it, the slowest warp ran 2x longer than the average and the kernel took 2.6 ms instead of 1.5).
+// Blocked apply (the default): every warp owns a CONTIGUOUS block of segments instead of every W-th one.
 // Three quarters of the entries lie in rows longer than four segments, so most segments are interior to one row:
 // with a contiguous block the warp keeps that row's products as per-lane partial sums in a register ("carry") across
 // segments and reduces over the lanes once, when the row ends -- no shuffle tree, no partial sum and no combine
@@ -544,29 +542,33 @@ struct BlockPartials {
 enum { BLK_NONE = 0, BLK_CLOSED = 1, BLK_WHOLE = 2, BLK_EMPTY = 3, BLK_OPEN = 1 };
 
 __global__ void __launch_bounds__(256, 4) backproject_blocked_kernel(const int2 *__restrict__ seg_rows,
-                                                                      const long long *__restrict__ ptr,
-                                                                      const unsigned int *__restrict__ row_voxel,
-                                                                      const unsigned char *__restrict__ runs,
-                                                                      const unsigned long long *__restrict__ run_ptr,
-                                                                      const double *__restrict__ weight,
-                                                                      const double *__restrict__ coef,
-                                                                      const RowScale scale, long long nnz,
-                                                                      long long seg_begin, long long seg_end,
-                                                                      int segs_per_block, long long n_blocks,
-                                                                      BlockPartials P, double *__restrict__ out) {
+                                                                   const long long *__restrict__ ptr,
+                                                                   const unsigned int *__restrict__ row_voxel,
+                                                                   const unsigned char *__restrict__ runs,
+                                                                   const unsigned long long *__restrict__ run_ptr,
+                                                                   const double *__restrict__ weight,
+                                                                   const double *__restrict__ coef,
+                                                                   const RowScale scale, long long nnz,
+                                                                   long long seg_begin, long long seg_end,
+                                                                   long long segs_per_block, BlockPartials P,
+                                                                   double *__restrict__ out) {
     extern __shared__ __align__(128) unsigned char bp_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     constexpr int STAGE = BP_WSEG * 8 + BP_RUNREC_MAX;         // weights then the run record
     unsigned char *mine = bp_smem + (size_t)warp * (2 * STAGE);
     uint64_t *bar = reinterpret_cast<uint64_t *>(bp_smem + (size_t)nwarp * 2 * STAGE) + warp * 2;
-    const long long wg = (long long)blockIdx.x * nwarp + warp, wtot = (long long)gridDim.x * nwarp;
+    const long long wg = (long long)blockIdx.x * nwarp + warp;
+    const long long lo = seg_begin + wg * segs_per_block;
+    const long long hi = min(lo + segs_per_block, seg_end);
     if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncwarp();
-    if (wg >= n_blocks) return;
+    if (lo >= hi) {
+        if (lane == 0) { P.head_state[wg] = BLK_EMPTY; P.tail_state[wg] = BLK_NONE; }
+        return;
+    }
     const uint64_t pol = policy_evict_first();
     const unsigned full = 0xffffffffu;
-    const long long S = segs_per_block;
     auto issue = [&](long long seg, int buf, unsigned long long u0, unsigned long long u1) {
         if (lane == 0) {
             const unsigned int rec_bytes = (unsigned int)(u1 - u0) * 16u;
@@ -580,27 +582,14 @@ __global__ void __launch_bounds__(256, 4) backproject_blocked_kernel(const int2 
         if (lane <= min(n, 31)) p = __ldg(ptr + first + lane);
         if (lane < min(n, 31)) vox = __ldg(row_voxel + first + lane);
     };
-    // the segment after `seg` in this warp's sequence: the next one of its block, else the first one of the warp's
-    // next block (blocks are dealt round-robin: blk, blk + wtot, ...); -1 when the warp is done
-    auto successor = [&](long long seg, long long blk, long long &seg2, long long &blk2) {
-        seg2 = seg + 1;
-        blk2 = blk;
-        if (seg2 >= min(seg_begin + (blk + 1) * S, seg_end)) {
-            blk2 = blk + wtot;
-            seg2 = (blk2 < n_blocks) ? seg_begin + blk2 * S : -1;
-        }
-    };
-    long long seg = seg_begin + wg * S, blk = wg;
-    long long seg1, blk1;
-    successor(seg, blk, seg1, blk1);
-    int2 rr = __ldg(seg_rows + seg);
+    int2 rr = __ldg(seg_rows + lo);
     int2 rr1 = make_int2(0, -1);
     unsigned long long v0 = 0, v1 = 0;
-    issue(seg, 0, __ldg(run_ptr + seg), __ldg(run_ptr + seg + 1));
-    if (seg1 >= 0) {
-        rr1 = __ldg(seg_rows + seg1);
-        v0 = __ldg(run_ptr + seg1);
-        v1 = __ldg(run_ptr + seg1 + 1);
+    issue(lo, 0, __ldg(run_ptr + lo), __ldg(run_ptr + lo + 1));
+    if (lo + 1 < hi) {
+        rr1 = __ldg(seg_rows + lo + 1);
+        v0 = __ldg(run_ptr + lo + 1);
+        v1 = __ldg(run_ptr + lo + 2);
     }
     long long myptr;
     unsigned int myvox;
@@ -611,33 +600,29 @@ __global__ void __launch_bounds__(256, 4) backproject_blocked_kernel(const int2 
     double carry = 0.0;                 // per-lane partial sums of the open row
     bool open = false, from_start = false;
     int head_state = BLK_NONE;
-    while (seg >= 0) {
+    int last_row = rr.y;
+    for (long long seg = lo; seg < hi; ++seg, buf ^= 1) {
         const long long k0 = seg * BP_WSEG;
         const int kend = (int)(min(k0 + (long long)BP_WSEG, nnz) - k0);
-        long long seg2 = -1, blk2 = blk1;
-        if (seg1 >= 0) {
-            issue(seg1, buf ^ 1, v0, v1);
-            successor(seg1, blk1, seg2, blk2);
-        }
+        const long long nxt = seg + 1, nxt2 = seg + 2;
+        if (nxt < hi) issue(nxt, buf ^ 1, v0, v1);
         long long nptr = 0;
         unsigned int nvox = 0;
-        if (seg1 >= 0) load_rows(rr1.x, rr1.y - rr1.x + 1, nptr, nvox);
+        if (nxt < hi) load_rows(rr1.x, rr1.y - rr1.x + 1, nptr, nvox);
         int2 rr2 = make_int2(0, -1);
         unsigned long long w0 = 0, w1 = 0;
-        if (seg2 >= 0) {
-            rr2 = __ldg(seg_rows + seg2);
-            w0 = __ldg(run_ptr + seg2);
-            w1 = __ldg(run_ptr + seg2 + 1);
+        if (nxt2 < hi) {
+            rr2 = __ldg(seg_rows + nxt2);
+            w0 = __ldg(run_ptr + nxt2);
+            w1 = __ldg(run_ptr + nxt2 + 1);
         }
         const int n_rows = rr.y - rr.x + 1;
+        last_row = rr.y;
         double myscale = 1.0;
         if (lane < min(n_rows, 31)) myscale = row_scale(scale, myvox);
         int pb = (int)max(min(myptr - k0, (long long)(BP_WSEG + 1)), -1LL);
         const bool cont = __shfl_sync(full, pb, 0) < 0;       // the segment's first row began before it
-        if (seg == seg_begin + blk * S) {                      // first segment of a block
-            head_state = BLK_NONE;
-            open = cont; from_start = cont; carry = 0.0;
-        }
+        if (seg == lo && cont) { open = true; from_start = true; carry = 0.0; }
         mbar_wait(&bar[buf], (phase >> buf) & 1u);
         phase ^= 1u << buf;
         double *prod = reinterpret_cast<double *>(mine + buf * STAGE);
@@ -660,7 +645,7 @@ __global__ void __launch_bounds__(256, 4) backproject_blocked_kernel(const int2 
                 const double t = warp_sum(carry);
                 if (from_start) {
                     head_state = BLK_CLOSED;
-                    if (lane == 0) P.head_sum[blk] = t;
+                    if (lane == 0) P.head_sum[wg] = t;
                 } else if (lane == 0) {
                     out[myvox] = t * myscale;
                 }
@@ -694,7 +679,7 @@ __global__ void __launch_bounds__(256, 4) backproject_blocked_kernel(const int2 
                     if (pb >= 0 && mye <= kend) {
                         out[myvox] = mysum * myscale;                       // a row complete inside the segment
                     } else if (pb < 0) {                                     // the continued first row ends here
-                        if (from_start) P.head_sum[blk] = mysum + wc;
+                        if (from_start) P.head_sum[wg] = mysum + wc;
                         else out[myvox] = (mysum + wc) * myscale;
                     } else {                                                 // the last row stays open
                         lane_open = true;
@@ -713,26 +698,22 @@ __global__ void __launch_bounds__(256, 4) backproject_blocked_kernel(const int2 
             from_start = false;
             carry = lane_open ? open_sum : 0.0;
         }
-        if (blk1 != blk || seg1 < 0) {
-            // end of the block: what is still open crosses into the next block
-            int tail_state = BLK_NONE;
-            if (open) {
-                const double t = warp_sum(carry);
-                if (from_start) {                       // the whole block lies inside one row
-                    head_state = BLK_WHOLE;
-                    if (lane == 0) P.head_sum[blk] = t;
-                } else {
-                    tail_state = BLK_OPEN;
-                    if (lane == 0) { P.tail_sum[blk] = t; P.tail_row[blk] = rr.y; }
-                }
-            }
-            if (lane == 0) { P.head_state[blk] = head_state; P.tail_state[blk] = tail_state; }
-        }
         __syncwarp();
         rr = rr1; rr1 = rr2; v0 = w0; v1 = w1; myptr = nptr; myvox = nvox;
-        seg = seg1; blk = blk1; seg1 = seg2; blk1 = blk2;
-        buf ^= 1;
     }
+    // end of the block: what is still open crosses into the next block
+    int tail_state = BLK_NONE;
+    if (open) {
+        const double t = warp_sum(carry);
+        if (from_start) {                       // the whole block lies inside one row
+            head_state = BLK_WHOLE;
+            if (lane == 0) P.head_sum[wg] = t;
+        } else {
+            tail_state = BLK_OPEN;
+            if (lane == 0) { P.tail_sum[wg] = t; P.tail_row[wg] = last_row; }
+        }
+    }
+    if (lane == 0) { P.head_state[wg] = head_state; P.tail_state[wg] = tail_state; }
 }
 
 // One thread per open tail (and one for the row the previous chunk launch left open): add the heads of the
@@ -1078,8 +1059,8 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
             BP_TRY(cudaStreamSynchronize(st));
             cudaFree(h->ray_idx); h->ray_idx = nullptr;   // not read again in this mode
             h->use_runs = 1;
-            // partial sums of the blocked apply: one slot per block of >= 4 segments (+ one per chunk boundary)
-            h->blk_cap = (int)(nseg / 4 + 32);
+            // partial sums of the blocked apply: one slot per warp of the largest launch (16 CTAs per SM x 8 warps)
+            h->blk_cap = sm_count() * 16 * 8;
             BP_TRY(cudaMalloc(&h->blk_head_sum, (size_t)h->blk_cap * sizeof(double)));
             BP_TRY(cudaMalloc(&h->blk_tail_sum, (size_t)h->blk_cap * sizeof(double)));
             BP_TRY(cudaMalloc(&h->blk_head_state, (size_t)h->blk_cap * sizeof(int)));
@@ -1144,12 +1125,10 @@ static int bp_apply_chunks(iono_backprojector_t h, const double *coef, bool perm
         const long long want = (nseg + warps - 1) / warps;
         const int ctas_seg = (int)(want < cap ? want : cap);
         const char *eb = getenv("IONO_BP_BLOCKED");
-        if (h->use_runs && !(eb && atoi(eb) == 0)) {
+        if (h->use_runs && !(eb && atoi(eb) == 0) && per_sm <= 16) {
             const int smem_r = warps * 2 * (BP_WSEG * 8 + BP_RUNREC_MAX) + warps * 16 + 64;
-            int S = 16;                                  // segments per block (dealt round-robin to the warps)
-            if (const char *es = getenv("IONO_BP_BLOCK_SEGS")) { int v = atoi(es); if (v >= 4 && v <= 4096) S = v; }
-            const long long n_blocks = (nseg + S - 1) / S;
-            if (n_blocks > h->blk_cap) return fail(IONO_EBADARG, "iono_backprojector_apply: block table too small");
+            const int W = ctas_seg * warps;
+            const long long B = (nseg + W - 1) / W;
             if (c0 == 0) h->blk_launches = 0;
             const double *pend_in = (h->blk_launches == 0) ? nullptr : h->blk_pend + 3 * ((h->blk_launches - 1) & 1);
             double *pend_out = h->blk_pend + 3 * (h->blk_launches & 1);
@@ -1158,10 +1137,9 @@ static int bp_apply_chunks(iono_backprojector_t h, const double *coef, bool perm
             CU_CHECK(cudaMemsetAsync(pend_out, 0, 3 * sizeof(double), st));
             CU_CHECK(cudaFuncSetAttribute(backproject_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
             backproject_blocked_kernel<<<ctas_seg, warps * 32, smem_r, st>>>(
-                h->items, h->ptr, dst, h->runs, h->run_ptr, h->weight, coef_int, scale, h->nnz, sb, se, S, n_blocks, P, out);
+                h->items, h->ptr, dst, h->runs, h->run_ptr, h->weight, coef_int, scale, h->nnz, sb, se, B, P, out);
             CU_CHECK(cudaGetLastError());
-            backproject_blocked_combine_kernel<<<ew_grid(n_blocks + 1), 256, 0, st>>>(P, (int)n_blocks, dst, scale, out,
-                                                                                     pend_in, pend_out);
+            backproject_blocked_combine_kernel<<<(W + 1 + 255) / 256, 256, 0, st>>>(P, W, dst, scale, out, pend_in, pend_out);
             CU_CHECK(cudaGetLastError());
             return IONO_OK;
         }

@@ -122,8 +122,8 @@ def main():
                                                              _lib.stream_ptr()), args.reps)
             out["apply_gradient_relerr"] = float(((acc - ref).abs().max() / ref.abs().max()).item())
             out["bp_rows"] = int(_lib.load().iono_backprojector_n_rows(bp.handle))
-            for name, env in (("unblocked", {"IONO_BP_BLOCKED": "0"}), ("blk8", {"IONO_BP_BLOCK_SEGS": "8"}),
-                              ("blk32", {"IONO_BP_BLOCK_SEGS": "32"}), ("blk64", {"IONO_BP_BLOCK_SEGS": "64"})):
+            for name, env in (("unblocked", {"IONO_BP_BLOCKED": "0"}), ("w8_c3", {"IONO_BP_CTAS": "3"}),
+                              ("w6_c5", {"IONO_BP_WARPS": "6", "IONO_BP_CTAS": "5"})):
                 os.environ.update(env)
                 out["apply_runs1_" + name] = timeit(lambda: bp.apply_permuted(perm, scale=ne, out=acc), args.reps)
                 assert float((acc - ref).abs().max()) <= 1e-12 * float(ref.abs().max())
