@@ -49,12 +49,6 @@ struct iono_backprojector {
     unsigned long long *run_ptr;   // [nseg+1] record offsets in 16-byte units
     long long run_bytes;
     int use_runs;
-    // blocked apply (backproject_blocked_kernel): per warp-block partial sums of the rows that cross block boundaries
-    double *blk_head_sum, *blk_tail_sum;   // [blk_cap]
-    int *blk_head_state, *blk_tail_state, *blk_tail_row;
-    double *blk_pend;                      // 2 x {open, sum, row}: the row left open by the previous chunk launch
-    int blk_cap;
-    int blk_launches;                      // chunk launches since chunk 0 (selects the pending slot)
 };
 
 // Per-row factor applied when a finished row is stored: nothing, a grid array (scale[v]), or the chain-rule
@@ -523,231 +517,6 @@ __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__re
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Blocked apply (the default): every warp owns a CONTIGUOUS block of segments instead of every W-th one.
-// Three quarters of the entries lie in rows longer than four segments, so most segments are interior to one row:
-// with a contiguous block the warp keeps that row's products as per-lane partial sums in a register ("carry") across
-// segments and reduces over the lanes once, when the row ends -- no shuffle tree, no partial sum and no combine
-// work per segment.  Only rows that cross a BLOCK boundary (at most two per warp) leave partial sums:
-//   head: the block's first row began in an earlier block   (CLOSED: it ends inside this block; WHOLE: the whole
-//         block lies inside that row),   tail: the block's last row continues into the next block (OPEN),
-// which one thread per open tail chains together afterwards (backproject_blocked_combine_kernel), including the
-// row a previous chunk launch left open (`pend`).  Fixed assignment and order => bit-reproducible; the grouping of
-// the additions depends on the launch's segment range, so a chunked apply equals the one-shot apply to rounding.
-// ---------------------------------------------------------------------------------------------
-struct BlockPartials {
-    double *head_sum, *tail_sum;
-    int *head_state, *tail_state, *tail_row;
-};
-enum { BLK_NONE = 0, BLK_CLOSED = 1, BLK_WHOLE = 2, BLK_EMPTY = 3, BLK_OPEN = 1 };
-
-__global__ void __launch_bounds__(256, 4) backproject_blocked_kernel(const int2 *__restrict__ seg_rows,
-                                                                   const long long *__restrict__ ptr,
-                                                                   const unsigned int *__restrict__ row_voxel,
-                                                                   const unsigned char *__restrict__ runs,
-                                                                   const unsigned long long *__restrict__ run_ptr,
-                                                                   const double *__restrict__ weight,
-                                                                   const double *__restrict__ coef,
-                                                                   const RowScale scale, long long nnz,
-                                                                   long long seg_begin, long long seg_end,
-                                                                   long long segs_per_block, BlockPartials P,
-                                                                   double *__restrict__ out) {
-    extern __shared__ __align__(128) unsigned char bp_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    constexpr int STAGE = BP_WSEG * 8 + BP_RUNREC_MAX;         // weights then the run record
-    unsigned char *mine = bp_smem + (size_t)warp * (2 * STAGE);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(bp_smem + (size_t)nwarp * 2 * STAGE) + warp * 2;
-    const long long wg = (long long)blockIdx.x * nwarp + warp;
-    const long long lo = seg_begin + wg * segs_per_block;
-    const long long hi = min(lo + segs_per_block, seg_end);
-    if (lane == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncwarp();
-    if (lo >= hi) {
-        if (lane == 0) { P.head_state[wg] = BLK_EMPTY; P.tail_state[wg] = BLK_NONE; }
-        return;
-    }
-    const uint64_t pol = policy_evict_first();
-    const unsigned full = 0xffffffffu;
-    auto issue = [&](long long seg, int buf, unsigned long long u0, unsigned long long u1) {
-        if (lane == 0) {
-            const unsigned int rec_bytes = (unsigned int)(u1 - u0) * 16u;
-            mbar_expect_tx(&bar[buf], BP_WSEG * 8 + rec_bytes);
-            bulk_g2s(mine + buf * STAGE, weight + seg * BP_WSEG, BP_WSEG * 8, &bar[buf], pol);
-            bulk_g2s(mine + buf * STAGE + BP_WSEG * 8, runs + u0 * 16ull, rec_bytes, &bar[buf], pol);
-        }
-    };
-    auto load_rows = [&](int first, int n, long long &p, unsigned int &vox) {
-        p = 0; vox = 0;
-        if (lane <= min(n, 31)) p = __ldg(ptr + first + lane);
-        if (lane < min(n, 31)) vox = __ldg(row_voxel + first + lane);
-    };
-    int2 rr = __ldg(seg_rows + lo);
-    int2 rr1 = make_int2(0, -1);
-    unsigned long long v0 = 0, v1 = 0;
-    issue(lo, 0, __ldg(run_ptr + lo), __ldg(run_ptr + lo + 1));
-    if (lo + 1 < hi) {
-        rr1 = __ldg(seg_rows + lo + 1);
-        v0 = __ldg(run_ptr + lo + 1);
-        v1 = __ldg(run_ptr + lo + 2);
-    }
-    long long myptr;
-    unsigned int myvox;
-    load_rows(rr.x, rr.y - rr.x + 1, myptr, myvox);
-    unsigned int phase = 0;
-    int buf = 0;
-    constexpr int PER = BP_WSEG / 32;
-    double carry = 0.0;                 // per-lane partial sums of the open row
-    bool open = false, from_start = false;
-    int head_state = BLK_NONE;
-    int last_row = rr.y;
-    for (long long seg = lo; seg < hi; ++seg, buf ^= 1) {
-        const long long k0 = seg * BP_WSEG;
-        const int kend = (int)(min(k0 + (long long)BP_WSEG, nnz) - k0);
-        const long long nxt = seg + 1, nxt2 = seg + 2;
-        if (nxt < hi) issue(nxt, buf ^ 1, v0, v1);
-        long long nptr = 0;
-        unsigned int nvox = 0;
-        if (nxt < hi) load_rows(rr1.x, rr1.y - rr1.x + 1, nptr, nvox);
-        int2 rr2 = make_int2(0, -1);
-        unsigned long long w0 = 0, w1 = 0;
-        if (nxt2 < hi) {
-            rr2 = __ldg(seg_rows + nxt2);
-            w0 = __ldg(run_ptr + nxt2);
-            w1 = __ldg(run_ptr + nxt2 + 1);
-        }
-        const int n_rows = rr.y - rr.x + 1;
-        last_row = rr.y;
-        double myscale = 1.0;
-        if (lane < min(n_rows, 31)) myscale = row_scale(scale, myvox);
-        int pb = (int)max(min(myptr - k0, (long long)(BP_WSEG + 1)), -1LL);
-        const bool cont = __shfl_sync(full, pb, 0) < 0;       // the segment's first row began before it
-        if (seg == lo && cont) { open = true; from_start = true; carry = 0.0; }
-        mbar_wait(&bar[buf], (phase >> buf) & 1u);
-        phase ^= 1u << buf;
-        double *prod = reinterpret_cast<double *>(mine + buf * STAGE);
-        const unsigned char *rec = mine + buf * STAGE + BP_WSEG * 8;
-        const uint2 idw = *reinterpret_cast<const uint2 *>(rec + lane * 8);
-        const unsigned int *bases = reinterpret_cast<const unsigned int *>(rec + BP_WSEG);
-        double c[PER];
-#pragma unroll
-        for (int u = 0; u < PER; ++u) {
-            const unsigned int run = ((u < 4 ? idw.x : idw.y) >> (8 * (u & 3))) & 0xffu;
-            c[u] = __ldg(coef + (bases[run] + (unsigned int)(32 * u + lane)));
-        }
-        if (n_rows == 1) {
-            double s = 0.0;
-#pragma unroll
-            for (int u = 0; u < PER; ++u) s = fma(prod[lane + u * 32], c[u], s);   // padding has weight 0
-            if (cont) carry += s;
-            else { carry = s; open = true; from_start = false; }
-            if (__shfl_sync(full, pb, 1) <= kend) {            // the row ends in this segment
-                const double t = warp_sum(carry);
-                if (from_start) {
-                    head_state = BLK_CLOSED;
-                    if (lane == 0) P.head_sum[wg] = t;
-                } else if (lane == 0) {
-                    out[myvox] = t * myscale;
-                }
-                open = false; from_start = false; carry = 0.0;
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < PER; ++u) prod[lane + u * 32] *= c[u];
-            const double wc = cont ? warp_sum(carry) : 0.0;   // what the open row has collected before this segment
-            __syncwarp();
-            bool lane_open = false;
-            double open_sum = 0.0;
-            int r0 = 0;
-            while (true) {
-                const int nb = min(n_rows - r0, 31);
-                double mysum = 0.0;
-                for (int q0 = 0; q0 < nb; q0 += 4) {
-                    const int q = q0 + (lane >> 3);
-                    const int b = __shfl_sync(full, pb, min(q, 31)), e = __shfl_sync(full, pb, min(q + 1, 31));
-                    const int l0 = max(b, 0), h0 = (q < nb) ? min(e, kend) : l0;
-                    double s = 0.0;
-                    for (int j = l0 + (lane & 7); j < h0; j += 8) s += prod[j];
-                    s += __shfl_xor_sync(full, s, 4);
-                    s += __shfl_xor_sync(full, s, 2);
-                    s += __shfl_xor_sync(full, s, 1);
-                    const double t = __shfl_sync(full, s, ((lane - q0) & 3) << 3);
-                    if (lane >= q0 && lane < q0 + 4) mysum = t;
-                }
-                const int mye = __shfl_down_sync(full, pb, 1);
-                if (lane < nb) {
-                    if (pb >= 0 && mye <= kend) {
-                        out[myvox] = mysum * myscale;                       // a row complete inside the segment
-                    } else if (pb < 0) {                                     // the continued first row ends here
-                        if (from_start) P.head_sum[wg] = mysum + wc;
-                        else out[myvox] = (mysum + wc) * myscale;
-                    } else {                                                 // the last row stays open
-                        lane_open = true;
-                        open_sum = mysum;
-                    }
-                }
-                r0 += nb;
-                if (r0 >= n_rows) break;
-                load_rows(rr.x + r0, n_rows - r0, myptr, myvox);
-                myscale = 1.0;
-                if (lane < min(n_rows - r0, 31)) myscale = row_scale(scale, myvox);
-                pb = (int)max(min(myptr - k0, (long long)(BP_WSEG + 1)), -1LL);
-            }
-            if (cont && from_start) head_state = BLK_CLOSED;
-            open = __ballot_sync(full, lane_open) != 0u;
-            from_start = false;
-            carry = lane_open ? open_sum : 0.0;
-        }
-        __syncwarp();
-        rr = rr1; rr1 = rr2; v0 = w0; v1 = w1; myptr = nptr; myvox = nvox;
-    }
-    // end of the block: what is still open crosses into the next block
-    int tail_state = BLK_NONE;
-    if (open) {
-        const double t = warp_sum(carry);
-        if (from_start) {                       // the whole block lies inside one row
-            head_state = BLK_WHOLE;
-            if (lane == 0) P.head_sum[wg] = t;
-        } else {
-            tail_state = BLK_OPEN;
-            if (lane == 0) { P.tail_sum[wg] = t; P.tail_row[wg] = last_row; }
-        }
-    }
-    if (lane == 0) { P.head_state[wg] = head_state; P.tail_state[wg] = tail_state; }
-}
-
-// One thread per open tail (and one for the row the previous chunk launch left open): add the heads of the
-// following blocks until the row closes; if it does not close inside this launch, hand it on.
-__global__ void __launch_bounds__(256) backproject_blocked_combine_kernel(BlockPartials P, int W,
-                                                                           const unsigned int *__restrict__ dst,
-                                                                           const RowScale scale, double *__restrict__ out,
-                                                                           const double *__restrict__ pend_in,
-                                                                           double *__restrict__ pend_out) {
-    const int stride = gridDim.x * blockDim.x;
-    for (int w = blockIdx.x * blockDim.x + threadIdx.x - 1; w < W; w += stride) {
-        double total;
-        int row;
-        if (w < 0) {
-            if (!pend_in || pend_in[0] == 0.0) continue;
-            total = pend_in[1];
-            row = (int)pend_in[2];
-        } else {
-            if (P.tail_state[w] != BLK_OPEN) continue;
-            total = P.tail_sum[w];
-            row = P.tail_row[w];
-        }
-        int j = w + 1;
-        while (j < W && P.head_state[j] == BLK_WHOLE) { total += P.head_sum[j]; ++j; }
-        if (j < W && P.head_state[j] == BLK_CLOSED) {
-            total += P.head_sum[j];
-            const unsigned int v = dst[row];
-            out[v] = total * row_scale(scale, v);
-        } else {
-            pend_out[0] = 1.0; pend_out[1] = total; pend_out[2] = (double)row;
-        }
-    }
-}
-
 // One THREAD per straddling row whose partials lie in at most 8 segments (the common case).
 __global__ void __launch_bounds__(256) backproject_combine_short_kernel(const int *__restrict__ rows, int n_rows,
                                                                          int seg, const long long *__restrict__ ptr,
@@ -843,8 +612,6 @@ extern "C" int iono_backprojector_destroy(iono_backprojector_t h) {
     cudaFree(h->coef_perm);
     cudaFree(h->runs);
     cudaFree(h->run_ptr);
-    cudaFree(h->blk_head_sum); cudaFree(h->blk_tail_sum); cudaFree(h->blk_head_state); cudaFree(h->blk_tail_state);
-    cudaFree(h->blk_tail_row); cudaFree(h->blk_pend);
     delete h;
     return IONO_OK;
 }
@@ -874,8 +641,6 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
     h->ray_idx = nullptr; h->weight = nullptr; h->ptr = nullptr; h->row_voxel = nullptr; h->n_rows = 0; h->long_rows = nullptr; h->n_long = 0; h->vlong_rows = nullptr; h->n_vlong = 0; h->partial = nullptr; h->items = nullptr;
     h->nnz = 0; h->V = V; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->coef_perm = nullptr;
     h->runs = nullptr; h->run_ptr = nullptr; h->run_bytes = 0; h->use_runs = 0;
-    h->blk_head_sum = h->blk_tail_sum = nullptr; h->blk_head_state = h->blk_tail_state = h->blk_tail_row = nullptr;
-    h->blk_pend = nullptr; h->blk_cap = 0; h->blk_launches = 0;
     cudaGetDevice(&h->device);
     unsigned long long *k0 = nullptr, *k1 = nullptr, *uk = nullptr;
     double *v0 = nullptr, *v1 = nullptr;
@@ -1059,15 +824,6 @@ extern "C" int iono_backprojector_create(iono_grid_t grid, const double *rays, i
             BP_TRY(cudaStreamSynchronize(st));
             cudaFree(h->ray_idx); h->ray_idx = nullptr;   // not read again in this mode
             h->use_runs = 1;
-            // partial sums of the blocked apply: one slot per warp of the largest launch (16 CTAs per SM x 8 warps)
-            h->blk_cap = sm_count() * 16 * 8;
-            BP_TRY(cudaMalloc(&h->blk_head_sum, (size_t)h->blk_cap * sizeof(double)));
-            BP_TRY(cudaMalloc(&h->blk_tail_sum, (size_t)h->blk_cap * sizeof(double)));
-            BP_TRY(cudaMalloc(&h->blk_head_state, (size_t)h->blk_cap * sizeof(int)));
-            BP_TRY(cudaMalloc(&h->blk_tail_state, (size_t)h->blk_cap * sizeof(int)));
-            BP_TRY(cudaMalloc(&h->blk_tail_row, (size_t)h->blk_cap * sizeof(int)));
-            BP_TRY(cudaMalloc(&h->blk_pend, 6 * sizeof(double)));
-            BP_TRY(cudaMemsetAsync(h->blk_pend, 0, 6 * sizeof(double), st));
         }
     }
 #undef BP_TRY
@@ -1124,25 +880,6 @@ static int bp_apply_chunks(iono_backprojector_t h, const double *coef, bool perm
         const long long cap = (long long)sm_count() * per_sm;
         const long long want = (nseg + warps - 1) / warps;
         const int ctas_seg = (int)(want < cap ? want : cap);
-        const char *eb = getenv("IONO_BP_BLOCKED");
-        if (h->use_runs && !(eb && atoi(eb) == 0) && per_sm <= 16) {
-            const int smem_r = warps * 2 * (BP_WSEG * 8 + BP_RUNREC_MAX) + warps * 16 + 64;
-            const int W = ctas_seg * warps;
-            const long long B = (nseg + W - 1) / W;
-            if (c0 == 0) h->blk_launches = 0;
-            const double *pend_in = (h->blk_launches == 0) ? nullptr : h->blk_pend + 3 * ((h->blk_launches - 1) & 1);
-            double *pend_out = h->blk_pend + 3 * (h->blk_launches & 1);
-            ++h->blk_launches;
-            BlockPartials P{h->blk_head_sum, h->blk_tail_sum, h->blk_head_state, h->blk_tail_state, h->blk_tail_row};
-            CU_CHECK(cudaMemsetAsync(pend_out, 0, 3 * sizeof(double), st));
-            CU_CHECK(cudaFuncSetAttribute(backproject_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
-            backproject_blocked_kernel<<<ctas_seg, warps * 32, smem_r, st>>>(
-                h->items, h->ptr, dst, h->runs, h->run_ptr, h->weight, coef_int, scale, h->nnz, sb, se, B, P, out);
-            CU_CHECK(cudaGetLastError());
-            backproject_blocked_combine_kernel<<<(W + 1 + 255) / 256, 256, 0, st>>>(P, W, dst, scale, out, pend_in, pend_out);
-            CU_CHECK(cudaGetLastError());
-            return IONO_OK;
-        }
         if (h->use_runs) {
             const int smem_r = warps * 2 * (BP_WSEG * 8 + BP_RUNREC_MAX) + warps * 16 + 64;
             CU_CHECK(cudaFuncSetAttribute(backproject_wruns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));

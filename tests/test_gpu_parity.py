@@ -711,18 +711,8 @@ def test_binned_backprojector_chunked_apply(ib, runs, monkeypatch):
             bp.apply_permuted(perm, scale=scale, out=out, c0=c0, c1=c0 + step)
             done = bp.chunk_voxels(c0 + step)
             assert 0 <= done <= V
-            # (the blocked apply groups its additions by the launch's segment range: equal to rounding)
-            assert float((out.reshape(-1)[:done] - ref.reshape(-1)[:done]).abs().max()) <= 1e-13 * float(ref.abs().max())
-        assert float((out - ref).abs().max()) <= 1e-13 * float(ref.abs().max())
-    if runs == "1":           # without the blocked assignment every split gives the same bits
-        monkeypatch.setenv("IONO_BP_BLOCKED", "0")
-        ref0 = bp.apply(y, scale=scale)
-        out = torch.full_like(ref, float("nan"))
-        for c0 in range(0, 16, 4):
-            bp.apply_permuted(perm, scale=scale, out=out, c0=c0, c1=c0 + 4)
-        assert torch.equal(out, ref0)
-        assert float((ref0 - ref).abs().max()) <= 1e-13 * float(ref.abs().max())
-        monkeypatch.delenv("IONO_BP_BLOCKED")
+            assert torch.equal(out.reshape(-1)[:done], ref.reshape(-1)[:done])
+        assert torch.equal(out, ref)
     # the chain-rule factor evaluated inside the apply: ne[v] = k exp(m[v]) for the touched rows, zero elsewhere
     from ionotomo_b200 import _lib
     m = torch.as_tensor(P["m"]).cuda()
@@ -855,28 +845,8 @@ def test_binned_backprojector_run_compressed(ib, shape, monkeypatch):
     assert run_bp.nnz == ref_bp.nnz
     if Nt >= 16:      # runs of consecutive times exist: the records are smaller than 4 B per entry
         assert run_bp.nbytes < ref_bp.nbytes
-    # default = blocked assignment (a warp carries a row's partial sums across its contiguous segments): equal to the
-    # plain warp-private apply to rounding; with IONO_BP_BLOCKED=0 the run-compressed kernel adds in the same order
-    ref_s, ref_n = ref_bp.apply(y, scale=scale), ref_bp.apply(y)
-    tol = 1e-13 * float(ref_n.abs().max())
-    assert float((run_bp.apply(y, scale=scale) - ref_s).abs().max()) <= tol
-    assert float((run_bp.apply(y) - ref_n).abs().max()) <= tol
-    assert torch.equal(run_bp.apply(y), run_bp.apply(y))                       # reproducible
-    # few, long blocks (one warp per SM): rows carried across many segments, heads/tails chained over several blocks
-    monkeypatch.setenv("IONO_BP_WARPS", "1")
-    monkeypatch.setenv("IONO_BP_CTAS", "1")
-    assert float((run_bp.apply(y, scale=scale) - ref_s).abs().max()) <= tol
-    out4 = torch.full_like(ref_s, float("nan"))
-    perm = y.permute(0, 2, 1).contiguous().reshape(-1)
-    for c0 in range(0, 16, 4):                                                 # and rows left open across chunk launches
-        run_bp.apply_permuted(perm, scale=scale, out=out4, c0=c0, c1=c0 + 4)
-    assert float((out4 - ref_s).abs().max()) <= tol
-    monkeypatch.delenv("IONO_BP_WARPS")
-    monkeypatch.delenv("IONO_BP_CTAS")
-    monkeypatch.setenv("IONO_BP_BLOCKED", "0")
-    assert torch.equal(run_bp.apply(y, scale=scale), ref_s)
-    assert torch.equal(run_bp.apply(y), ref_n)
-    monkeypatch.delenv("IONO_BP_BLOCKED")
+    assert torch.equal(run_bp.apply(y, scale=scale), ref_bp.apply(y, scale=scale))
+    assert torch.equal(run_bp.apply(y), ref_bp.apply(y))
 
 
 def test_sweep_shrinks_cta_for_large_axis_tables(ib):
