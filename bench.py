@@ -407,6 +407,7 @@ def main():
     # replay timed with CUDA events on the launching stream (device time without host launch gaps) ----------
     REP = 8
     kms = {}
+    phases = None
 
     def timed(name, fn):
         fn()
@@ -454,6 +455,8 @@ def main():
                 ts.append(a.elapsed_time(b))
             kms["allreduce_nccl"] = float(np.median(ts))
         timed("peer_reduce_expand" if (world > 1 and args.reducer == "peer") else "expand", ses._enqueue_reduce)
+        if world > 1 and args.reducer == "peer":
+            phases = ses.reducer.phase_times_us()
     ses.misfit_and_gradient(m_dev)          # leave the session's buffers in the state of a whole step
     torch.cuda.synchronize()
 
@@ -568,6 +571,8 @@ def main():
         elif name in ("binned_adjoint", "ray_sweep_adjoint_scatter"):
             k.update(algorithmic_bytes=bytes_adj, achieved_gbs=bytes_adj / msk / 1e6, frac=bytes_adj / msk / 1e6 / hbm,
                      rays_per_s=Rr / msk * 1e3)
+        if name == "peer_reduce_expand" and phases:
+            k["phases_us_rank0_last_call"] = phases
         kernels[name] = k
     kernels["cast_rays"] = {"ms": cast_ms, "algorithmic_bytes": Rr * 4 * Ns * 8, "achieved_gbs": Rr * 4 * Ns * 8 / cast_ms / 1e6,
                             "frac": Rr * 4 * Ns * 8 / cast_ms / 1e6 / hbm, "in_step": False}

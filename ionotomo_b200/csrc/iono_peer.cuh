@@ -27,7 +27,8 @@ constexpr int IONO_MAX_PEERS = 16;
 struct PeerTable {
     double *acc[IONO_MAX_PEERS];                 // compact accumulators (L doubles), [me] is local
     double *res[IONO_MAX_PEERS];                 // result vectors (L doubles), [me] is local
-    unsigned long long *flags[IONO_MAX_PEERS];   // per rank: [2][IONO_MAX_PEERS] epochs, arrival counter, call counter
+    unsigned long long *flags[IONO_MAX_PEERS];   // per rank: [2][IONO_MAX_PEERS] epochs, arrival counter, call counter,
+                                                 // 5 phase time stamps of the last call
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
@@ -74,12 +75,24 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
     // every CTA reads the call counter before its arrival below; CTA 0 advances it after the second wait,
     // which cannot complete before all CTAs of this grid have arrived
     const unsigned long long epoch = ld_acquire_sys(calls) + 1ull;
+    // phase time stamps of CTA 0 (ns, %globaltimer) for the last call: start, accumulators complete everywhere,
+    // my slice reduced and pushed, slices complete everywhere, expansion done (read by the bench for the record)
+    unsigned long long *stamps = my_flags + 2 * IONO_MAX_PEERS + 2;
+    auto stamp = [&](int i) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            stamps[i] = t;
+        }
+    };
+    stamp(0);
     // 1. my accumulator was finished by the previous kernel of this stream: tell everybody (one CTA does)
     if (blockIdx.x == 0 && (int)threadIdx.x < N) {
         __threadfence_system();
         st_release_sys(T.flags[threadIdx.x] + 0 * IONO_MAX_PEERS + me, epoch);
     }
     wait_all_ranks(my_flags, 0, N, epoch);
+    stamp(1);
     // 2. + 3. my slice (pairs of doubles; L is padded to an even length by the caller)
     const long long pairs = L / 2;
     const long long p0 = pairs * me / N, p1 = pairs * (me + 1) / N;
@@ -100,6 +113,7 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
     // every CTA's peer stores must be out before the slice is announced: the CTA barrier orders the threads'
     // stores before thread 0's system-scope fence (cumulative), the last CTA to arrive signals
     __syncthreads();
+    stamp(2);
     if (threadIdx.x == 0) {
         __threadfence_system();
         last = (atomicAdd(arrivals, 1u) == gridDim.x - 1);
@@ -113,6 +127,7 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
         if (threadIdx.x == 0) *arrivals = 0u;      // nobody of this launch reads it again
     }
     wait_all_ranks(my_flags, 1, N, epoch);
+    stamp(3);
     if (blockIdx.x == 0 && threadIdx.x == 0) *calls = epoch;
     // 4. expansion with the chain-rule factor; the last element of the vector is the summed misfit
     const double *res = T.res[me];
@@ -122,6 +137,7 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
         grad[v] = k * exp(__ldg(m + v)) * ld_peer(res + i);
     }
     if (misfit_out && blockIdx.x == 0 && threadIdx.x == 0) misfit_out[0] = ld_peer(res + n_union);
+    stamp(4);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
@@ -162,7 +178,7 @@ extern "C" int iono_peer_free(void *ptr) {
     return IONO_OK;
 }
 
-extern "C" int64_t iono_peer_flag_bytes(void) { return (2 * IONO_MAX_PEERS + 2) * 8; }
+extern "C" int64_t iono_peer_flag_bytes(void) { return (2 * IONO_MAX_PEERS + 2 + 6) * 8; }
 
 // acc, res, flags: arrays of N device pointers (entry `me` local, the others opened with iono_peer_open);
 // L: length of the compact vectors (even; element n_union carries the misfit).

@@ -90,6 +90,14 @@ class PeerReducer(object):
                   self.rank, self.L, ctypes.c_void_p(union_voxels.data_ptr()), int(n_union), _lib.ptr(m), float(k),
                   _lib.ptr(grad), _lib.ptr(misfit_out) if misfit_out is not None else None, _lib.stream_ptr())
 
+    def phase_times_us(self):
+        """Phases of the LAST reduce/expand call on this rank (CTA 0's time stamps): wait for all accumulators,
+        reduce my slice + push it, wait for all slices, expansion -- microseconds."""
+        torch.cuda.synchronize()
+        t = self.flags.tensor(torch.int64)[2 * 16 + 2:2 * 16 + 7].cpu().numpy().astype("float64")
+        names = ("wait_accumulators", "reduce_and_push_slice", "wait_slices", "expand")
+        return {n: float(t[i + 1] - t[i]) / 1e3 for i, n in enumerate(names)}
+
     def close(self):
         for b in (self.acc, self.res, self.flags):
             b.close()
