@@ -137,26 +137,10 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
     for (int r = 0; r < N; ++r) {
         const long long i0 = 2 * (pairs * r / N), i1 = min(2 * (pairs * (r + 1) / N), n_union);
         const double *res = T.res[r];
-        // pairs of elements per thread and four pairs in flight: the loop is a chain of peer-load latencies
-        for (long long i = i0 + 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x); i < i1; i += 8 * stride) {
-            double2 val[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long j = i + 2 * u * stride;
-                if (j < i1) val[u] = ld_peer_v2(res + j);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long j = i + 2 * u * stride;
-                if (j < i1) {
-                    const int va = __ldg(voxel + j);
-                    grad[va] = k * exp(__ldg(m + va)) * val[u].x;
-                    if (j + 1 < i1) {
-                        const int vb = __ldg(voxel + j + 1);
-                        grad[vb] = k * exp(__ldg(m + vb)) * val[u].y;
-                    }
-                }
-            }
+#pragma unroll 4
+        for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += stride) {
+            const int v = __ldg(voxel + i);
+            grad[v] = k * exp(__ldg(m + v)) * ld_peer(res + i);
         }
     }
     if (misfit_out && blockIdx.x == 0 && threadIdx.x == 0) {
