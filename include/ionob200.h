@@ -286,8 +286,8 @@ int iono_backprojector_destroy(iono_backprojector_t bp);
  *   sum[k]   = sum over ranks r = 0..N-1 (in that order: same bits on every rank) of acc[r][k],  k < L
  *   grad[union_voxels[k]] = k_scale * exp(m[union_voxels[k]]) * sum[k]     for k < n_union   (local grid)
  *   misfit_out[0] = sum[n_union]                                           (if misfit_out != NULL)
- * as ONE kernel per rank: flag handshake, reduce-scatter by peer loads, flag handshake, all-gather by peer
- * loads fused with the expansion.  acc, res, flags: arrays of N device pointers (index = rank; entry `me` is this
+ * as ONE kernel per rank: flag handshake, reduce-scatter by peer loads, all-gather by peer stores, flag
+ * handshake, expansion.  acc, res, flags: arrays of N device pointers (index = rank; entry `me` is this
  * rank's own allocation): compact accumulators (L doubles, L even, n_union < L), result vectors (L doubles)
  * and flag blocks (iono_peer_flag_bytes(), zeroed).  The launch has no per-call arguments (the call
  * counter lives in the flag block), so it can be replayed from a CUDA graph. */

@@ -9,10 +9,10 @@
 //   1. signals "my accumulator is complete" to every peer and waits for theirs      (flags in peer memory),
 //   2. reduce-scatter by PULL: sums its 1/N slice over the ranks' accumulators in rank order -- peer loads
 //      over NVLink, a fixed order, so all ranks get the same bits run after run --
-//   3. stores the summed slice in its own result vector, signals, waits for the other slices,
-//   4. all-gather by PULL fused with the expansion: grad[voxel[k]] = K exp(m[voxel[k]]) * sum[k] with sum[k] read
-//      from its owner's result vector (voxels no ray touches keep their zero), and hands out the summed misfit that
-//      travels as the last element of the vector.
+//   3. all-gather by PUSH: stores the summed slice into every rank's result vector (peer stores), signals,
+//      waits for the other slices,
+//   4. expands: grad[voxel[k]] = K exp(m[voxel[k]]) * sum[k]  (voxels no ray touches keep their zero),
+//      and hands out the summed misfit that travels as the last element of the vector.
 // Nothing but this kernel touches the link; no NCCL call sits on the step's critical path.
 //
 // Epoch counters instead of flag resets: call e writes e, waits for >= e; the epoch itself lives in device memory
@@ -108,12 +108,10 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
             for (int r = 0; r < 8; ++r)
                 if (r0 + r < N) { s.x += v[r].x; s.y += v[r].y; }
         }
-        *reinterpret_cast<double2 *>(T.res[me] + 2 * p) = s;      // LOCAL store: the peers pull it in step 4
+        for (int r = 0; r < N; ++r) *reinterpret_cast<double2 *>(T.res[r] + 2 * p) = s;
     }
-    // every CTA's stores must be visible system-wide before the slice is announced: the CTA barrier orders the
-    // threads' stores before thread 0's system-scope fence (cumulative), the last CTA to arrive signals.  (A first
-    // version PUSHED the slice into every peer's result vector here; the fence then had to wait for 7 x 1.6 MB of
-    // remote stores to be acknowledged and the second handshake took 46 us of the kernel's 70 at N = 8.)
+    // every CTA's peer stores must be out before the slice is announced: the CTA barrier orders the threads'
+    // stores before thread 0's system-scope fence (cumulative), the last CTA to arrive signals
     __syncthreads();
     stamp(2);
     if (threadIdx.x == 0) {
@@ -131,25 +129,14 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
     wait_all_ranks(my_flags, 1, N, epoch);
     stamp(3);
     if (blockIdx.x == 0 && threadIdx.x == 0) *calls = epoch;
-    // 4. all-gather by PULL fused with the expansion: every element is read from its owner's result vector (peer
-    // loads, no acknowledgement to wait for) and written to the local grid with the chain-rule factor; the last
-    // element of the vector is the summed misfit
-    for (int r = 0; r < N; ++r) {
-        const long long i0 = 2 * (pairs * r / N), i1 = min(2 * (pairs * (r + 1) / N), n_union);
-        const double *res = T.res[r];
+    // 4. expansion with the chain-rule factor; the last element of the vector is the summed misfit
+    const double *res = T.res[me];
 #pragma unroll 4
-        for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += stride) {
-            const int v = __ldg(voxel + i);
-            grad[v] = k * exp(__ldg(m + v)) * ld_peer(res + i);
-        }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_union; i += stride) {
+        const int v = __ldg(voxel + i);
+        grad[v] = k * exp(__ldg(m + v)) * ld_peer(res + i);
     }
-    if (misfit_out && blockIdx.x == 0 && threadIdx.x == 0) {
-        const long long pm = n_union / 2;                       // the pair that holds the misfit
-        int owner = 0;
-        for (int r = 0; r < N; ++r)
-            if (pm >= pairs * r / N && pm < pairs * (r + 1) / N) owner = r;
-        misfit_out[0] = ld_peer(T.res[owner] + n_union);
-    }
+    if (misfit_out && blockIdx.x == 0 && threadIdx.x == 0) misfit_out[0] = ld_peer(res + n_union);
     stamp(4);
 }
 
