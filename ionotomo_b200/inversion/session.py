@@ -111,8 +111,23 @@ class DeviceSession(object):
         L = self.n_union + 1                                    # + the misfit
         self.reducer_kind = reducer
         if reducer == "peer":
+            # peer memory needs CUDA IPC + peer access between all GPUs of the job; if any rank cannot map its peers
+            # every rank falls back to the NCCL reduction (decided collectively, so nobody waits on a flag forever)
             from ..peer import PeerReducer
-            self.reducer = PeerReducer(L, self.group)
+            ok = torch.ones(1, dtype=torch.int32, device=self.device)
+            try:
+                self.reducer = PeerReducer(L, self.group)
+            except _lib.IonoError as exc:
+                self.reducer = None
+                self._peer_error = str(exc)
+                ok.zero_()
+            if self.world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if int(ok.item()) == 0:
+                if self.reducer is not None:
+                    self.reducer = None          # (its buffers stay mapped until the process exits)
+                reducer = self.reducer_kind = "nccl"
+        if reducer == "peer":
             self.acc_c = self.reducer.acc_t
         else:
             from ..peer import LocalExpander

@@ -38,13 +38,19 @@ class PeerBuffer(object):
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle.raw), group=group)
         self.ptrs = []
+        err = None
         for r, h in enumerate(handles):
             if r == self.rank:
                 self.ptrs.append(self.local)
             else:
                 q = ctypes.c_void_p()
-                _lib.call("iono_peer_open", ctypes.c_char_p(h), ctypes.byref(q))
+                try:
+                    _lib.call("iono_peer_open", ctypes.c_char_p(h), ctypes.byref(q))
+                except _lib.IonoError as exc:      # keep going: every rank must reach the same collectives
+                    err = exc
                 self.ptrs.append(q.value)
+        if err is not None:
+            raise err
         self.table = (ctypes.c_void_p * self.world)(*self.ptrs)
 
     def tensor(self, dtype=torch.float64, offset_bytes=0, n=None):

@@ -136,3 +136,17 @@ def test_direction_shard_and_union_index_single_process():
     assert n == 3 and uv.tolist() == [3, 4, 10] and row_dst.tolist() == [0, 1, 2]
     row_dst, uv, n = sharding.union_index(torch.zeros(0, dtype=torch.int32), 16)
     assert n == 0 and uv.numel() == 0 and row_dst.numel() == 0
+
+
+def test_simpson_grid_weights_reproduce_the_reference_inner_product():
+    """``solver.simpson_grid_weights`` (the optional metric of the L-BFGS driver) == triple ``simps`` over the grid
+    (geometry/tri_cubic.py:61-67, bfgs_dask.py:165-167), odd and even axis lengths, non-uniform axes."""
+    from oracle import ionotomo_oracle as O
+    from ionotomo_b200.inversion.solver import simpson_grid_weights
+    rng = np.random.RandomState(8)
+    xv = np.cumsum(rng.uniform(0.5, 1.5, 9))
+    yv = np.cumsum(rng.uniform(0.5, 1.5, 6))
+    zv = np.linspace(0., 10., 8)
+    a, b = rng.normal(size=(9, 6, 8)), rng.normal(size=(9, 6, 8))
+    w = simpson_grid_weights(xv, yv, zv)
+    np.testing.assert_allclose((w * a * b).sum(), O.tci_inner(xv, yv, zv, a, b), rtol=1e-12)
