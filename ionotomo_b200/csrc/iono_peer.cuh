@@ -9,10 +9,11 @@
 //   1. signals "my accumulator is complete" to every peer and waits for theirs      (flags in peer memory),
 //   2. reduce-scatter by PULL: sums its 1/N slice over the ranks' accumulators in rank order -- peer loads
 //      over NVLink, a fixed order, so all ranks get the same bits run after run --
-//   3. all-gather by PUSH: stores the summed slice into every rank's result vector (peer stores), signals,
-//      waits for the other slices,
-//   4. expands: grad[voxel[k]] = K exp(m[voxel[k]]) * sum[k]  (voxels no ray touches keep their zero),
-//      and hands out the summed misfit that travels as the last element of the vector.
+//   3. all-gather by PUSH: stores the summed slice into every rank's result vector (peer stores) and signals,
+//   4. expands: grad[voxel[k]] = K exp(m[voxel[k]]) * sum[k]  (voxels no ray touches keep their zero) -- its own
+//      slice straight from the registers that summed it, every other slice as soon as that slice's owner has
+//      signalled, so the expansion overlaps the arrival of the later slices -- and hands out the summed misfit
+//      that travels as the last element of the vector.
 // Nothing but this kernel touches the link; no NCCL call sits on the step's critical path.
 //
 // Epoch counters instead of flag resets: call e writes e, waits for >= e; the epoch itself lives in device memory
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
     // which cannot complete before all CTAs of this grid have arrived
     const unsigned long long epoch = ld_acquire_sys(calls) + 1ull;
     // phase time stamps of CTA 0 (ns, %globaltimer) for the last call: start, accumulators complete everywhere,
-    // my slice reduced and pushed, slices complete everywhere, expansion done (read by the bench for the record)
+    // my slice reduced, pushed and expanded, first foreign slice arrived, all slices expanded (read by the bench)
     unsigned long long *stamps = my_flags + 2 * IONO_MAX_PEERS + 2;
     auto stamp = [&](int i) {
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -93,10 +94,23 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
     }
     wait_all_ranks(my_flags, 0, N, epoch);
     stamp(1);
-    // 2. + 3. my slice (pairs of doubles; L is padded to an even length by the caller)
+    // 2. + 3. my slice (pairs of doubles; L is padded to an even length by the caller).  The thread that summed a
+    // pair also expands it -- the sum is in its registers -- so the own slice never waits for anything
     const long long pairs = L / 2;
     const long long p0 = pairs * me / N, p1 = pairs * (me + 1) / N;
     const long long stride = (long long)gridDim.x * blockDim.x;
+    auto expand_pair = [&](long long p, double2 s) {
+        const long long i = 2 * p;
+        if (i + 1 < n_union) {
+            const int2 v = __ldg(reinterpret_cast<const int2 *>(voxel + i));
+            const double e0 = exp(__ldg(m + v.x)), e1 = exp(__ldg(m + v.y));
+            grad[v.x] = k * e0 * s.x;
+            grad[v.y] = k * e1 * s.y;
+        } else if (i < n_union) {
+            const int v = __ldg(voxel + i);
+            grad[v] = k * exp(__ldg(m + v)) * s.x;
+        }
+    };
     for (long long p = p0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < p1; p += stride) {
         double2 s = make_double2(0.0, 0.0);
         for (int r0 = 0; r0 < N; r0 += 8) {          // 8 peer loads in flight per thread, summed in rank order
@@ -109,6 +123,7 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
                 if (r0 + r < N) { s.x += v[r].x; s.y += v[r].y; }
         }
         for (int r = 0; r < N; ++r) *reinterpret_cast<double2 *>(T.res[r] + 2 * p) = s;
+        expand_pair(p, s);
     }
     // every CTA's peer stores must be out before the slice is announced: the CTA barrier orders the threads'
     // stores before thread 0's system-scope fence (cumulative), the last CTA to arrive signals
@@ -126,17 +141,30 @@ __global__ void __launch_bounds__(1024, 1) peer_reduce_expand_kernel(PeerTable T
         }
         if (threadIdx.x == 0) *arrivals = 0u;      // nobody of this launch reads it again
     }
-    wait_all_ranks(my_flags, 1, N, epoch);
-    stamp(3);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *calls = epoch;
-    // 4. expansion with the chain-rule factor; the last element of the vector is the summed misfit
+    // 4. the other slices, each as soon as ITS owner has announced it (no all-ranks wait: the expansion of the
+    // early slices hides the arrival of the late ones): grad[voxel[i]] = K exp(m[voxel[i]]) * sum[i]
     const double *res = T.res[me];
-#pragma unroll 4
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_union; i += stride) {
-        const int v = __ldg(voxel + i);
-        grad[v] = k * exp(__ldg(m + v)) * ld_peer(res + i);
+    for (int dr = 1; dr < N; ++dr) {
+        const int r = (me + dr) % N;
+        if (threadIdx.x == 0) {
+            const unsigned long long *f = my_flags + 1 * IONO_MAX_PEERS + r;
+            while (ld_acquire_sys(f) < epoch) __nanosleep(32);
+        }
+        __syncthreads();
+        if (dr == 1) stamp(3);
+        const long long q0 = pairs * r / N, q1 = pairs * (r + 1) / N;
+        for (long long p = q0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; p < q1; p += stride)
+            expand_pair(p, ld_peer_v2(res + 2 * p));
     }
-    if (misfit_out && blockIdx.x == 0 && threadIdx.x == 0) misfit_out[0] = ld_peer(res + n_union);
+    // the call counter advances once every CTA of this grid has read it, i.e. after this rank's own announcement
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long *f = my_flags + 1 * IONO_MAX_PEERS + me;
+        while (ld_acquire_sys(f) < epoch) __nanosleep(32);
+        *calls = epoch;
+        // the last element of the vector is the summed misfit (reduced by the owner of the last slice; every
+        // slice has been waited for above)
+        if (misfit_out) misfit_out[0] = ld_peer(res + n_union);
+    }
     stamp(4);
 }
 

@@ -98,10 +98,11 @@ class PeerReducer(object):
 
     def phase_times_us(self):
         """Phases of the LAST reduce/expand call on this rank (CTA 0's time stamps): wait for all accumulators,
-        reduce my slice + push it, wait for all slices, expansion -- microseconds."""
+        reduce, push and expand my slice, wait for the first foreign slice, expand the others as they arrive --
+        microseconds."""
         torch.cuda.synchronize()
         t = self.flags.tensor(torch.int64)[2 * 16 + 2:2 * 16 + 7].cpu().numpy().astype("float64")
-        names = ("wait_accumulators", "reduce_and_push_slice", "wait_slices", "expand")
+        names = ("wait_accumulators", "reduce_push_expand_own_slice", "wait_first_foreign_slice", "expand_arriving_slices")
         return {n: float(t[i + 1] - t[i]) / 1e3 for i, n in enumerate(names)}
 
     def close(self):
