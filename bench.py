@@ -391,7 +391,11 @@ def main():
     launches = _lib.launch_count - l0
     ms = start.elapsed_time(stop) / args.steps
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    ms_ranks = None
     if world > 1:
+        tl = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(tl, t)
+        ms_ranks = [float(x[0]) for x in tl]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     S_val = float(S)
@@ -554,6 +558,13 @@ def main():
                                "kernels, rays streamed over PCIe"}
             del rays_h
 
+    kms_ranks = None
+    if world > 1:
+        names = sorted(kms)
+        tk = torch.tensor([kms[n] for n in names], dtype=torch.float64, device="cuda")
+        tl = [torch.zeros_like(tk) for _ in range(world)]
+        dist.all_gather(tl, tk)
+        kms_ranks = {n: [round(float(x[i]), 4) for x in tl] for i, n in enumerate(names)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -593,6 +604,7 @@ def main():
     line = {
         "metric": "forward+adjoint ray passes per second", "value": R_total / ms * 1e3, "unit": "rays/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "ms_per_step_ranks": ms_ranks, "kernel_ms_ranks": kms_ranks,
         "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": dict(workload_config(world, nt, Nd, args.scaling), dx_km=w["dx_km"], dy_km=w["dy_km"], dz_km=w["dz_km"],
