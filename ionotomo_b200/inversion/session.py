@@ -165,7 +165,10 @@ class DeviceSession(object):
                       _lib.stream_ptr())
 
     def _enqueue_residual(self):
-        if self.sharded:
+        if self.sharded and self.reducer_kind == "nccl" and self.world > 1:
+            # the in-place all_reduce leaves the SUM in this rank's accumulator: the rows only other ranks touch must
+            # be cleared again.  (Peer reducer: the accumulator is only ever read by the peers; the apply overwrites
+            # this rank's rows with plain stores and the others stay zero from the allocation.)
             _lib.call("iono_zero_f64", _lib.ptr(self.acc_c), self.acc_c.numel(), _lib.stream_ptr())
         residual(self.tec, self.dobs, self.CdCt, self.i0, want_coef=self.bp is None, want_perm=self.bp is not None,
                  out=dict(dtec=self.dtec, coef=self.coef, coef_perm=self.coef_perm, scratch=self.scratch,
