@@ -175,8 +175,13 @@ int iono_tec_adjoint_f64(iono_grid_t grid, const double *rays, int Na, int Nt, i
  * iterative_newton.py:954-1017): per sample the cell index, the in-cell fractions and the
  * Simpson weight are computed once (create) and streamed by apply, 36 B per sample, HBM owned
  * by the handle.  apply writes tec_out[a,t,d] = simps(interp(ne; ray), s), bit-identical to
- * iono_tec_forward_f64 (same device functions, same summation order).  create counts samples
- * outside the grid in *oob_count (device) -- the caller raises like the forward does. */
+ * iono_tec_forward_f64 (same device functions, same summation order).  When every ray's weights
+ * are one common pattern times a per-ray factor to 2e-13 relative (s a linspace: every ray set the
+ * casting entry points make), create stores the weights factored -- 28 B per sample,
+ * iono_forwardprojector_factored() == 1 -- and apply agrees with iono_tec_forward_f64 to ~1e-14
+ * relative instead of bitwise; the environment variable IONO_PREP_FACTOR=0 (read by create) keeps
+ * per-sample weights.  create counts samples outside the grid in *oob_count (device) -- the caller
+ * raises like the forward does. */
 typedef struct iono_forwardprojector *iono_forwardprojector_t;
 int iono_forwardprojector_create(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
                                  iono_forwardprojector_t *out, unsigned long long *oob_count,
@@ -192,6 +197,7 @@ int iono_forwardprojector_quads_from_m_f64(iono_forwardprojector_t fp, const dou
                                            double *quads_out, void *stream);
 long long iono_forwardprojector_n_records(iono_forwardprojector_t fp);
 long long iono_forwardprojector_bytes(iono_forwardprojector_t fp);
+int iono_forwardprojector_factored(iono_forwardprojector_t fp);
 int iono_forwardprojector_destroy(iono_forwardprojector_t fp);
 
 /* ---- chord-length adjoint (the reference's generation-A gradient) ----------------

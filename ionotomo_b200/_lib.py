@@ -90,6 +90,7 @@ SIGNATURES = {
     "iono_forwardprojector_quads_from_m_f64": (_i, [_vp, _vp, _d, _vp, _vp]),
     "iono_forwardprojector_n_records": (ctypes.c_longlong, [_vp]),
     "iono_forwardprojector_bytes": (ctypes.c_longlong, [_vp]),
+    "iono_forwardprojector_factored": (ctypes.c_int, [_vp]),
     "iono_forwardprojector_destroy": (_i, [_vp]),
 }
 

@@ -5,27 +5,40 @@
 //
 //   assembly (once per geometry): per sample the cell index v, the in-cell fractions (tx,ty,tz) and
 //     the Simpson 'avg' weight w -- computed by the SAME device functions the stateless sweep
-//     (iono_sweep.cuh, MODE 0) evaluates per launch -- are written as a 36-byte record stream, rays
-//     stored in the sweep's time-fastest traversal order;
+//     (iono_sweep.cuh, MODE 0) evaluates per launch -- are written as a record stream, rays stored in
+//     the sweep's time-fastest traversal order and every ray cut into 64-sample BLOCKS that hold
+//     tx[n] ty[n] tz[n] (w[n]) cell[n] back to back, so that one chunk of one ray is ONE contiguous
+//     bulk copy (2304 bytes) -- the producer's instruction count per chunk was the kernel's largest
+//     cost with one copy per row (profiles/r02_ncu_step_summary.txt: 158 warp instructions per 32
+//     samples, 35 of them the interpolation);
+//   factored weights: when every ray's weights are one common pattern times a per-ray factor,
+//     w[q][i] = c[q] P[i] to 2e-13 relative (true for every ray set the casting kernels make: s is a
+//     linspace, so w = h/3 * {1,4,2,...} up to the rounding of the differences), the w row is dropped
+//     -- 28 bytes per sample instead of 36 -- and the apply multiplies by P[i] from shared memory and
+//     by c[q] once per ray.  Checked per geometry at create time; IONO_PREP_FACTOR=0 disables it.
 //   apply: tec[ray] = sum_s w_s * trilerp(ne; v_s, t_s).  One warp per ray, lanes = consecutive
 //     samples, records streamed by TMA 1-D bulk copies into a warp-private ring (as the sweep), but no
 //     cell search, no table reads and no weight arithmetic in the loop: 8 corner gathers, 14 fp64
 //     operations and one fma per sample.
 //
 // v, t and w are bit-identical to what MODE 0 derives and the per-lane accumulation order is the
-// same, so the result is bit-identical to iono_tec_forward_f64 (tested).  The stream is 36 B per
-// sample against the 32 B of the raw ray rows; the roofline fraction is still quoted on the
-// algorithmic bytes of the reference's API boundary.
+// same, so with per-sample weights the result is bit-identical to iono_tec_forward_f64 (tested); with
+// factored weights it agrees to ~1e-14 relative.  The roofline fraction is quoted on the algorithmic
+// bytes of the reference's API boundary (32 B per sample).
 #pragma once
 #include <cub/cub.cuh>
 
+constexpr int PREP_C = 64;      // samples per block and per ring stage
+
 struct iono_forwardprojector {
-    int *cell;        // (R, Nsp) flat index of the cell's low corner
-    double *frac;     // (R, 4, Nsp) rows tx, ty, tz, w
+    unsigned char *rec;   // (R, Nsp) samples in blocks of PREP_C: tx[n] ty[n] tz[n] (w[n]) doubles, cell[n] ints
+    double *wscale;       // [R] per-ray weight factor c[q], slot order (factored weights only)
+    double *pattern;      // [Ns] common weight pattern P[i] (factored weights only)
+    int factored;
     int *records;     // quad records (iono_device.cuh) the samples read: cells v and v + ny*nz, ascending
     long long n_records;
     long long R;
-    int Na, Nt, Nd, Ns, Nsp;   // Nsp = Ns rounded up to a multiple of 4 (16-byte rows for the bulk copies)
+    int Na, Nt, Nd, Ns, Nsp;   // Nsp = Ns rounded up to a multiple of 4 (16-byte pieces for the bulk copies)
     int nx, ny, nz;
     int device;
 };
@@ -40,12 +53,56 @@ __device__ __forceinline__ long long prepared_ray_of(int q, int Na, int Nt, int 
     return ((long long)a * Nt + t) * Nd + d;
 }
 
-template <int AXK>
+__device__ __forceinline__ double prepared_weight(const double *sp, int i, int Ns, bool n_odd) {
+    // neighbours outside [0, Ns) are never used by simpson_weight; clamp the reads
+    return simpson_weight(i, Ns, n_odd, sp[max(i - 2, 0)], sp[max(i - 1, 0)], sp[i], sp[min(i + 1, Ns - 1)],
+                          sp[min(i + 2, Ns - 1)]);
+}
+
+// P[i] = w[slot 0][i] * Ns / sum_i w[slot 0][i]   (one warp)
+__global__ void __launch_bounds__(32) weight_pattern_kernel(const double *__restrict__ rays, int Na, int Nt, int Nd,
+                                                             int Ns, double *__restrict__ pattern) {
+    const int lane = threadIdx.x;
+    const double *sp = rays + prepared_ray_of(0, Na, Nt, Nd) * 4 * Ns + 3 * Ns;
+    const bool n_odd = Ns & 1;
+    double tot = 0.0;
+    for (int i = lane; i < Ns; i += 32) tot += prepared_weight(sp, i, Ns, n_odd);
+    tot = warp_sum(tot);
+    tot = __shfl_sync(0xffffffffu, tot, 0);
+    for (int i = lane; i < Ns; i += 32) pattern[i] = (tot != 0.0) ? prepared_weight(sp, i, Ns, n_odd) * (double)Ns / tot : 0.0;
+}
+
+// c[q] = sum_i w[q][i] / Ns, and the check |w[q][i] - c[q] P[i]| <= tol |c[q] P[i]| for every sample (warp per ray)
+__global__ void __launch_bounds__(256) weight_factor_kernel(const double *__restrict__ rays, int R, int Na, int Nt,
+                                                             int Nd, int Ns, const double *__restrict__ pattern,
+                                                             double tol, double *__restrict__ wscale,
+                                                             int *__restrict__ mismatch) {
+    const int lane = threadIdx.x & 31;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const bool n_odd = Ns & 1;
+    bool bad = false;
+    for (int q = warp_global; q < R; q += n_warps) {
+        const double *sp = rays + prepared_ray_of(q, Na, Nt, Nd) * 4 * Ns + 3 * Ns;
+        double tot = 0.0;
+        for (int i = lane; i < Ns; i += 32) tot += prepared_weight(sp, i, Ns, n_odd);
+        tot = warp_sum(tot);
+        const double c = __shfl_sync(0xffffffffu, tot, 0) / (double)Ns;
+        for (int i = lane; i < Ns; i += 32) {
+            const double want = c * pattern[i];
+            if (!(fabs(prepared_weight(sp, i, Ns, n_odd) - want) <= tol * fabs(want))) bad = true;   // (NaN -> bad)
+        }
+        if (lane == 0) wscale[q] = c;
+    }
+    if (bad) atomicOr(mismatch, 1);
+}
+
+template <int AXK, bool FACT>
 __global__ void __launch_bounds__(256) prepare_samples_kernel(Grid g, const double *__restrict__ rays, int R, int Na,
                                                                int Nt, int Nd, int Ns, int Nsp,
-                                                               int *__restrict__ cell, double *__restrict__ frac,
+                                                               unsigned char *__restrict__ rec,
                                                                unsigned char *__restrict__ used,
                                                                unsigned long long *oob_count) {
+    constexpr int RB = FACT ? 28 : 36;          // bytes per sample
     const int ny = g.ax[1].n, nz = g.ax[2].n;
     const AxisR ax = axis_regs(g.ax[0]), ay = axis_regs(g.ax[1]), az = axis_regs(g.ax[2]);
     const double2 *tabx = g.ax[0].tab, *taby = g.ax[1].tab, *tabz = g.ax[2].tab;
@@ -59,69 +116,49 @@ __global__ void __launch_bounds__(256) prepare_samples_kernel(Grid g, const doub
         double tx = 0.0, ty = 0.0, tz = 0.0, w = 0.0;
         if (i < Ns) {   // the pad samples (i >= Ns) are never read back as data
             const double *rp = rays + prepared_ray_of(q, Na, Nt, Nd) * 4 * Ns;
-            const double *sp = rp + 3 * Ns;
             const double px = rp[i], py = rp[Ns + i], pz = rp[2 * Ns + i];
             int ix, iy, iz;
             n_oob += locate3<AXK>(tabx, taby, tabz, ax, ay, az, px, py, pz, ix, iy, iz, tx, ty, tz);
-            // neighbours outside [0, Ns) are never used by simpson_weight; clamp the reads
-            w = simpson_weight(i, Ns, n_odd, sp[max(i - 2, 0)], sp[max(i - 1, 0)], sp[i], sp[min(i + 1, Ns - 1)],
-                               sp[min(i + 2, Ns - 1)]);
+            if (!FACT) w = prepared_weight(rp + 3 * Ns, i, Ns, n_odd);
             v = (ix * ny + iy) * nz + iz;
             used[v] = 1;                 // quad records this sample gathers from (benign race: all writers store 1)
             used[v + ny * nz] = 1;
         }
-        cell[k] = v;
-        double *f = frac + (long long)q * 4 * Nsp + i;
-        f[0] = tx; f[Nsp] = ty; f[2 * Nsp] = tz; f[3 * Nsp] = w;
+        const int c0 = i / PREP_C * PREP_C, j = i - c0, n4 = min(PREP_C, Nsp - c0);
+        unsigned char *blk = rec + ((long long)q * Nsp + c0) * RB;
+        double *f = reinterpret_cast<double *>(blk);
+        f[j] = tx; f[n4 + j] = ty; f[2 * n4 + j] = tz;
+        if (!FACT) f[3 * n4 + j] = w;
+        reinterpret_cast<int *>(f + (FACT ? 3 : 4) * n4)[j] = v;
     }
     if (n_oob) atomicAdd(oob_count, (unsigned long long)n_oob);
 }
 
-// A stage holds tx[C], ty[C], tz[C], w[C] and cell[C] (int32).
-template <int C>
+template <bool FACT>
 struct PreparedStage {
-    static constexpr int CELL_OFF = 4 * C;   // in doubles
-    static constexpr int BYTES = ((4 * C * 8 + C * 4 + 127) / 128) * 128;
+    static constexpr int RB = FACT ? 28 : 36;
+    static constexpr int BYTES = ((PREP_C * RB + 127) / 128) * 128;
 };
 
-// n_cp: samples to copy (a multiple of 4, so every piece is a multiple of 16 bytes)
-template <int C, bool BULK>
-__device__ __forceinline__ void fill_prepared(double *stage, uint64_t *bar, const double *frac_q, const int *cell_q,
-                                              int Nsp, int c0, int n_cp, int lane, uint64_t policy) {
-    if (BULK) {
-        if (lane == 0) {
-            mbar_expect_tx(bar, (uint32_t)(n_cp * 36));
-            bulk_g2s(stage, frac_q + c0, n_cp * 8, bar, policy);
-            bulk_g2s(stage + C, frac_q + Nsp + c0, n_cp * 8, bar, policy);
-            bulk_g2s(stage + 2 * C, frac_q + 2 * Nsp + c0, n_cp * 8, bar, policy);
-            bulk_g2s(stage + 3 * C, frac_q + 3 * Nsp + c0, n_cp * 8, bar, policy);
-            bulk_g2s(stage + PreparedStage<C>::CELL_OFF, cell_q + c0, n_cp * 4, bar, policy);
-        }
-    } else {
-        int *cdst = reinterpret_cast<int *>(stage + PreparedStage<C>::CELL_OFF);
-        for (int i = lane; i < n_cp; i += 32) {
-            stage[i] = ld_stream(frac_q + c0 + i, policy);
-            stage[C + i] = ld_stream(frac_q + Nsp + c0 + i, policy);
-            stage[2 * C + i] = ld_stream(frac_q + 2 * Nsp + c0 + i, policy);
-            stage[3 * C + i] = ld_stream(frac_q + 3 * Nsp + c0 + i, policy);
-            cdst[i] = __ldcs(cell_q + c0 + i);
-        }
-    }
-}
-
-template <int C, bool BULK, int MAXT, int LAYOUT>
-__global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const double *__restrict__ frac,
-                                                                    const int *__restrict__ cell,
+template <bool FACT, bool BULK, int MAXT, int LAYOUT>
+__global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const unsigned char *__restrict__ rec,
+                                                                    const double *__restrict__ wscale,
+                                                                    const double *__restrict__ pattern,
                                                                     const double *__restrict__ field,
                                                                     double *__restrict__ tec, int R, int Na, int Nt,
                                                                     int Nd, int Ns, int Nsp, int stages, int sy,
                                                                     int sx) {
+    constexpr int C = PREP_C, RB = PreparedStage<FACT>::RB, SB = PreparedStage<FACT>::BYTES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    // shared: [per-warp mbarriers][per-warp stages]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw) + warp * stages;
-    const unsigned int off = ((unsigned int)(nwarp * stages) * 8u + 127u) / 128u * 128u;
-    unsigned char *ring = smem_raw + off + (unsigned int)(warp * stages) * PreparedStage<C>::BYTES;
+    // shared: [weight pattern (FACT)][per-warp mbarriers][per-warp stages]
+    const double *pat = reinterpret_cast<const double *>(smem_raw);
+    unsigned int off = FACT ? ((unsigned int)Ns * 8u + 127u) / 128u * 128u : 0u;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + off) + warp * stages;
+    off += ((unsigned int)(nwarp * stages) * 8u + 127u) / 128u * 128u;
+    unsigned char *ring = smem_raw + off + (unsigned int)(warp * stages) * SB;
+    if (FACT)
+        for (int i = threadIdx.x; i < Ns; i += blockDim.x) reinterpret_cast<double *>(smem_raw)[i] = pattern[i];
     if (BULK && lane == 0)
         for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
     if (BULK) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -136,17 +173,20 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const double 
     int my_rays = (n_bundles > (int)blockIdx.x) ? (n_bundles - 1 - (int)blockIdx.x) / G + 1 : 0;
     if (my_rays > 0 && ((int)blockIdx.x + (my_rays - 1) * G) * nwarp + warp >= R) --my_rays;
     const int q0 = (int)blockIdx.x * nwarp + warp, qstep = G * nwarp;
+    const long long ray_bytes = (long long)Nsp * RB;
 
-    // producer cursor (ray fk = slot fq, chunk fc, stage fs)
-    int fk = 0, fc = 0, fs = 0, fq = q0;
+    // producer (lane 0): the block of (ray slot fq, chunk fc) -> stage fs, ONE bulk copy
+    int fk = 0, fc = 0, fs = 0;
+    const unsigned char *fsrc = rec + (long long)q0 * ray_bytes;
     auto produce = [&]() {
         if (fk < my_rays) {
-            const int c0 = fc * C;
-            fill_prepared<C, true>(reinterpret_cast<double *>(ring + fs * PreparedStage<C>::BYTES), &bars[fs],
-                                   frac + (long long)fq * 4 * Nsp, cell + (long long)fq * Nsp, Nsp, c0,
-                                   min(C, Nsp - c0), lane, pol_stream);
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)(min(C, Nsp - fc * C) * RB);
+                mbar_expect_tx(&bars[fs], bytes);
+                bulk_g2s(ring + fs * SB, fsrc + (long long)fc * (C * RB), bytes, &bars[fs], pol_stream);
+            }
             fs = (fs + 1 == stages) ? 0 : fs + 1;
-            if (++fc == chunks) { fc = 0; ++fk; fq += qstep; }
+            if (++fc == chunks) { fc = 0; ++fk; fsrc += (long long)qstep * ray_bytes; }
         }
     };
     if (BULK)
@@ -159,18 +199,20 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const double 
         double acc = 0.0;
         for (int chunk = 0; chunk < chunks; ++chunk) {
             const int c0 = chunk * C;
-            double *stage = reinterpret_cast<double *>(ring + us * PreparedStage<C>::BYTES);
+            const int n4 = min(C, Nsp - c0);
+            double *stage = reinterpret_cast<double *>(ring + us * SB);
             if (BULK) {
                 produce();
                 mbar_wait(&bars[us], (phases >> us) & 1u);
                 phases ^= 1u << us;
             } else {
-                fill_prepared<C, false>(stage, nullptr, frac + (long long)q * 4 * Nsp, cell + (long long)q * Nsp, Nsp,
-                                        c0, min(C, Nsp - c0), lane, pol_stream);
+                const unsigned char *src = rec + (long long)q * ray_bytes + (long long)c0 * RB;
+                for (int i = lane; i < n4 * RB / 4; i += 32)
+                    reinterpret_cast<int *>(stage)[i] = __ldcs(reinterpret_cast<const int *>(src) + i);
                 __syncwarp();
             }
-            const double *tx_ = stage, *ty_ = stage + C, *tz_ = stage + 2 * C, *w_ = stage + 3 * C;
-            const int *cell_ = reinterpret_cast<const int *>(stage + PreparedStage<C>::CELL_OFF);
+            const double *tx_ = stage, *ty_ = stage + n4, *tz_ = stage + 2 * n4, *w_ = FACT ? pat + c0 : stage + 3 * n4;
+            const int *cell_ = reinterpret_cast<const int *>(stage + (FACT ? 3 : 4) * n4);
             const int n_c = min(C, Ns - c0);
 #pragma unroll 2
             for (int jb = 0; jb < n_c; jb += 32) {
@@ -186,8 +228,11 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const double 
             us = (us + 1 == stages) ? 0 : us + 1;
             __syncwarp();
         }
-        const double tot = warp_sum(acc);
-        if (lane == 0) tec[prepared_ray_of(q, Na, Nt, Nd)] = tot;
+        double tot = warp_sum(acc);
+        if (lane == 0) {
+            if (FACT) tot *= __ldg(wscale + q);
+            tec[prepared_ray_of(q, Na, Nt, Nd)] = tot;
+        }
     }
 }
 
@@ -224,14 +269,31 @@ extern "C" int iono_forwardprojector_quads_from_m_f64(iono_forwardprojector_t h,
 extern "C" int iono_forwardprojector_destroy(iono_forwardprojector_t h) {
     if (!h) return IONO_OK;
     cudaFree(h->records);
-    cudaFree(h->cell);
-    cudaFree(h->frac);
+    cudaFree(h->rec);
+    cudaFree(h->wscale);
+    cudaFree(h->pattern);
     delete h;
     return IONO_OK;
 }
 
 extern "C" long long iono_forwardprojector_bytes(iono_forwardprojector_t h) {
-    return h ? h->R * h->Nsp * 36 : 0;
+    if (!h) return 0;
+    return h->R * h->Nsp * (h->factored ? 28 : 36) + (h->factored ? (h->R + h->Ns) * 8 : 0);
+}
+
+// 1 when the operator stores factored Simpson weights (28 bytes per sample), 0 for per-sample weights (36)
+extern "C" int iono_forwardprojector_factored(iono_forwardprojector_t h) { return h ? h->factored : 0; }
+
+template <int AXK>
+static void launch_prepare_samples(iono_forwardprojector *h, iono_grid_t grid, const double *rays,
+                                   unsigned char *used, unsigned long long *oob_count, cudaStream_t st) {
+    const long long n = h->R * h->Nsp;
+    if (h->factored)
+        prepare_samples_kernel<AXK, true><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)h->R, h->Na, h->Nt, h->Nd,
+                                                                      h->Ns, h->Nsp, h->rec, used, oob_count);
+    else
+        prepare_samples_kernel<AXK, false><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)h->R, h->Na, h->Nt, h->Nd,
+                                                                       h->Ns, h->Nsp, h->rec, used, oob_count);
 }
 
 extern "C" int iono_forwardprojector_create(iono_grid_t grid, const double *rays, int Na, int Nt, int Nd, int Ns,
@@ -244,38 +306,52 @@ extern "C" int iono_forwardprojector_create(iono_grid_t grid, const double *rays
     cudaStream_t st = (cudaStream_t)stream;
     CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
     iono_forwardprojector *h = new iono_forwardprojector();
-    h->cell = nullptr; h->frac = nullptr; h->records = nullptr; h->n_records = 0; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->Ns = Ns;
+    h->rec = nullptr; h->wscale = nullptr; h->pattern = nullptr; h->factored = 0;
+    h->records = nullptr; h->n_records = 0; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->Ns = Ns;
     h->Nsp = (Ns + 3) / 4 * 4;
     h->nx = grid->nx; h->ny = grid->ny; h->nz = grid->nz;
     cudaGetDevice(&h->device);
     if (R > 0 && Ns >= 2) {   // simps of a single sample is 0: nothing to store
         const long long n = R * h->Nsp;
-        cudaError_t e = cudaMalloc(&h->cell, (size_t)n * sizeof(int));
-        if (e == cudaSuccess) e = cudaMalloc(&h->frac, (size_t)n * 4 * sizeof(double));
-        if (e != cudaSuccess) {
-            iono_forwardprojector_destroy(h);
-            return fail(IONO_ECUDA, "iono_forwardprojector_create: cudaMalloc: %s", cudaGetErrorString(e));
-        }
         const long long V = (long long)grid->nx * grid->ny * grid->nz;
+        cudaError_t e = cudaSuccess;
         unsigned char *used = nullptr;
         long long *d_n = nullptr;
         void *tmp = nullptr;
+        int *d_bad = nullptr;
         auto bail = [&](const char *what) {
-            cudaFree(used); cudaFree(d_n); cudaFree(tmp);
+            cudaFree(used); cudaFree(d_n); cudaFree(tmp); cudaFree(d_bad);
             iono_forwardprojector_destroy(h);
             return fail(IONO_ECUDA, "iono_forwardprojector_create: %s: %s", what, cudaGetErrorString(e));
         };
+        // common weight pattern x per-ray factor?  (one pass over the s rows)
+        const char *env = getenv("IONO_PREP_FACTOR");
+        if (!(env && atoi(env) == 0)) {
+            if ((e = cudaMalloc(&h->wscale, (size_t)R * sizeof(double))) != cudaSuccess) return bail("cudaMalloc");
+            if ((e = cudaMalloc(&h->pattern, (size_t)Ns * sizeof(double))) != cudaSuccess) return bail("cudaMalloc");
+            if ((e = cudaMalloc(&d_bad, sizeof(int))) != cudaSuccess) return bail("cudaMalloc");
+            if ((e = cudaMemsetAsync(d_bad, 0, sizeof(int), st)) != cudaSuccess) return bail("cudaMemsetAsync");
+            weight_pattern_kernel<<<1, 32, 0, st>>>(rays, Na, Nt, Nd, Ns, h->pattern);
+            weight_factor_kernel<<<ew_grid(R * 32), 256, 0, st>>>(rays, (int)R, Na, Nt, Nd, Ns, h->pattern, 2e-13,
+                                                                  h->wscale, d_bad);
+            int bad = 1;
+            if ((e = cudaGetLastError()) != cudaSuccess) return bail("launch");
+            if ((e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
+                (e = cudaStreamSynchronize(st)) != cudaSuccess)
+                return bail("weight check");
+            cudaFree(d_bad); d_bad = nullptr;
+            h->factored = bad ? 0 : 1;
+            if (!h->factored) {
+                cudaFree(h->wscale); cudaFree(h->pattern);
+                h->wscale = nullptr; h->pattern = nullptr;
+            }
+        }
+        if ((e = cudaMalloc(&h->rec, (size_t)n * (h->factored ? 28 : 36))) != cudaSuccess) return bail("cudaMalloc");
         if ((e = cudaMalloc(&used, (size_t)V)) != cudaSuccess) return bail("cudaMalloc");
         if ((e = cudaMemsetAsync(used, 0, (size_t)V, st)) != cudaSuccess) return bail("cudaMemsetAsync");
-        if (grid->exact)
-            prepare_samples_kernel<2><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
-                                                                  h->cell, h->frac, used, oob_count);
-        else if (grid->uniform)
-            prepare_samples_kernel<1><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
-                                                                  h->cell, h->frac, used, oob_count);
-        else
-            prepare_samples_kernel<0><<<ew_grid(n), 256, 0, st>>>(grid->dev, rays, (int)R, Na, Nt, Nd, Ns, h->Nsp,
-                                                                  h->cell, h->frac, used, oob_count);
+        if (grid->exact) launch_prepare_samples<2>(h, grid, rays, used, oob_count, st);
+        else if (grid->uniform) launch_prepare_samples<1>(h, grid, rays, used, oob_count, st);
+        else launch_prepare_samples<0>(h, grid, rays, used, oob_count, st);
         if ((e = cudaGetLastError()) != cudaSuccess) return bail("launch");
         // list of the quad records in use (ascending)
         if ((e = cudaMalloc(&d_n, sizeof(long long))) != cudaSuccess) return bail("cudaMalloc");
@@ -307,13 +383,13 @@ extern "C" int iono_forwardprojector_create(iono_grid_t grid, const double *rays
     return IONO_OK;
 }
 
-template <int C, bool BULK, int MAXT, int LAYOUT>
+template <bool FACT, bool BULK, int MAXT, int LAYOUT>
 static int launch_prepared_t(iono_forwardprojector_t h, const double *ne, double *tec, int warps, int stages,
                              size_t smem, int ctas, cudaStream_t st) {
-    auto kern = prepared_forward_kernel<C, BULK, MAXT, LAYOUT>;
+    auto kern = prepared_forward_kernel<FACT, BULK, MAXT, LAYOUT>;
     CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<ctas, warps * 32, smem, st>>>(h->frac, h->cell, ne, tec, (int)h->R, h->Na, h->Nt, h->Nd, h->Ns, h->Nsp,
-                                         stages, h->nz, h->ny * h->nz);
+    kern<<<ctas, warps * 32, smem, st>>>(h->rec, h->wscale, h->pattern, ne, tec, (int)h->R, h->Na, h->Nt, h->Nd, h->Ns,
+                                         h->Nsp, stages, h->nz, h->ny * h->nz);
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
 }
@@ -326,37 +402,36 @@ static int forwardprojector_apply(iono_forwardprojector_t h, const double *field
         CU_CHECK(cudaMemsetAsync(tec_out, 0, (size_t)h->R * sizeof(double), st));
         return IONO_OK;
     }
-    // 32 warps x 64-sample chunks: the kernel waits on its gathers (long-scoreboard stalls), so more warps per SM
-    // beat longer chunks -- 1.18 ms against 1.26 ms for 24 x 128 at the LOFAR case (profiles/r02_kernel_bench.json)
-    int warps = 32, stages = 2, chunk = 64;
+    // 32 warps x 64-sample stages: the kernel waits on its gathers (long-scoreboard stalls), so more warps per SM
+    // beat longer chunks (profiles/r02_kernel_bench.json)
+    int warps = 32, stages = 2;
     const char *e;
     if ((e = getenv("IONO_PREP_WARPS"))) warps = atoi(e);
     if ((e = getenv("IONO_PREP_STAGES"))) stages = atoi(e);
-    if ((e = getenv("IONO_PREP_CHUNK"))) chunk = atoi(e);
     if (warps < 1) warps = 1;
     if (warps > 32) warps = 32;
     if (stages < 2) stages = 2;
     if (stages > 8) stages = 8;
-    if (chunk != 64) chunk = 128;
-    const size_t stage_bytes = chunk == 64 ? PreparedStage<64>::BYTES : PreparedStage<128>::BYTES;
+    const size_t stage_bytes = h->factored ? PreparedStage<true>::BYTES : PreparedStage<false>::BYTES;
+    const size_t pat_bytes = h->factored ? ((size_t)h->Ns * 8 + 127) / 128 * 128 : 0;
     auto smem_for = [&](int w) {
-        return (((size_t)w * stages * sizeof(uint64_t)) + 127) / 128 * 128 + (size_t)w * stages * stage_bytes;
+        return pat_bytes + (((size_t)w * stages * sizeof(uint64_t)) + 127) / 128 * 128 + (size_t)w * stages * stage_bytes;
     };
     while (warps > 4 && smem_for(warps) > 227 * 1024) warps -= 4;
     const size_t smem = smem_for(warps);
     if (smem > 227 * 1024) return fail(IONO_EBADARG, "prepared sweep: shared-memory configuration exceeds 227 KB");
-    const bool bulk = !getenv("IONO_SWEEP_NO_BULK");   // rows are padded to 16 bytes, cudaMalloc bases are aligned
+    const bool bulk = !getenv("IONO_SWEEP_NO_BULK");   // blocks are multiples of 16 bytes, cudaMalloc bases are aligned
     const int n_bundles = (int)((h->R + warps - 1) / warps);
     int ctas = sm_count();
     if (ctas > n_bundles) ctas = n_bundles;
-#define IONO_PREP_DISPATCH(CC, B)                                                                                \
+#define IONO_PREP_DISPATCH(F, B)                                                                                \
     do {                                                                                                         \
-        if (warps > 24) return launch_prepared_t<CC, B, 1024, LAYOUT>(h, field, tec_out, warps, stages, smem, ctas, st); \
-        if (warps > 16) return launch_prepared_t<CC, B, 768, LAYOUT>(h, field, tec_out, warps, stages, smem, ctas, st);  \
-        return launch_prepared_t<CC, B, 512, LAYOUT>(h, field, tec_out, warps, stages, smem, ctas, st);          \
+        if (warps > 24) return launch_prepared_t<F, B, 1024, LAYOUT>(h, field, tec_out, warps, stages, smem, ctas, st); \
+        if (warps > 16) return launch_prepared_t<F, B, 768, LAYOUT>(h, field, tec_out, warps, stages, smem, ctas, st);  \
+        return launch_prepared_t<F, B, 512, LAYOUT>(h, field, tec_out, warps, stages, smem, ctas, st);          \
     } while (0)
-    if (chunk == 64) { if (bulk) IONO_PREP_DISPATCH(64, true); else IONO_PREP_DISPATCH(64, false); }
-    else             { if (bulk) IONO_PREP_DISPATCH(128, true); else IONO_PREP_DISPATCH(128, false); }
+    if (h->factored) { if (bulk) IONO_PREP_DISPATCH(true, true); else IONO_PREP_DISPATCH(true, false); }
+    else             { if (bulk) IONO_PREP_DISPATCH(false, true); else IONO_PREP_DISPATCH(false, false); }
 #undef IONO_PREP_DISPATCH
 }
 

@@ -96,6 +96,7 @@ class ForwardProjector(object):
                   ctypes.byref(h), ctypes.c_void_p(oob.data_ptr()), _lib.stream_ptr())
         self.handle = h
         self.nbytes = int(lib.iono_forwardprojector_bytes(h))
+        self.factored = bool(lib.iono_forwardprojector_factored(h))   # Simpson weights stored as pattern x per-ray factor
         if check_bounds and int(oob.item()) != 0:
             raise ValueError("One of the requested xi is out of bounds (%d ray samples outside the grid)"
                              % int(oob.item()))

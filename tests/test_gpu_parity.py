@@ -766,7 +766,7 @@ def test_gaussian_adjoint_vs_oracle(ib, Ns, Nk):
 
 @pytest.mark.parametrize("Ns", [2, 3, 4, 5, 30, 31, 64, 65, 66, 127, 128, 130, 200, 257])
 @pytest.mark.parametrize("uniform", [True, False])
-def test_forward_projector_bit_identical_to_sweep(ib, Ns, uniform):
+def test_forward_projector_bit_identical_to_sweep(ib, Ns, uniform, monkeypatch):
     """The prepared forward derives cell, fractions and weights with the sweep's own device functions and
     sums in the same order: TEC must be bit-identical, for every Ns (padding to 4), both grid kinds."""
     import torch
@@ -775,7 +775,11 @@ def test_forward_projector_bit_identical_to_sweep(ib, Ns, uniform):
     rays[..., 3, :] = rays[..., 3, :] + 0.3 * np.sin(rays[..., 3, :] / 50.)
     m_tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
     rays_d = torch.as_tensor(rays).cuda()
+    if Ns == 2:       # two samples: the weights are (h/2, h/2) whatever s is, i.e. always a pattern x a factor
+        monkeypatch.setenv("IONO_PREP_FACTOR", "0")
     fp = ib.ForwardProjector(rays_d, m_tci)
+    # the perturbed arc lengths above are not a common pattern x a per-ray factor: per-sample weights, 36 B
+    assert not fp.factored
     assert fp.nbytes == rays_d.shape[0] * rays_d.shape[1] * rays_d.shape[2] * ((Ns + 3) // 4 * 4) * 36
     dtec0, tec0 = ib.forward_equation(rays_d, P["K_ne"], m_tci, 2, return_tec=True)
     dtec1, tec1 = ib.forward_equation(rays_d, P["K_ne"], m_tci, 2, return_tec=True, projector=fp)
@@ -784,8 +788,37 @@ def test_forward_projector_bit_identical_to_sweep(ib, Ns, uniform):
     assert relerr(tec1.cpu().numpy(), ref_tec) < TOL
 
 
-@pytest.mark.parametrize("env", [{"IONO_SWEEP_NO_BULK": "1"}, {"IONO_PREP_CHUNK": "64"}, {"IONO_PREP_WARPS": "32"},
-                                 {"IONO_PREP_WARPS": "5", "IONO_PREP_STAGES": "3"}])
+@pytest.mark.parametrize("Ns", [2, 3, 4, 5, 31, 64, 65, 100, 128, 130, 257])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_forward_projector_factored_weights(ib, Ns, uniform, monkeypatch):
+    """Rays made by the casting kernels have s = linspace: the Simpson weights are one pattern x a per-ray factor,
+    the operator stores 28 B per sample and agrees with the stateless sweep to rounding (not bitwise: the weight
+    is re-associated); IONO_PREP_FACTOR=0 keeps per-sample weights and bitwise equality."""
+    import torch
+    P = small_problem(900 + Ns, 5, 3, 4, Ns, 14, 12, 16, uniform=uniform)
+    m_tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    rays = ib.cast_ray((torch.as_tensor(P["origins"]).cuda(), torch.as_tensor(P["directions"]).cuda()),
+                       ib.Fermat(m_tci), P["tmax"], Ns)
+    fp = ib.ForwardProjector(rays, m_tci)
+    assert fp.factored
+    R = rays.shape[0] * rays.shape[1] * rays.shape[2]
+    assert fp.nbytes == R * ((Ns + 3) // 4 * 4) * 28 + (R + Ns) * 8
+    tec0 = ib.forward_equation(rays, P["K_ne"], m_tci, 2, return_tec=True)[1]
+    tec1 = ib.forward_equation(rays, P["K_ne"], m_tci, 2, return_tec=True, projector=fp)[1]
+    assert relerr(tec1.cpu().numpy(), tec0.cpu().numpy()) < 2e-13
+    ref_tec = O.tec(rays.cpu().numpy(), P["xvec"], P["yvec"], P["zvec"], O.ne_from_m(P["m"], P["K_ne"]))
+    assert relerr(tec1.cpu().numpy(), ref_tec) < TOL
+    monkeypatch.setenv("IONO_PREP_FACTOR", "0")
+    fp0 = ib.ForwardProjector(rays, m_tci)
+    monkeypatch.delenv("IONO_PREP_FACTOR")
+    assert not fp0.factored
+    assert torch.equal(ib.forward_equation(rays, P["K_ne"], m_tci, 2, return_tec=True, projector=fp0)[1], tec0)
+
+
+@pytest.mark.parametrize("env", [{"IONO_SWEEP_NO_BULK": "1"}, {"IONO_PREP_FACTOR": "0"}, {"IONO_PREP_WARPS": "32"},
+                                 {"IONO_PREP_WARPS": "5", "IONO_PREP_STAGES": "3"},
+                                 {"IONO_PREP_FACTOR": "0", "IONO_SWEEP_NO_BULK": "1"},
+                                 {"IONO_PREP_FACTOR": "0", "IONO_PREP_WARPS": "7", "IONO_PREP_STAGES": "4"}])
 def test_forward_projector_launch_variants(ib, env, monkeypatch):
     import torch
     for k, v in env.items():
@@ -798,7 +831,11 @@ def test_forward_projector_launch_variants(ib, env, monkeypatch):
     for k in env:
         monkeypatch.delenv(k)
     b = ib.forward_equation(rays, P["K_ne"], m_tci, 0)
-    assert torch.equal(a, b)
+    if fp.factored:
+        assert env.get("IONO_PREP_FACTOR") != "0"
+        assert relerr(a.cpu().numpy(), b.cpu().numpy()) < 1e-12      # dTEC: differences of TECs equal to ~1e-14
+    else:
+        assert torch.equal(a, b)
 
 
 def test_forward_projector_edges(ib):
@@ -822,7 +859,7 @@ def test_forward_projector_edges(ib):
     m = torch.as_tensor(P["m"]).cuda()
     pa = InversionProblem(rays, P["K_ne"], m_tci, 0, dobs, C, prepared=True)
     pb = InversionProblem(rays, P["K_ne"], m_tci, 0, dobs, C, prepared=False)
-    assert torch.equal(pa.forward(m), pb.forward(m))
+    assert relerr(pa.forward(m).cpu().numpy(), pb.forward(m).cpu().numpy()) < 1e-12    # (factored weights: not bitwise)
 
 
 @pytest.mark.parametrize("shape", [(20, 3, 16, 64, 40, 36, 64), (6, 40, 5, 30, 24, 20, 30), (3, 1, 2, 9, 10, 9, 11)])
@@ -889,7 +926,9 @@ def test_forward_quads_bit_identical_to_plain_layout(ib, Ns, uniform, monkeypatc
     ne = _ne_from_m(m_dev, P["K_ne"])
     monkeypatch.setenv("IONO_FWD_LAYOUT", "plain")
     t_plain = tec_from_ne(rays, tci.grid(), ne)
+    monkeypatch.setenv("IONO_PREP_FACTOR", "0")      # per-sample weights: bitwise equal to the sweep
     fp = ib.ForwardProjector(rays, tci)
+    monkeypatch.delenv("IONO_PREP_FACTOR")
     p_plain = fp.tec(ne)
     monkeypatch.setenv("IONO_FWD_LAYOUT", "quads")
     t_quads = tec_from_ne(rays, tci.grid(), ne)
