@@ -32,7 +32,10 @@ struct AdjRunsParams {
 template <int AXK, bool BULK, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) adjoint_runs_kernel(const AdjRunsParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform, keeps everything derived from it
+    // (ring and barrier addresses, the producer's source pointers) in uniform registers and issues the bulk copies
+    // without a per-lane address loop
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarp = blockDim.x >> 5;
     const int nx = p.g.ax[0].n, ny = p.g.ax[1].n, nz = p.g.ax[2].n;
     // shared: [axis tables (AXK != 2)][per-warp mbarriers][per-warp rings][per-warp queues: 8 x QCAP doubles + QCAP ints]
     double2 *tabx = reinterpret_cast<double2 *>(smem_raw);
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(MAXT, 1) adjoint_runs_kernel(const AdjRunsPara
         };
         if (BULK)
             for (int t = 0; t < AR_STAGES - 1; ++t) produce(t);
+        const SimpsonCoef sk = simpson_coef(i, Ns, n_odd);      // i is fixed for the whole walk along the time axis
         int v_cur = -1;
         double a000 = 0, a001 = 0, a010 = 0, a011 = 0, a100 = 0, a101 = 0, a110 = 0, a111 = 0;
         for (int t = 0; t < Nt; ++t) {
@@ -126,8 +130,7 @@ __global__ void __launch_bounds__(MAXT, 1) adjoint_runs_kernel(const AdjRunsPara
                 const bool oob = locate3<AXK>(tabx, taby, tabz, ax, ay, az, stage[lane], stage[AR_C + lane],
                                               stage[2 * AR_C + lane], ix, iy, iz, tx, ty, tz);
                 n_oob += oob;
-                const double w = simpson_weight(i, Ns, n_odd, ss_[lane - 2], ss_[lane - 1], ss_[lane], ss_[lane + 1],
-                                                ss_[lane + 2]);
+                const double w = simpson_weight_c(sk, ss_[lane - 2], ss_[lane - 1], ss_[lane], ss_[lane + 1], ss_[lane + 2]);
                 v = (ix * ny + iy) * nz + iz;
                 const double aw = coef * w;
                 const double ax1 = aw * tx, ax0 = aw - ax1;
@@ -151,12 +154,12 @@ __global__ void __launch_bounds__(MAXT, 1) adjoint_runs_kernel(const AdjRunsPara
                 qtail += __popc(m);
                 if (qtail - qhead >= 32) drain(32);
             }
-            if (v != v_cur) {
-                v_cur = v;
-                a000 = l00; a001 = h00; a010 = l01; a011 = h01; a100 = l10; a101 = h10; a110 = l11; a111 = h11;
-            } else {
-                a000 += l00; a001 += h00; a010 += l01; a011 += h01; a100 += l10; a101 += h10; a110 += l11; a111 += h11;
-            }
+            // same cell: add; new cell: start over -- as 8 fmas with keep = 1 or 0 (fma(1, a, l) == a + l exactly)
+            const double keep = (v == v_cur) ? 1.0 : 0.0;
+            v_cur = v;
+            a000 = fma(keep, a000, l00); a001 = fma(keep, a001, h00); a010 = fma(keep, a010, l01);
+            a011 = fma(keep, a011, h01); a100 = fma(keep, a100, l10); a101 = fma(keep, a101, h10);
+            a110 = fma(keep, a110, l11); a111 = fma(keep, a111, h11);
             __syncwarp();     // the stage is free for the producer again
         }
         // end of the task: what the lanes still hold
@@ -189,8 +192,7 @@ static int launch_adjoint_runs_m(const AdjRunsParams &p, int warps, size_t smem,
 }
 template <int AXK, bool BULK>
 static int launch_adjoint_runs_t(const AdjRunsParams &p, int warps, size_t smem, int ctas, cudaStream_t st) {
-    // the kernel waits on its row stream and its reductions: more warps per SM win (2.15 ms with 16, 3.45 ms with 8 at
-    // the LOFAR case); beyond 16 warps the register budget is 80 per thread
+    // beyond 16 warps the register budget is 80 per thread
     if (warps > 16) return launch_adjoint_runs_m<AXK, BULK, 768>(p, warps, smem, ctas, st);
     return launch_adjoint_runs_m<AXK, BULK, 512>(p, warps, smem, ctas, st);
 }
@@ -205,7 +207,7 @@ static int launch_adjoint_runs(iono_grid_t grid, const double *rays, int Na, int
     const int axk = grid->exact ? 2 : (grid->uniform ? 1 : 0);
     const size_t table_bytes =
         (axk == 2) ? 0 : (((size_t)(grid->nx + grid->ny + grid->nz) * sizeof(double2)) + 127) / 128 * 128;
-    int warps = 24;
+    int warps = 20;      // 1.69 ms; 16: 1.71, 24: 1.78 at the LOFAR case (profiles/r02_kernel_bench.json)
     if (const char *e = getenv("IONO_ADJOINT_RUNS_WARPS")) { int v = atoi(e); if (v >= 1 && v <= 24) warps = v; }
     auto smem_for = [&](int w) {
         return table_bytes + (((size_t)w * AR_STAGES * sizeof(uint64_t)) + 127) / 128 * 128 +

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *
                                                                      double *__restrict__ out,
                                                                      double *__restrict__ partial) {
     extern __shared__ __align__(128) unsigned char bp_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarp = blockDim.x >> 5;   // (warp-uniform for the compiler)
     constexpr int STAGE = BP_WSEG * 12;                       // weights then ray indices
     unsigned char *mine = bp_smem + (size_t)warp * (2 * STAGE);
     uint64_t *bar = reinterpret_cast<uint64_t *>(bp_smem + (size_t)nwarp * 2 * STAGE) + warp * 2;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(256) backproject_wsegments_kernel(const int2 *
     __syncwarp();
     const uint64_t pol = policy_evict_first();
     auto issue = [&](long long seg, int buf) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(&bar[buf], STAGE);
             bulk_g2s(mine + buf * STAGE, weight + seg * BP_WSEG, BP_WSEG * 8, &bar[buf], pol);
             bulk_g2s(mine + buf * STAGE + BP_WSEG * 8, ray_idx + seg * BP_WSEG, BP_WSEG * 4, &bar[buf], pol);
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__re
                                                                  double *__restrict__ out,
                                                                  double *__restrict__ partial) {
     extern __shared__ __align__(128) unsigned char bp_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarp = blockDim.x >> 5;   // (warp-uniform for the compiler)
     constexpr int STAGE = BP_WSEG * 8 + BP_RUNREC_MAX;         // weights then the run record
     unsigned char *mine = bp_smem + (size_t)warp * (2 * STAGE);
     uint64_t *bar = reinterpret_cast<uint64_t *>(bp_smem + (size_t)nwarp * 2 * STAGE) + warp * 2;
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256) backproject_wruns_kernel(const int2 *__re
     if (gw >= nseg) return;
     const uint64_t pol = policy_evict_first();
     auto issue = [&](long long seg, int buf, unsigned long long u0, unsigned long long u1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const unsigned int rec_bytes = (unsigned int)(u1 - u0) * 16u;
             mbar_expect_tx(&bar[buf], BP_WSEG * 8 + rec_bytes);
             bulk_g2s(mine + buf * STAGE, weight + seg * BP_WSEG, BP_WSEG * 8, &bar[buf], pol);

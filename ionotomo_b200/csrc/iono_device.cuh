@@ -88,32 +88,50 @@ __device__ __forceinline__ double fast_rcp(double d) {
 //   middle of a triple : (hm+hp)^3
 //   right end          : (h0+hm)(2hm-h0) hp
 //   left end           : (hp+h3)(2hp-h3) hm
-__device__ __forceinline__ double simpson_weight(int i, int N, bool n_odd, double sm2, double sm1, double s0,
-                                                 double sp1, double sp2) {
-    double hm = s0 - sm1, hp = sp1 - s0;
-    if (i < 1) hm = hp;
-    if (i > N - 2) hp = hm;
-    const double h0 = (i >= 2) ? sm1 - sm2 : hm;
-    const double h3 = (i <= N - 3) ? sp2 - sp1 : hp;
+// The part that depends on (i, N) only is split off so that a loop over rays with i fixed evaluates it once
+// (iono_adjoint_runs.cuh); simpson_weight() is the two halves back to back, same operations in the same order.
+struct SimpsonCoef {
+    double cm, cr, cl, tp, tm;        // triple-middle / right-end / left-end factors, trapezoid multipliers of hp, hm
+    bool first, last, has_h0, has_h3;
+};
+__device__ __forceinline__ SimpsonCoef simpson_coef(int i, int N, bool n_odd) {
+    SimpsonCoef k;
+    k.first = i < 1; k.last = i > N - 2; k.has_h0 = i >= 2; k.has_h3 = i <= N - 3;
     const int par = i & 1;
-    double cm, cr, cl, trap = 0.0;
+    k.tp = 0.0; k.tm = 0.0;
     if (n_odd) {   // warp-uniform branch
-        cm = par ? 1.0 : 0.0;
-        cr = (par | (i < 2)) ? 0.0 : 1.0;
-        cl = (par | (i > N - 3)) ? 0.0 : 1.0;
+        k.cm = par ? 1.0 : 0.0;
+        k.cr = (par | (i < 2)) ? 0.0 : 1.0;
+        k.cl = (par | (i > N - 3)) ? 0.0 : 1.0;
     } else {
-        cm = (par ? (i <= N - 3) : (i >= 2)) ? 0.5 : 0.0;
-        cr = (i >= 2 + par) ? 0.5 : 0.0;
-        cl = (i <= N - 4 + par) ? 0.5 : 0.0;
-        if (i < 2 || i > N - 3)
-            trap = 0.25 * (hp * (double)((i == 0) + (i == N - 2)) + hm * (double)((i == 1) + (i == N - 1)));
+        k.cm = (par ? (i <= N - 3) : (i >= 2)) ? 0.5 : 0.0;
+        k.cr = (i >= 2 + par) ? 0.5 : 0.0;
+        k.cl = (i <= N - 4 + par) ? 0.5 : 0.0;
+        if (i < 2 || i > N - 3) {
+            k.tp = (double)((i == 0) + (i == N - 2));
+            k.tm = (double)((i == 1) + (i == N - 1));
+        }
     }
+    return k;
+}
+__device__ __forceinline__ double simpson_weight_c(const SimpsonCoef &k, double sm2, double sm1, double s0, double sp1,
+                                                   double sp2) {
+    double hm = s0 - sm1, hp = sp1 - s0;
+    if (k.first) hm = hp;
+    if (k.last) hp = hm;
+    const double h0 = k.has_h0 ? sm1 - sm2 : hm;
+    const double h3 = k.has_h3 ? sp2 - sp1 : hp;
+    const double trap = 0.25 * (hp * k.tp + hm * k.tm);      // 0 away from the ends and for odd N
     const double A = hm + hp;
-    double num = (cm * A) * (A * A);
-    num = fma(cr * (h0 + hm) * fma(2.0, hm, -h0), hp, num);
-    num = fma(cl * (hp + h3) * fma(2.0, hp, -h3), hm, num);
+    double num = (k.cm * A) * (A * A);
+    num = fma(k.cr * (h0 + hm) * fma(2.0, hm, -h0), hp, num);
+    num = fma(k.cl * (hp + h3) * fma(2.0, hp, -h3), hm, num);
     const double r = fast_rcp(6.0 * hm * hp);
     return fma(num, r, trap);
+}
+__device__ __forceinline__ double simpson_weight(int i, int N, bool n_odd, double sm2, double sm1, double s0,
+                                                 double sp1, double sp2) {
+    return simpson_weight_c(simpson_coef(i, N, n_odd), sm2, sm1, s0, sp1, sp2);
 }
 
 // ---------------------------------------------------------------------------
@@ -143,6 +161,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
+}
+// One lane of the (converged) warp.  With elect.sync the compiler knows that exactly one thread runs the guarded
+// block: a bulk copy inside it is a single UBLKCP, not a loop over the active lanes' addresses.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;

@@ -150,7 +150,10 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const unsigne
                                                                     int sx) {
     constexpr int C = PREP_C, RB = PreparedStage<FACT>::RB, SB = PreparedStage<FACT>::BYTES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform, keeps everything derived from it
+    // (ring and barrier addresses, the producer's source pointers) in uniform registers and issues the bulk copies
+    // without a per-lane address loop
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarp = blockDim.x >> 5;
     // shared: [weight pattern (FACT)][per-warp mbarriers][per-warp stages]
     const double *pat = reinterpret_cast<const double *>(smem_raw);
     unsigned int off = FACT ? ((unsigned int)Ns * 8u + 127u) / 128u * 128u : 0u;
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const unsigne
     const unsigned char *fsrc = rec + (long long)q0 * ray_bytes;
     auto produce = [&]() {
         if (fk < my_rays) {
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t bytes = (uint32_t)(min(C, Nsp - fc * C) * RB);
                 mbar_expect_tx(&bars[fs], bytes);
                 bulk_g2s(ring + fs * SB, fsrc + (long long)fc * (C * RB), bytes, &bars[fs], pol_stream);
@@ -194,6 +197,9 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const unsigne
 
     unsigned int phases = 0;   // bit s: parity to wait for on stage s
     int us = 0;                // stage to consume
+    // (t, a, d) of the slot, advanced by the digits of qstep instead of three divisions per ray
+    int rt = q0 % Nt, ra = (q0 / Nt) % Na, rd = (q0 / Nt) / Na;
+    const int st_t = qstep % Nt, st_a = (qstep / Nt) % Na, st_d = (qstep / Nt) / Na;
     for (int k = 0; k < my_rays; ++k) {
         const int q = q0 + k * qstep;
         double acc = 0.0;
@@ -231,8 +237,13 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const unsigne
         double tot = warp_sum(acc);
         if (lane == 0) {
             if (FACT) tot *= __ldg(wscale + q);
-            tec[prepared_ray_of(q, Na, Nt, Nd)] = tot;
+            tec[((long long)ra * Nt + rt) * Nd + rd] = tot;
         }
+        rt += st_t;
+        if (rt >= Nt) { rt -= Nt; ++ra; }
+        ra += st_a;
+        if (ra >= Na) { ra -= Na; ++rd; }
+        rd += st_d;
     }
 }
 
@@ -404,7 +415,8 @@ static int forwardprojector_apply(iono_forwardprojector_t h, const double *field
     }
     // 32 warps x 64-sample stages: the kernel waits on its gathers (long-scoreboard stalls), so more warps per SM
     // beat longer chunks (profiles/r02_kernel_bench.json)
-    int warps = 32, stages = 2;
+    // factored records (1792 B per stage) leave room for a third stage: 0.94 ms against 0.96 ms at the LOFAR case
+    int warps = 32, stages = h->factored ? 3 : 2;
     const char *e;
     if ((e = getenv("IONO_PREP_WARPS"))) warps = atoi(e);
     if ((e = getenv("IONO_PREP_STAGES"))) stages = atoi(e);

@@ -53,7 +53,7 @@ __device__ __forceinline__ void fill_stage(double *stage, uint64_t *bar, const d
     const int s_lo = max(c0 - 2, 0), s_hi = min(c0 + C + 2, Ns);
     double *sdst = stage + StageLayout<C>::S_OFF + (s_lo - (c0 - 2));
     if (BULK) {
-        if (lane == 0) {
+        if (elect_one()) {      // (callers are warp-converged here)
             mbar_expect_tx(bar, (uint32_t)((3 * n_c + (s_hi - s_lo)) * 8));
             bulk_g2s(stage, ray + c0, n_c * 8, bar, policy);
             bulk_g2s(stage + C, ray + Ns + c0, n_c * 8, bar, policy);
@@ -232,7 +232,10 @@ __device__ __forceinline__ double trilerp_quads(const double4 *__restrict__ q, i
 template <int MODE, int AXK, int C, bool BULK, int MAXT, int LAYOUT>
 __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    // the warp index through a shuffle: the compiler then knows it is warp-uniform, keeps everything derived from it
+    // (ring and barrier addresses, the producer's source pointers) in uniform registers and issues the bulk copies
+    // without a per-lane address loop
+    const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarp = blockDim.x >> 5;
     const int nx = p.g.ax[0].n, ny = p.g.ax[1].n, nz = p.g.ax[2].n;
     const int stages = p.stages;
 

@@ -86,15 +86,24 @@ def main():
         out["touched_quads_same_tec"] = bool(torch.equal(fp.tec_quads(q2), t_ref))
         del q2
         # launch-shape variants of the prepared forward (environment is read at every apply)
-        for name, env in (("w32_c64", {"IONO_PREP_WARPS": "32", "IONO_PREP_CHUNK": "64"}),
-                          ("w32_c64_s3", {"IONO_PREP_WARPS": "32", "IONO_PREP_CHUNK": "64", "IONO_PREP_STAGES": "3"}),
-                          ("w24_c64_s4", {"IONO_PREP_WARPS": "24", "IONO_PREP_CHUNK": "64", "IONO_PREP_STAGES": "4"}),
-                          ("w16_c128_s3", {"IONO_PREP_WARPS": "16", "IONO_PREP_CHUNK": "128", "IONO_PREP_STAGES": "3"})):
+        out["fp_factored"] = bool(fp.factored)
+        for name, env in (("w32_s2", {"IONO_PREP_WARPS": "32", "IONO_PREP_STAGES": "2"}),
+                          ("w32_s3", {"IONO_PREP_WARPS": "32", "IONO_PREP_STAGES": "3"}),
+                          ("w32_s4", {"IONO_PREP_WARPS": "32", "IONO_PREP_STAGES": "4"}),
+                          ("w24_s4", {"IONO_PREP_WARPS": "24", "IONO_PREP_STAGES": "4"})):
             os.environ.update(env)
             out["prepared_quads_" + name] = timeit(lambda: fp.tec_quads(quads, out=tec), args.reps)
             assert torch.equal(tec, t_ref)
             for k in env:
                 del os.environ[k]
+        # per-sample weights (36 B per sample) for comparison
+        os.environ["IONO_PREP_FACTOR"] = "0"
+        fp0 = ForwardProjector(rays, m_tci)
+        del os.environ["IONO_PREP_FACTOR"]
+        out["prepared_quads_unfactored"] = timeit(lambda: fp0.tec_quads(quads, out=tec), args.reps)
+        out["factored_vs_unfactored_relerr"] = float(((tec - t_ref).abs().max() / t_ref.abs().max()).item())
+        out["unfactored_equals_sweep"] = bool(torch.equal(tec, tec_from_quads(rays, grid, quads, check_bounds=False)))
+        del fp0
     dobs = ib.forward_equation(rays, K, ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_true"]), 0)
     dobs = dobs + 0.01 * torch.randn_like(dobs)
     CdCt = torch.full_like(dobs, 1e-4)
