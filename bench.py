@@ -57,8 +57,13 @@ def parse():
     ap.add_argument("--forward", default="prepared", choices=["sweep", "prepared"],
                     help="prepared: per-geometry forward projector (36 B/sample records assembled once per ray "
                          "geometry, outside the timed steps, like the binned adjoint); sweep: stateless ray sweep")
-    ap.add_argument("--adjoint", default="binned", choices=["binned", "scatter"],
-                    help="binned: pre-assembled voxel-binned gather (default); scatter: stateless fp64 atomics")
+    ap.add_argument("--adjoint", default=None, choices=["binned", "prepared", "scatter"],
+                    help="prepared: the forward projector's records applied transposed, run-aggregated fp64 reductions "
+                         "(default with --forward prepared); binned: pre-assembled voxel-binned gather, bitwise "
+                         "reproducible; scatter: stateless kernel on the rays (default with --forward sweep)")
+    ap.add_argument("--e2e-adjoint", default=None, choices=["binned", "prepared", "scatter"],
+                    help="adjoint of the host-level e2e legs (default: HostSession's own choice -- binned for full-grid "
+                         "gradients on one GPU, whose download it pipelines behind the kernel; prepared otherwise)")
     ap.add_argument("--emulate-shard", type=int, default=0,
                     help="ONE GPU: run rank 0's share of an N-way direction split through the sharded (compact "
                          "accumulator) step without the link -- what one rank of N executes; for profiling only")
@@ -367,6 +372,7 @@ def main():
                             use_graph=not args.no_graph)
     torch.cuda.synchronize()
     build_s = time.time() - t_b
+    adjoint_used = ses.adjoint_kind
 
     def fence():
         torch.cuda.synchronize()
@@ -447,7 +453,8 @@ def main():
         timed("ray_sweep_forward", lambda: tec_from_quads(ses.rays, grid, ses.quads, order=args.order,
                                                           check_bounds=False, out=ses.tec, oob=ses.oob))
     timed("residual", ses._enqueue_residual)
-    timed("binned_adjoint" if ses.bp is not None else "ray_sweep_adjoint_scatter", ses._enqueue_adjoint)
+    timed({"binned": "binned_adjoint", "prepared": "prepared_adjoint", "scatter": "ray_sweep_adjoint_scatter"}[ses.adjoint_kind],
+          ses._enqueue_adjoint)
     if ses.sharded:
         if world > 1 and args.reducer == "nccl":
             ts = []
@@ -507,7 +514,7 @@ def main():
 
         def time_host_session(active):
             hs = HostSession(None, K_ne, m_tci, i0, dobs_h, C_h, origins=origins_h, directions=directions_h,
-                             tmax=w["tmax"], Ns=w["Ns"], forward=args.forward, adjoint=args.adjoint, order=args.order,
+                             tmax=w["tmax"], Ns=w["Ns"], forward=args.forward, adjoint=args.e2e_adjoint, order=args.order,
                              use_graph=not args.no_graph, reducer=args.reducer, active_only=active)
             if not active:
                 hs.m_host.copy_(m_dev)
@@ -526,7 +533,7 @@ def main():
             dt = float(tt[0])
             res = {"value": R_total / dt, "unit": "rays/s", "h2d_bytes_per_step": int(hs.h2d_bytes_per_call),
                    "d2h_bytes_per_step": int(hs.d2h_bytes_per_call), "ms_per_step": dt * 1e3, "steps": n_steps,
-                   "misfit": S_h}
+                   "misfit": S_h, "adjoint": hs.session.adjoint_kind}
             hs.close()
             del hs
             torch.cuda.empty_cache()
@@ -582,7 +589,7 @@ def main():
         if name in ("prepared_forward", "ray_sweep_forward"):
             k.update(algorithmic_bytes=bytes_fwd, achieved_gbs=bytes_fwd / msk / 1e6, frac=bytes_fwd / msk / 1e6 / hbm,
                      rays_per_s=Rr / msk * 1e3)
-        elif name in ("binned_adjoint", "ray_sweep_adjoint_scatter"):
+        elif name in ("binned_adjoint", "prepared_adjoint", "ray_sweep_adjoint_scatter"):
             k.update(algorithmic_bytes=bytes_adj, achieved_gbs=bytes_adj / msk / 1e6, frac=bytes_adj / msk / 1e6 / hbm,
                      rays_per_s=Rr / msk * 1e3)
         if name == "peer_reduce_expand" and phases:
@@ -591,7 +598,7 @@ def main():
     kernels["cast_rays"] = {"ms": cast_ms, "algorithmic_bytes": Rr * 4 * Ns * 8, "achieved_gbs": Rr * 4 * Ns * 8 / cast_ms / 1e6,
                             "frac": Rr * 4 * Ns * 8 / cast_ms / 1e6 / hbm, "in_step": False}
     fwd_name = "prepared_forward" if "prepared_forward" in kernels else "ray_sweep_forward"
-    adj_name = "binned_adjoint" if "binned_adjoint" in kernels else "ray_sweep_adjoint_scatter"
+    adj_name = [n for n in ("binned_adjoint", "prepared_adjoint", "ray_sweep_adjoint_scatter") if n in kernels][0]
     dom = adj_name if kernels[adj_name]["ms"] >= kernels[fwd_name]["ms"] else fwd_name
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -611,7 +618,7 @@ def main():
         "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": dict(workload_config(world, nt, Nd, args.scaling), dx_km=w["dx_km"], dy_km=w["dy_km"], dz_km=w["dz_km"],
-                       ray_order=args.order, forward=args.forward, adjoint=args.adjoint,
+                       ray_order=args.order, forward=args.forward, adjoint=adjoint_used,
                        cuda_graph=not args.no_graph, reducer=(args.reducer if world > 1 else None),
                        model="resident in the session's buffer, updated there in place by the optimiser "
                              "(no per-step copy of the grid); the e2e legs upload it from the host every step"),

@@ -198,6 +198,22 @@ int iono_forwardprojector_quads_from_m_f64(iono_forwardprojector_t fp, const dou
 long long iono_forwardprojector_n_records(iono_forwardprojector_t fp);
 long long iono_forwardprojector_bytes(iono_forwardprojector_t fp);
 int iono_forwardprojector_factored(iono_forwardprojector_t fp);
+/* The transpose of the same operator (the adjoint of inversion/gradient.py:15-54 without a second copy of the
+ * matrix): acc[v] += sum_ray coef_perm[(a*Nd + d)*Nt + t] * A[ray, v], A the matrix apply() applies, coefficients in
+ * the time-fastest order iono_residual_f64 writes as coef_perm, acc the full (nx,ny,nz) grid.  The kernel walks the
+ * time axis and aggregates the contributions of consecutive time steps to the same cell in registers; the sums reach
+ * acc as fp64 reductions, so results are reproducible to rounding, not bitwise.  acc must be zero on entry at the
+ * grid nodes the operator touches (n_voxels / voxels: ascending flat indices, int32); the finish_* calls consume the
+ * accumulator at exactly those nodes and zero it again:
+ *   finish_gradient: grad[v] = k * exp(m[v]) * acc[v]                (chain rule of ne = K exp(m), k = K/1e13)
+ *   finish_compact : out[dst[i]] = acc[voxel_i]  (dst NULL: out[i])  (compact accumulator of the sharded adjoint) */
+long long iono_forwardprojector_n_voxels(iono_forwardprojector_t fp);
+int iono_forwardprojector_voxels(iono_forwardprojector_t fp, int *out, void *stream);
+int iono_forwardprojector_adjoint_f64(iono_forwardprojector_t fp, const double *coef_perm, double *acc, void *stream);
+int iono_forwardprojector_finish_gradient_f64(iono_forwardprojector_t fp, double *acc, const double *m, double k,
+                                              double *grad, void *stream);
+int iono_forwardprojector_finish_compact_f64(iono_forwardprojector_t fp, double *acc, const unsigned int *dst,
+                                             double *out, void *stream);
 int iono_forwardprojector_destroy(iono_forwardprojector_t fp);
 
 /* ---- chord-length adjoint (the reference's generation-A gradient) ----------------

@@ -91,6 +91,11 @@ SIGNATURES = {
     "iono_forwardprojector_n_records": (ctypes.c_longlong, [_vp]),
     "iono_forwardprojector_bytes": (ctypes.c_longlong, [_vp]),
     "iono_forwardprojector_factored": (ctypes.c_int, [_vp]),
+    "iono_forwardprojector_n_voxels": (ctypes.c_longlong, [_vp]),
+    "iono_forwardprojector_voxels": (ctypes.c_int, [_vp, _vp, _vp]),
+    "iono_forwardprojector_adjoint_f64": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "iono_forwardprojector_finish_gradient_f64": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_double, _vp, _vp]),
+    "iono_forwardprojector_finish_compact_f64": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "iono_forwardprojector_destroy": (_i, [_vp]),
 }
 
@@ -105,7 +110,9 @@ KERNEL_LAUNCHES = {
     "iono_backprojector_apply_f64": 4, "iono_backprojector_apply_chunks_f64": 3,
     "iono_backprojector_apply_permuted_f64": 3, "iono_backprojector_apply_gradient_f64": 3,
     "iono_backprojector_apply_compact_f64": 3, "iono_backprojector_ne_rows_f64": 1, "iono_forwardprojector_quads_from_m_f64": 1,
-    "iono_forwardprojector_create": 1, "iono_forwardprojector_apply_f64": 2, "iono_forwardprojector_apply_quads_f64": 1,
+    "iono_forwardprojector_create": 5, "iono_forwardprojector_apply_f64": 2, "iono_forwardprojector_apply_quads_f64": 1,
+    "iono_forwardprojector_adjoint_f64": 1, "iono_forwardprojector_finish_gradient_f64": 1,
+    "iono_forwardprojector_finish_compact_f64": 1,
     "iono_peer_reduce_expand_f64": 1, "iono_multi_dot_f64": 2, "iono_multi_dot3_f64": 4, "iono_lincomb_f64": 1, "iono_gather_f64": 1, "iono_scatter_set_f64": 1,
     "iono_scatter_axpy_f64": 1,
     "iono_quads_from_ne_f64": 1, "iono_ne_quads_from_m_f64": 1, "iono_tec_forward_quads_f64": 1, "iono_residual_f64": 1,

@@ -467,6 +467,7 @@ extern "C" int iono_tci_interp_f64(iono_grid_t grid, const double *M, const doub
 #include "iono_sweep.cuh"
 #include "iono_adjoint_runs.cuh"
 #include "iono_prepared.cuh"
+#include "iono_prepared_adjoint.cuh"
 #include "iono_backproject.cuh"
 #include "iono_chord.cuh"
 #include "iono_gaussian.cuh"

@@ -37,6 +37,8 @@ struct iono_forwardprojector {
     int factored;
     int *records;     // quad records (iono_device.cuh) the samples read: cells v and v + ny*nz, ascending
     long long n_records;
+    int *voxels;      // grid nodes that are a corner of a visited cell, ascending (the support of the adjoint)
+    long long n_voxels;
     long long R;
     int Na, Nt, Nd, Ns, Nsp;   // Nsp = Ns rounded up to a multiple of 4 (16-byte pieces for the bulk copies)
     int nx, ny, nz;
@@ -247,6 +249,21 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const unsigne
     }
 }
 
+// flag[u] = 1 for the grid nodes that are a corner of a cell the rays visit: `used` marks the quad records
+// r in {v, v + ny*nz}; record r covers the nodes r, r+1, r+nz, r+nz+1
+__global__ void __launch_bounds__(256) touched_nodes_kernel(const unsigned char *__restrict__ used, long long V, int ny,
+                                                            int nz, unsigned char *__restrict__ flag) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < V; u += stride) {
+        const int iz = (int)(u % nz), iy = (int)((u / nz) % ny);
+        unsigned char f = used[u];
+        if (iz >= 1) f |= used[u - 1];
+        if (iy >= 1) f |= used[u - nz];
+        if (iz >= 1 && iy >= 1) f |= used[u - nz - 1];
+        flag[u] = f ? 1 : 0;
+    }
+}
+
 // quad records of ne = k * exp(m) for the listed records only (the rays of a shard touch ~12-20 % of the grid)
 __global__ void __launch_bounds__(256) quads_list_kernel(const double *__restrict__ m, double k,
                                                           const int *__restrict__ list, long long n, int ny, int nz,
@@ -280,6 +297,7 @@ extern "C" int iono_forwardprojector_quads_from_m_f64(iono_forwardprojector_t h,
 extern "C" int iono_forwardprojector_destroy(iono_forwardprojector_t h) {
     if (!h) return IONO_OK;
     cudaFree(h->records);
+    cudaFree(h->voxels);
     cudaFree(h->rec);
     cudaFree(h->wscale);
     cudaFree(h->pattern);
@@ -318,7 +336,7 @@ extern "C" int iono_forwardprojector_create(iono_grid_t grid, const double *rays
     CU_CHECK(cudaMemsetAsync(oob_count, 0, sizeof(unsigned long long), st));
     iono_forwardprojector *h = new iono_forwardprojector();
     h->rec = nullptr; h->wscale = nullptr; h->pattern = nullptr; h->factored = 0;
-    h->records = nullptr; h->n_records = 0; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->Ns = Ns;
+    h->records = nullptr; h->n_records = 0; h->voxels = nullptr; h->n_voxels = 0; h->R = R; h->Na = Na; h->Nt = Nt; h->Nd = Nd; h->Ns = Ns;
     h->Nsp = (Ns + 3) / 4 * 4;
     h->nx = grid->nx; h->ny = grid->ny; h->nz = grid->nz;
     cudaGetDevice(&h->device);
@@ -377,6 +395,29 @@ extern "C" int iono_forwardprojector_create(iono_grid_t grid, const double *rays
         if ((e = cudaMemcpyAsync(&h->n_records, d_n, sizeof(long long), cudaMemcpyDeviceToHost, st)) != cudaSuccess ||
             (e = cudaStreamSynchronize(st)) != cudaSuccess)
             return bail("select");
+        // list of the grid nodes those records cover (ascending): the support of the adjoint
+        {
+            unsigned char *flag = nullptr;
+            if ((e = cudaMalloc(&flag, (size_t)V)) != cudaSuccess) return bail("cudaMalloc");
+            touched_nodes_kernel<<<ew_grid(V), 256, 0, st>>>(used, V, grid->ny, grid->nz, flag);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMalloc(&h->voxels, (size_t)V * sizeof(int));
+            if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(tmp, tmp_bytes, ids, flag, h->voxels, d_n, (int)V, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&h->n_voxels, d_n, sizeof(long long), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            cudaFree(flag);
+            if (e != cudaSuccess) return bail("voxel list");
+            if (h->n_voxels < V) {
+                int *small = nullptr;
+                if (cudaMalloc(&small, (size_t)(h->n_voxels > 0 ? h->n_voxels : 1) * sizeof(int)) == cudaSuccess) {
+                    cudaMemcpy(small, h->voxels, (size_t)h->n_voxels * sizeof(int), cudaMemcpyDeviceToDevice);
+                    cudaFree(h->voxels);
+                    h->voxels = small;
+                } else {
+                    cudaGetLastError();
+                }
+            }
+        }
         cudaFree(used); cudaFree(d_n); cudaFree(tmp);
         // shrink the list to its size
         if (h->n_records < V) {

@@ -73,12 +73,14 @@ def tec_from_ne(rays_dev, grid, ne_dev, order="time", check_bounds=True):
 
 
 class ForwardProjector(object):
-    """Prepared form of the TEC forward for a fixed ray geometry (``iono_forwardprojector_*``).
+    """Prepared form of the TEC forward for a fixed ray geometry (``iono_forwardprojector_*``) -- and of its
+    adjoint: the same record stream applied transposed.
 
     Build once per solve: cell index, in-cell fractions and Simpson weight of every sample are computed
-    once and streamed afterwards (36 B per sample of HBM), so ``tec(ne)`` is gathers and fmas only.  The
-    result is bit-identical to ``tec_from_ne`` on the same rays.  Raises ``ValueError`` at construction when
-    a sample lies outside the grid, as every forward on those rays would.
+    once and streamed afterwards (36 B per sample of HBM; 28 B when the weights factor into a common pattern x a
+    per-ray factor, ``self.factored``), so ``tec(ne)`` is gathers and fmas only.  With per-sample weights the
+    result is bit-identical to ``tec_from_ne`` on the same rays, with factored weights equal to ~1e-14 relative.
+    Raises ``ValueError`` at construction when a sample lies outside the grid, as every forward on those rays would.
     """
 
     def __init__(self, rays, tci, check_bounds=True):
@@ -116,6 +118,39 @@ class ForwardProjector(object):
         _lib.call("iono_forwardprojector_apply_quads_f64", self.handle, _lib.ptr(quads), _lib.ptr(tec),
                   _lib.stream_ptr())
         return tec
+
+    # ---- the transpose ------------------------------------------------------------------------------
+    @property
+    def n_voxels(self):
+        return int(_lib.load().iono_forwardprojector_n_voxels(self.handle))
+
+    def voxels(self):
+        """Flat indices of the grid nodes the operator touches (corners of visited cells), ascending, int32."""
+        out = torch.empty(max(self.n_voxels, 1), dtype=torch.int32, device=self.device)
+        _lib.call("iono_forwardprojector_voxels", self.handle, ctypes.c_void_p(out.data_ptr()), _lib.stream_ptr())
+        return out[:self.n_voxels]
+
+    def adjoint(self, coef_perm, acc):
+        """``acc[v] += sum_ray coef[ray] A[ray, v]`` with ``A`` the matrix ``tec`` applies; ``coef_perm``: the
+        coefficients in (antenna, direction, time) order as ``residual(..., want_perm=True)`` writes them; ``acc``:
+        the ``(nx,ny,nz)`` accumulator (zero where the operator touches it, see ``finish_*``)."""
+        Na, Nt, Nd = self.ray_shape
+        assert coef_perm.numel() == Na * Nt * Nd and coef_perm.is_contiguous()
+        assert tuple(acc.shape) == self.shape and acc.is_contiguous()
+        _lib.call("iono_forwardprojector_adjoint_f64", self.handle, _lib.ptr(coef_perm), _lib.ptr(acc), _lib.stream_ptr())
+        return acc
+
+    def finish_gradient(self, acc, m, k, grad):
+        """``grad[v] = k exp(m[v]) acc[v]`` and ``acc[v] = 0`` on the touched voxels (``grad`` elsewhere untouched)."""
+        _lib.call("iono_forwardprojector_finish_gradient_f64", self.handle, _lib.ptr(acc), _lib.ptr(m), float(k),
+                  _lib.ptr(grad), _lib.stream_ptr())
+        return grad
+
+    def finish_compact(self, acc, out, dst=None):
+        """``out[dst[i]] = acc[voxel_i]`` (``dst`` None: ``out[i]``) and ``acc[voxel_i] = 0``."""
+        _lib.call("iono_forwardprojector_finish_compact_f64", self.handle, _lib.ptr(acc),
+                  ctypes.c_void_p(dst.data_ptr()) if dst is not None else None, _lib.ptr(out), _lib.stream_ptr())
+        return out
 
     def __del__(self):
         try:

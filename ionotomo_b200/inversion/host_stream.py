@@ -186,6 +186,13 @@ class HostSession(object):
             assert origins is not None and directions is not None
             rays = cast_ray((_lib.to_device(origins), _lib.to_device(directions)), Fermat(m_tci), tmax,
                             Ns if Ns is not None else m_tci.nz)
+        if session_kw.get("adjoint") is None and session_kw.get("forward", "prepared") == "prepared":
+            # full-grid gradients on one GPU: the voxel-binned operator finishes the grid in voxel order, which lets the
+            # 67 MB download run behind the kernel piece by piece (_pipelined_step); otherwise the faster transposed
+            # forward operator
+            import torch.distributed as _d
+            one_gpu = not (_d.is_available() and _d.is_initialized() and _d.get_world_size() > 1)
+            session_kw["adjoint"] = "binned" if (one_gpu and not active_only and overlap_copies) else "prepared"
         self.session = DeviceSession(rays, K_ne, m_tci, i0, dobs, CdCt, **session_kw)
         s = self.session
         self.root = int(root)
@@ -194,15 +201,8 @@ class HostSession(object):
         self.active_only = bool(active_only)
         self.active_voxels = None
         if self.active_only:
-            if s.sharded:
-                idx = s.union_voxels
-            else:
-                assert s.bp is not None, "active_only needs the binned adjoint (its rows are the active voxels)"
-                nr = int(_lib.load().iono_backprojector_n_rows(s.bp.handle))
-                idx = torch.empty(max(nr, 1), dtype=torch.int32, device=s.device)
-                _lib.call("iono_backprojector_row_voxels", s.bp.handle, ctypes.c_void_p(idx.data_ptr()),
-                          _lib.stream_ptr())
-                idx = idx[:nr].contiguous()
+            idx = s.active_voxels()
+            assert idx is not None, "active_only needs a prepared adjoint (it knows the voxels the rays touch)"
             self._idx = idx
             self.active_voxels = idx.cpu().numpy().astype(np.int64)
             n = int(idx.numel())

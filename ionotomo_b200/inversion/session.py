@@ -12,8 +12,13 @@ the step as ONE CUDA graph:
     quad records of ne = K exp(m)/1e13      iono_forwardprojector_quads_from_m_f64 (touched records only)
     TEC per ray                             iono_forwardprojector_apply_quads_f64  (or the stateless sweep)
     dTEC, misfit, adjoint coefficients      iono_residual_f64
-    gradient = ne * A^T coef                iono_backprojector_ne_rows_f64 + iono_backprojector_apply_permuted_f64
-                                            (or the scatter adjoint)
+    gradient = ne * A^T coef                adjoint="binned":   iono_backprojector_ne_rows_f64 +
+                                                                iono_backprojector_apply_permuted_f64 (bitwise
+                                                                reproducible, second copy of the matrix in voxel order)
+                                            adjoint="prepared": iono_forwardprojector_adjoint_f64 + finish_gradient
+                                                                (the forward's records transposed, run-aggregated
+                                                                reductions; reproducible to rounding)
+                                            adjoint="scatter":  the stateless kernel on the rays
 
 Sharded (``torch.distributed`` initialised, world size > 1; shard the direction or time axis so that the
 reference antenna is local): the forward needs no exchange; the back-projector of every rank writes into a
@@ -34,7 +39,7 @@ from .gradient import BackProjector, backproject, residual
 
 
 class DeviceSession(object):
-    def __init__(self, rays, K_ne, m_tci, i0, dobs, CdCt, forward="prepared", adjoint="binned", order="time",
+    def __init__(self, rays, K_ne, m_tci, i0, dobs, CdCt, forward="prepared", adjoint=None, order="time",
                  use_graph=True, keep_rays=None, check_bounds=True, group=None, reducer="peer", compact=None):
         lib = _lib.load()
         self.rays = _lib.to_device(rays)
@@ -51,7 +56,13 @@ class DeviceSession(object):
         self.device = dev
         self.dobs = _lib.to_device(dobs).reshape(self.ray_shape).contiguous()
         self.CdCt = _lib.to_device(CdCt).reshape(self.ray_shape).contiguous()
-        assert forward in ("prepared", "sweep") and adjoint in ("binned", "scatter")
+        if adjoint is None:
+            # the transposed forward operator is the fastest adjoint and needs no second operator in HBM; "binned" is
+            # the bitwise-reproducible one (and the one HostSession pipelines its downloads behind)
+            adjoint = "prepared" if forward == "prepared" else "scatter"
+        assert forward in ("prepared", "sweep") and adjoint in ("binned", "prepared", "scatter")
+        assert adjoint != "prepared" or forward == "prepared", "adjoint='prepared' transposes the prepared forward"
+        self.adjoint_kind = adjoint
         self.group = group
         self.rank, self.world = sharding.world() if group is None else (dist.get_rank(group), dist.get_world_size(group))
         # compact=True on a single process: the sharded step without the link (what one rank does; profiling)
@@ -59,19 +70,22 @@ class DeviceSession(object):
         if self.world == 1 and self.sharded:
             reducer = "nccl"
         if self.sharded:
-            assert adjoint == "binned", "sharded rays: the compact accumulator is written by the binned adjoint"
+            assert adjoint in ("binned", "prepared"), "sharded rays: the compact accumulator needs a prepared adjoint"
             assert reducer in ("peer", "nccl")
         self.fp = ForwardProjector(self.rays, m_tci, check_bounds=check_bounds) if forward == "prepared" else None
         self.bp = BackProjector(self.rays, m_tci, check_bounds=check_bounds) if adjoint == "binned" else None
+        both_prepared = self.fp is not None and (self.bp is not None or adjoint == "prepared")
         if keep_rays is None:
-            keep_rays = not (self.fp is not None and self.bp is not None)
+            keep_rays = not both_prepared
         if not keep_rays:
-            assert self.fp is not None and self.bp is not None, "the stateless kernels read the rays"
+            assert both_prepared, "the stateless kernels read the rays"
             self.rays = None           # both operators are prepared: the 4 x Ns doubles per ray are not read again
         f64 = dict(dtype=torch.float64, device=dev)
         self.m = torch.empty(self.shape, **f64)                 # static input of the graph
-        self.ne = torch.empty(self.shape, **f64) if self.bp is None else None
+        self.ne = torch.empty(self.shape, **f64) if adjoint == "scatter" else None
         self.ne_rows = torch.empty(self.shape, **f64) if (self.bp is not None and not self.sharded) else None
+        # adjoint="prepared": full-grid accumulator of the reductions; zero between steps (finish_* clears what it reads)
+        self.acc_full = torch.zeros(self.shape, **f64) if adjoint == "prepared" else None
         # quad records (4 x the grid) pay while their hot part stays in L2; beyond 2^24 voxels the plain layout is used
         V = self.shape[0] * self.shape[1] * self.shape[2]
         self.use_quads = V <= (1 << 24)
@@ -83,8 +97,8 @@ class DeviceSession(object):
                 self.ne_rows = self.ne      # one buffer: the forward fills it, the apply scales with it
         self.tec = torch.empty(self.ray_shape, **f64)
         self.dtec = torch.empty(self.ray_shape, **f64)
-        self.coef = torch.empty(self.ray_shape, **f64) if self.bp is None else None
-        self.coef_perm = torch.empty(Na * Nt * Nd, **f64) if self.bp is not None else None
+        self.coef = torch.empty(self.ray_shape, **f64) if adjoint == "scatter" else None
+        self.coef_perm = torch.empty(Na * Nt * Nd, **f64) if adjoint != "scatter" else None
         self.scratch = torch.empty(int(lib.iono_residual_scratch_elems(Na, Nt, Nd)), **f64)
         self.S = torch.zeros(1, **f64)
         self.S_local = self.S
@@ -103,11 +117,16 @@ class DeviceSession(object):
     # ---- sharded set-up: common numbering of the voxels any rank touches ---------------------------
     def _setup_sharded(self, reducer):
         lib = _lib.load()
-        n_rows = int(lib.iono_backprojector_n_rows(self.bp.handle))
-        rows = torch.empty(max(n_rows, 1), dtype=torch.int32, device=self.device)
-        _lib.call("iono_backprojector_row_voxels", self.bp.handle, ctypes.c_void_p(rows.data_ptr()), _lib.stream_ptr())
+        if self.bp is not None:
+            n_rows = int(lib.iono_backprojector_n_rows(self.bp.handle))
+            rows = torch.empty(max(n_rows, 1), dtype=torch.int32, device=self.device)
+            _lib.call("iono_backprojector_row_voxels", self.bp.handle, ctypes.c_void_p(rows.data_ptr()),
+                      _lib.stream_ptr())
+            rows = rows[:n_rows]
+        else:
+            rows = self.fp.voxels()      # (a superset of the binned operator's rows: corners with weight exactly 0)
         V = self.shape[0] * self.shape[1] * self.shape[2]
-        self.row_dst, self.union_voxels, self.n_union = sharding.union_index(rows[:n_rows], V, self.group)
+        self.row_dst, self.union_voxels, self.n_union = sharding.union_index(rows, V, self.group)
         L = self.n_union + 1                                    # + the misfit
         self.reducer_kind = reducer
         if reducer == "peer":
@@ -170,12 +189,19 @@ class DeviceSession(object):
             # be cleared again.  (Peer reducer: the accumulator is only ever read by the peers; the apply overwrites
             # this rank's rows with plain stores and the others stay zero from the allocation.)
             _lib.call("iono_zero_f64", _lib.ptr(self.acc_c), self.acc_c.numel(), _lib.stream_ptr())
-        residual(self.tec, self.dobs, self.CdCt, self.i0, want_coef=self.bp is None, want_perm=self.bp is not None,
+        residual(self.tec, self.dobs, self.CdCt, self.i0, want_coef=self.coef is not None,
+                 want_perm=self.coef_perm is not None,
                  out=dict(dtec=self.dtec, coef=self.coef, coef_perm=self.coef_perm, scratch=self.scratch,
                           S=self.S_local))
 
     def _enqueue_adjoint(self):
-        if self.sharded:
+        if self.adjoint_kind == "prepared":
+            self.fp.adjoint(self.coef_perm, self.acc_full)
+            if self.sharded:
+                self.fp.finish_compact(self.acc_full, self.acc_c, self.row_dst)
+            else:
+                self.fp.finish_gradient(self.acc_full, self.m, self.K_ne / TECU, self.grad)
+        elif self.sharded:
             _lib.call("iono_backprojector_apply_compact_f64", self.bp.handle, _lib.ptr(self.coef_perm),
                       ctypes.c_void_p(self.row_dst.data_ptr()), _lib.ptr(self.acc_c), 0, 16, _lib.stream_ptr())
         elif self.bp is not None:
@@ -276,6 +302,20 @@ class DeviceSession(object):
                     self._enqueue_reduce()
             self._run("adjoint", fn)
         return self.grad
+
+    def active_voxels(self):
+        """Flat int32 indices (device) of the voxels the gradient can be non-zero on -- the union over ranks when
+        sharded -- or ``None`` when no prepared operator knows them (stateless kernels: the whole grid)."""
+        if self.sharded:
+            return self.union_voxels[:self.n_union]
+        if self.bp is not None:
+            nr = int(_lib.load().iono_backprojector_n_rows(self.bp.handle))
+            idx = torch.empty(max(nr, 1), dtype=torch.int32, device=self.device)
+            _lib.call("iono_backprojector_row_voxels", self.bp.handle, ctypes.c_void_p(idx.data_ptr()), _lib.stream_ptr())
+            return idx[:nr].contiguous()
+        if self.adjoint_kind == "prepared":
+            return self.fp.voxels().contiguous()
+        return None
 
     @property
     def operator_bytes(self):

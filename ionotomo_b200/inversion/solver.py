@@ -187,15 +187,8 @@ def lbfgs_solve(problem, m0, n_iter=50, history=10, c1=1e-4, max_backtracks=20, 
     dev = ses.device
     m = _lib.to_device(m0).reshape(ses.shape).clone()
     # active voxels: rows of the operator (union over ranks when sharded)
-    if ses.sharded:
-        idx = ses.union_voxels
-    elif ses.bp is not None:
-        lib = _lib.load()
-        nr = int(lib.iono_backprojector_n_rows(ses.bp.handle))
-        idx = torch.empty(max(nr, 1), dtype=torch.int32, device=dev)
-        _lib.call("iono_backprojector_row_voxels", ses.bp.handle, ctypes.c_void_p(idx.data_ptr()), _lib.stream_ptr())
-        idx = idx[:nr].contiguous()
-    else:
+    idx = ses.active_voxels()
+    if idx is None:
         idx = torch.arange(m.numel(), dtype=torch.int32, device=dev)
     n = int(idx.numel())
     w = None

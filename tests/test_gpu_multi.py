@@ -55,9 +55,10 @@ def _worker(rank, world, port, out):
     shards = {"time": (slice(None), slice(t0, t1)), "direction": (slice(None), slice(None), slice(d0, d1))}
     grads = {}
     for axis, sl in shards.items():
-        for reducer in ("peer", "nccl"):
+        for reducer, adjoint in (("peer", "binned"), ("nccl", "binned"), ("peer", "prepared"), ("nccl", "prepared")):
             ses = DeviceSession(np.ascontiguousarray(rays[sl]), P["K_ne"], tci, i0, np.ascontiguousarray(dobs[sl]),
-                                np.ascontiguousarray(CdCt[sl]), reducer=reducer)
+                                np.ascontiguousarray(CdCt[sl]), reducer=reducer, adjoint=adjoint)
+            reducer = reducer if adjoint == "binned" else reducer + "+" + adjoint
             for k in range(4):
                 m = P["m"] + 0.03 * k * np.cos(np.arange(P["m"].size)).reshape(P["m"].shape)
                 S, grad = ses.misfit_and_gradient(torch.as_tensor(m).cuda())

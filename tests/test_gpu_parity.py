@@ -532,6 +532,11 @@ def test_host_session_api(ib):
     hs = HostSession(None, P["K_ne"], tci, 1, dobs, CdCt, origins=P["origins"], directions=P["directions"],
                      tmax=P["tmax"], Ns=30)
     ha = HostSession(rays, P["K_ne"], tci, 1, dobs, CdCt, active_only=True)
+    hb = HostSession(rays, P["K_ne"], tci, 1, dobs, CdCt, active_only=True, adjoint="binned")
+    # defaults: the full-grid session pipelines its download behind the voxel-ordered binned operator, the
+    # active-only one transposes the forward operator (its voxel list includes corners of weight exactly zero)
+    assert hs.session.adjoint_kind == "binned" and ha.session.adjoint_kind == "prepared"
+    assert np.all(np.isin(hb.active_voxels, ha.active_voxels))
     assert ha.active_voxels.size < P["m"].size and np.all(np.diff(ha.active_voxels) > 0)
     for k in range(3):
         m = P["m"] + 0.04 * k * np.sin(np.arange(P["m"].size)).reshape(P["m"].shape)
@@ -542,7 +547,10 @@ def test_host_session_api(ib):
         assert abs(S - S_ref) <= 1e-7 * S_ref and np.abs(grad - grad_ref).max() <= 1e-7 * np.abs(grad_ref).max()
         assert np.abs(dtec - g_ref).max() <= 1e-9 * np.abs(g_ref).max()
         dtec_a, S_a, grad_a = ha.misfit_and_gradient(m.reshape(-1)[ha.active_voxels])
-        assert S_a == S and np.array_equal(grad_a, grad.reshape(-1)[ha.active_voxels]) and np.array_equal(dtec_a, dtec)
+        assert S_a == S and np.array_equal(dtec_a, dtec)
+        assert np.abs(grad_a - grad.reshape(-1)[ha.active_voxels]).max() <= 1e-12 * np.abs(grad).max()   # reductions
+        dtec_b, S_b, grad_b = hb.misfit_and_gradient(m.reshape(-1)[hb.active_voxels])
+        assert S_b == S and np.array_equal(grad_b, grad.reshape(-1)[hb.active_voxels]) and np.array_equal(dtec_b, dtec)
         outside = np.ones(grad.size, dtype=bool)
         outside[ha.active_voxels] = False
         assert not grad.reshape(-1)[outside].any()                              # nothing outside the active set
@@ -1027,7 +1035,67 @@ def test_fused_residual_kernel(ib, shape, i0):
     assert coef2 is None and torch.equal(perm2, perm1) and float(S2) == float(S1)     # reproducible
 
 
-@pytest.mark.parametrize("forward,adjoint", [("prepared", "binned"), ("sweep", "scatter"), ("sweep", "binned")])
+@pytest.mark.parametrize("shape", [(5, 7, 6, 34), (3, 1, 4, 64), (2, 40, 3, 65), (4, 33, 2, 130), (1, 5, 1, 2), (2, 3, 2, 200)])
+@pytest.mark.parametrize("factored", [True, False])
+@pytest.mark.parametrize("env", [{}, {"IONO_SWEEP_NO_BULK": "1"}, {"IONO_PADJ_WARPS": "3", "IONO_PADJ_STAGES": "2"}])
+def test_forward_projector_adjoint(ib, shape, factored, env, monkeypatch):
+    """The prepared operator applied transposed (time-walking, run-aggregated reductions) == the stateless scatter
+    adjoint == the oracle's exact adjoint; <Ax, y> == <x, A^T y>; the finish kernels consume and clear the
+    accumulator on exactly the operator's voxels."""
+    import torch
+    from ionotomo_b200.inversion.gradient import backproject
+    Na, Nt, Nd, Ns = shape
+    P = small_problem(1200 + Ns + Nt, Na, Nt, Nd, Ns, 15, 13, 17)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    rays = ib.cast_ray((torch.as_tensor(P["origins"]).cuda(), torch.as_tensor(P["directions"]).cuda()),
+                       ib.Fermat(tci), P["tmax"], Ns)
+    if not factored:
+        monkeypatch.setenv("IONO_PREP_FACTOR", "0")
+    fp = ib.ForwardProjector(rays, tci)
+    monkeypatch.delenv("IONO_PREP_FACTOR", raising=False)
+    assert fp.factored == factored
+    rng = np.random.RandomState(5)
+    coef = torch.as_tensor(rng.normal(size=(Na, Nt, Nd))).cuda()
+    perm = coef.permute(0, 2, 1).contiguous().reshape(-1)
+    acc = torch.zeros(tci.nx, tci.ny, tci.nz, dtype=torch.float64, device="cuda")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    fp.adjoint(perm, acc)
+    for k in env:
+        monkeypatch.delenv(k)
+    ref = backproject(rays, tci.grid(), coef, (tci.nx, tci.ny, tci.nz))
+    scale = float(ref.abs().max())
+    assert float((acc - ref).abs().max()) <= 1e-12 * scale
+    ora = O.backproject(rays.cpu().numpy(), P["xvec"], P["yvec"], P["zvec"], coef.cpu().numpy())
+    assert np.abs(acc.cpu().numpy() - ora).max() <= 1e-11 * np.abs(ora).max()
+    # adjointness against the forward of the same operator
+    x = torch.as_tensor(rng.uniform(0.5, 2.0, size=(tci.nx, tci.ny, tci.nz))).cuda()
+    lhs = float((fp.tec(x) * coef).sum())
+    rhs = float((acc * x).sum())
+    assert abs(lhs - rhs) <= 1e-11 * max(abs(lhs), float((fp.tec(x).abs() * coef.abs()).sum()))
+    # support and the finishing kernels
+    vox = fp.voxels().long()
+    nz_idx = torch.nonzero(acc.reshape(-1)).reshape(-1)
+    assert torch.isin(nz_idx, vox).all()
+    m = torch.as_tensor(P["m"]).cuda()
+    grad = torch.full_like(acc, -7.0)
+    keep = acc.clone()
+    fp.finish_gradient(acc, m, 0.37, grad)
+    want = 0.37 * torch.exp(m) * keep
+    assert torch.allclose(grad.reshape(-1)[vox], want.reshape(-1)[vox], rtol=1e-14, atol=0)
+    mask = torch.ones(acc.numel(), dtype=torch.bool, device="cuda")
+    mask[vox] = False
+    assert bool((grad.reshape(-1)[mask] == -7.0).all()) and float(acc.abs().max()) == 0.0
+    fp.adjoint(perm, acc)
+    comp = torch.zeros(vox.numel() + 3, dtype=torch.float64, device="cuda")
+    dst = torch.arange(vox.numel(), device="cuda", dtype=torch.int32).flip(0).contiguous() + 3
+    snapshot = acc.reshape(-1)[vox].clone()
+    fp.finish_compact(acc, comp, dst)
+    assert torch.equal(comp[dst.long()], snapshot) and float(acc.abs().max()) == 0.0 and float(comp[:3].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("forward,adjoint", [("prepared", "binned"), ("prepared", "prepared"), ("sweep", "scatter"),
+                                             ("sweep", "binned")])
 @pytest.mark.parametrize("graph", [True, False])
 def test_device_session_matches_separate_calls(ib, forward, adjoint, graph):
     import torch
@@ -1052,6 +1120,29 @@ def test_device_session_matches_separate_calls(ib, forward, adjoint, graph):
         assert np.abs(grad.cpu().numpy() - grad_ref).max() < 1e-7 * np.abs(grad_ref).max()
     dtec, S2 = ses.forward(torch.as_tensor(P["m"]).cuda())
     assert np.abs(dtec.cpu().numpy() - g_true).max() < TOL * tec_scale
+
+
+@pytest.mark.parametrize("adjoint", ["binned", "prepared"])
+def test_device_session_compact_single_process(ib, adjoint):
+    """compact=True: what one rank of a sharded job runs (compact accumulator over the touched voxels + the
+    expansion kernel), on one process -- must equal the plain session."""
+    import torch
+    from ionotomo_b200.inversion.session import DeviceSession
+    P = small_problem(902, 5, 9, 4, 40, 15, 14, 18)
+    rays = O.cast_ray(P["origins"], P["directions"], P["tmax"], 40)
+    tci = ib.TriCubic(P["xvec"], P["yvec"], P["zvec"], P["m"])
+    g_true = O.forward_equation(rays, P["K_ne"], P["xvec"], P["yvec"], P["zvec"], P["m"], 1)
+    dobs = g_true + 0.01 * P["rng"].normal(size=g_true.shape)
+    CdCt = np.full(g_true.shape, 1e-4)
+    a = DeviceSession(rays, P["K_ne"], tci, 1, dobs, CdCt, adjoint=adjoint)
+    b = DeviceSession(rays, P["K_ne"], tci, 1, dobs, CdCt, adjoint=adjoint, compact=True)
+    for k in range(3):
+        m = torch.as_tensor(P["m"] + 0.05 * k * np.sin(np.arange(P["m"].size)).reshape(P["m"].shape)).cuda()
+        Sa, ga = a.misfit_and_gradient(m)
+        Sb, gb = b.misfit_and_gradient(m)
+        assert abs(float(Sa) - float(Sb)) <= 1e-13 * abs(float(Sa))
+        assert float((ga - gb).abs().max()) <= 1e-12 * float(ga.abs().max())
+    b.close()
 
 
 def test_fermat_arclength_mode(ib, golden):

@@ -21,6 +21,7 @@ ap.add_argument("--grid", type=int, nargs=3, default=[512, 512, 256])
 ap.add_argument("--nt", type=int, default=100)
 ap.add_argument("--iters", type=int, default=50)
 ap.add_argument("--scatter", action="store_true")
+ap.add_argument("--adjoint", default=None, choices=[None, "binned", "prepared"], help="default: the session's (prepared)")
 ap.add_argument("--sweep", action="store_true", help="stateless forward sweep instead of the prepared forward projector")
 ap.add_argument("--metric", default=None, choices=[None, "simpson"])
 args = ap.parse_args()
@@ -39,7 +40,7 @@ if not args.scatter and need > 0.9 * free:
 torch.cuda.synchronize()
 t0 = time.time()
 prob = DeviceSession(rays, w["K_ne"], ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_prior"]), 0, dobs, CdCt,
-                     forward="sweep" if args.sweep else "prepared", adjoint="scatter" if args.scatter else "binned",
+                     forward="sweep" if args.sweep else "prepared", adjoint="scatter" if args.scatter else args.adjoint,
                      keep_rays=args.sweep or args.scatter)
 del rays
 torch.cuda.empty_cache()
@@ -77,7 +78,7 @@ print(json.dumps({
     "iterations": len(info["S"]) - 1, "seconds": dt, "s_per_iteration": dt / max(1, len(info["S"]) - 1),
     "steady_ms_per_iteration": steady * 1e3, "forwards_per_iteration": evals_f, "gradients_per_iteration": evals_g,
     "n_forward": info["n_forward"], "n_gradient": info["n_gradient"], "operator_build_s": t_build,
-    "operator_gb": (prob.bp.nbytes / 1e9) if prob.bp else 0.0, "adjoint": "scatter" if args.scatter else "binned",
+    "operator_gb": prob.operator_bytes / 1e9, "adjoint": prob.adjoint_kind,
     "forward": "sweep" if args.sweep else "prepared", "forward_operator_gb": (prob.fp.nbytes / 1e9) if prob.fp else 0.0,
     "misfit_first": info["S"][0], "misfit_last": info["S"][-1], "mean_abs_model_error": [err0, err1],
     "peak_hbm_gb": torch.cuda.max_memory_allocated() / 1e9}))

@@ -142,6 +142,23 @@ def main():
             out["runs_vs_plain_equal"] = bool(torch.equal(ref, acc))
         del bp
     os.environ.pop("IONO_BP_RUNS", None)
+    if "padj" not in skip:
+        # the forward projector applied transposed (+ the chain-rule finish over its voxels)
+        accf = torch.zeros((nx, ny, nz), dtype=torch.float64, device="cuda")
+        gradp = torch.zeros_like(accf)
+        out["fp_voxels"] = fp.n_voxels
+        for wv, stg in (("16", "4"), ("20", "3"), ("24", "2"), ("24", "3"), ("28", "2"), ("28", "3"), ("32", "2")):
+            os.environ.update({"IONO_PADJ_WARPS": wv, "IONO_PADJ_STAGES": stg})
+            out["prepared_adjoint_w%s_s%s" % (wv, stg)] = timeit(
+                lambda: (fp.adjoint(perm, accf), fp.finish_gradient(accf, m, K / 1e13, gradp)), args.reps)
+        del os.environ["IONO_PADJ_WARPS"], os.environ["IONO_PADJ_STAGES"]
+        out["prepared_adjoint"] = timeit(
+            lambda: (fp.adjoint(perm, accf), fp.finish_gradient(accf, m, K / 1e13, gradp)), args.reps)
+        out["prepared_adjoint_kernel_only"] = timeit(lambda: fp.adjoint(perm, accf), args.reps)
+        accf.zero_()
+        if "runs1" not in skip:
+            out["prepared_adjoint_vs_binned_relerr"] = float(((gradp - ref).abs().max() / ref.abs().max()).item())
+        del accf, gradp
     if "scatter" not in skip:
         os.environ["IONO_ADJOINT_RUNS"] = "0"
         out["scatter_adjoint_plain"] = timeit(lambda: backproject(rays, grid, coef, (nx, ny, nz), check_bounds=False, out=acc),
@@ -167,9 +184,11 @@ def main():
     bf, ba = R * (4 * Ns * 8 + 8) + V * 8, R * (4 * Ns * 8 + 8) + 2 * V * 8
     for k in list(out):
         if isinstance(out[k], dict) and "ms" in out[k]:
-            if k.startswith(("sweep", "prepared")):
+            if k.startswith("prepared_adjoint"):
+                out[k]["frac"] = ba / out[k]["ms"] / 1e6 / hbm
+            elif k.startswith(("sweep", "prepared")):
                 out[k]["frac"] = bf / out[k]["ms"] / 1e6 / hbm
-            elif k.startswith(("apply", "scatter_adjoint")):
+            elif k.startswith(("apply", "scatter_adjoint", "prepared_adjoint")):
                 out[k]["frac"] = ba / out[k]["ms"] / 1e6 / hbm
             elif k.startswith("session"):
                 out[k]["frac"] = (bf + ba) / out[k]["ms"] / 1e6 / hbm
