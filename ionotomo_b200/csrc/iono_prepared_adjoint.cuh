@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
                                                                     const double *__restrict__ pattern,
                                                                     const double *__restrict__ coef_perm,
                                                                     double *__restrict__ acc, int Na, int Nt, int Nd,
-                                                                    int Ns, int Nsp, int stages, int sy, int sx) {
+                                                                    int Ns, int Nsp, int stages, int sy, int sx,
+                                                                    int tsplit) {
     constexpr int C = PREP_C, RB = PreparedStage<FACT>::RB, SB = PreparedStage<FACT>::BYTES;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), nwarp = blockDim.x >> 5;
@@ -58,7 +59,10 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
 
     const uint64_t pol_stream = policy_evict_first();
     const int chunks = (Ns + C - 1) / C;
-    const long long n_tasks = (long long)Na * Nd * chunks;
+    // a task = (slot block, chunk, time segment): the time axis is cut into `tsplit` segments when there are too few
+    // (antenna, direction, chunk) triples to fill the machine (a shard of a multi-GPU job)
+    const int tseg = (Nt + tsplit - 1) / tsplit;
+    const long long n_tasks = (long long)Na * Nd * chunks * tsplit;
     const long long ray_bytes = (long long)Nsp * RB;
     const unsigned full = 0xffffffffu;
     unsigned int phases = 0;
@@ -147,17 +151,19 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
     };
 
     for (long long task = (long long)blockIdx.x * nwarp + warp; task < n_tasks; task += (long long)gridDim.x * nwarp) {
-        const int c = (int)(task % chunks);
-        const int ad = (int)(task / chunks);            // slot block: d * Na + a (time fastest inside)
+        const int seg = (int)(task % tsplit);
+        const int c = (int)((task / tsplit) % chunks);
+        const int ad = (int)(task / ((long long)tsplit * chunks));            // slot block: d * Na + a (time fastest inside)
         const int a_ = ad % Na, d_ = ad / Na;
+        const int t_lo = seg * tseg, n_t = min(Nt, t_lo + tseg) - t_lo;       // this task: time steps t_lo .. t_lo + n_t - 1
         const int c0 = c * C;
         const int n4 = min(C, Nsp - c0), n_c = min(C, Ns - c0);
-        const long long q0 = (long long)ad * Nt;
+        const long long q0 = (long long)ad * Nt + t_lo;
         const unsigned char *src0 = rec + q0 * ray_bytes + (long long)c0 * RB;
-        const double *cp = coef_perm + ((long long)a_ * Nd + d_) * Nt;
+        const double *cp = coef_perm + ((long long)a_ * Nd + d_) * Nt + t_lo;
         const uint32_t bytes = (uint32_t)(n4 * RB);
         auto produce = [&](int t) {
-            if (t < Nt && elect_one()) {
+            if (t < n_t && elect_one()) {
                 mbar_expect_tx(&bars[t % stages], bytes);
                 bulk_g2s(ring + (t % stages) * SB, src0 + (long long)t * ray_bytes, bytes, &bars[t % stages], pol_stream);
             }
@@ -178,10 +184,10 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
             for (int e = 0; e < 8; ++e) a[s][e] = 0.0;
         }
         double cw = 0.0;
-        for (int t = 0; t < Nt; ++t) {
+        for (int t = 0; t < n_t; ++t) {
             if ((t & 31) == 0) {      // coefficients (x the per-ray weight factor) of the next 32 time steps, one per lane
                 cw = 0.0;
-                if (t + lane < Nt) {
+                if (t + lane < n_t) {
                     cw = __ldg(cp + t + lane);
                     if (FACT) cw *= __ldg(wscale + q0 + t + lane);
                 }
@@ -266,11 +272,11 @@ extern "C" int iono_forwardprojector_voxels(iono_forwardprojector_t h, int *out,
 
 template <bool FACT, bool BULK, int MAXT>
 static int launch_prepared_adjoint_t(iono_forwardprojector_t h, const double *coef_perm, double *acc, int warps,
-                                     int stages, size_t smem, int ctas, cudaStream_t st) {
+                                     int stages, size_t smem, int ctas, int tsplit, cudaStream_t st) {
     auto kern = prepared_adjoint_kernel<FACT, BULK, MAXT>;
     CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctas, warps * 32, smem, st>>>(h->rec, h->wscale, h->pattern, coef_perm, acc, h->Na, h->Nt, h->Nd, h->Ns,
-                                         h->Nsp, stages, h->nz, h->ny * h->nz);
+                                         h->Nsp, stages, h->nz, h->ny * h->nz, tsplit);
     CU_CHECK(cudaGetLastError());
     return IONO_OK;
 }
@@ -303,16 +309,26 @@ extern "C" int iono_forwardprojector_adjoint_f64(iono_forwardprojector_t h, cons
     const size_t smem = smem_for(warps, stages);
     if (smem > 227 * 1024) return fail(IONO_EBADARG, "prepared adjoint: shared-memory configuration exceeds 227 KB");
     const bool bulk = !getenv("IONO_SWEEP_NO_BULK");
-    const long long n_tasks = (long long)h->Na * h->Nd * ((h->Ns + PREP_C - 1) / PREP_C);
+    long long n_tasks = (long long)h->Na * h->Nd * ((h->Ns + PREP_C - 1) / PREP_C);
+    // IONO_PADJ_TSPLIT cuts the time axis of every task into segments (more, shorter tasks for a small shard).  Off by
+    // default: every segment ends with a whole-cell flush, and at 1/8 of the LOFAR case (0.87 tasks per warp) 2, 4 and
+    // 8 segments measured 0.186, 0.191 and 0.209 ms against 0.182 ms unsplit (profiles/README.md)
+    int tsplit = 1;
+    if ((e = getenv("IONO_PADJ_TSPLIT"))) {
+        tsplit = atoi(e);
+        if (tsplit < 1) tsplit = 1;
+        if (tsplit > h->Nt) tsplit = h->Nt;
+    }
+    n_tasks *= tsplit;
     long long want = (n_tasks + warps - 1) / warps;
     int ctas = sm_count();
     if (ctas > want) ctas = (int)want;
 #define IONO_PADJ_DISPATCH(F, B)                                                                              \
     do {                                                                                                       \
-        if (warps > 28) return launch_prepared_adjoint_t<F, B, 1024>(h, coef_perm, acc, warps, stages, smem, ctas, st); \
-        if (warps > 24) return launch_prepared_adjoint_t<F, B, 896>(h, coef_perm, acc, warps, stages, smem, ctas, st); \
-        if (warps > 16) return launch_prepared_adjoint_t<F, B, 768>(h, coef_perm, acc, warps, stages, smem, ctas, st);  \
-        return launch_prepared_adjoint_t<F, B, 512>(h, coef_perm, acc, warps, stages, smem, ctas, st);         \
+        if (warps > 28) return launch_prepared_adjoint_t<F, B, 1024>(h, coef_perm, acc, warps, stages, smem, ctas, tsplit, st); \
+        if (warps > 24) return launch_prepared_adjoint_t<F, B, 896>(h, coef_perm, acc, warps, stages, smem, ctas, tsplit, st); \
+        if (warps > 16) return launch_prepared_adjoint_t<F, B, 768>(h, coef_perm, acc, warps, stages, smem, ctas, tsplit, st);  \
+        return launch_prepared_adjoint_t<F, B, 512>(h, coef_perm, acc, warps, stages, smem, ctas, tsplit, st);         \
     } while (0)
     if (h->factored) { if (bulk) IONO_PADJ_DISPATCH(true, true); else IONO_PADJ_DISPATCH(true, false); }
     else             { if (bulk) IONO_PADJ_DISPATCH(false, true); else IONO_PADJ_DISPATCH(false, false); }

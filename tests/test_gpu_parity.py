@@ -1037,7 +1037,8 @@ def test_fused_residual_kernel(ib, shape, i0):
 
 @pytest.mark.parametrize("shape", [(5, 7, 6, 34), (3, 1, 4, 64), (2, 40, 3, 65), (4, 33, 2, 130), (1, 5, 1, 2), (2, 3, 2, 200)])
 @pytest.mark.parametrize("factored", [True, False])
-@pytest.mark.parametrize("env", [{}, {"IONO_SWEEP_NO_BULK": "1"}, {"IONO_PADJ_WARPS": "3", "IONO_PADJ_STAGES": "2"}])
+@pytest.mark.parametrize("env", [{}, {"IONO_SWEEP_NO_BULK": "1"}, {"IONO_PADJ_WARPS": "3", "IONO_PADJ_STAGES": "2"},
+                                 {"IONO_PADJ_TSPLIT": "3"}, {"IONO_PADJ_TSPLIT": "64", "IONO_PADJ_WARPS": "16"}])
 def test_forward_projector_adjoint(ib, shape, factored, env, monkeypatch):
     """The prepared operator applied transposed (time-walking, run-aggregated reductions) == the stateless scatter
     adjoint == the oracle's exact adjoint; <Ax, y> == <x, A^T y>; the finish kernels consume and clear the
