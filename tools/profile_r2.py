@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """ncu target (round 2): one launch of each hot kernel at the benchmark size -- stateless sweep (quad layout),
-prepared forward (quad layout), fused residual kernel, run-compressed binned adjoint, scatter adjoint.
+prepared forward (quad layout), fused residual kernel, prepared (transposed) adjoint, run-compressed binned adjoint,
+stateless run-aggregated adjoint (SCATTER=1).
     NT=100 ncu --set full --clock-control none --import-source on -k regex:"ray_sweep|prepared_forward|backproject_w|residual" \
         -o gpurun_out/prof python tools/profile_r2.py"""
 import os
@@ -25,6 +26,8 @@ bp = BackProjector(rays, m_tci)
 dobs = torch.zeros(rays.shape[:3], dtype=torch.float64, device="cuda")
 C = torch.full_like(dobs, 1e-4)
 from ionotomo_b200 import _lib
+acc_full = torch.zeros((256, 256, 128), dtype=torch.float64, device="cuda")
+grad_p = torch.zeros_like(acc_full)
 for _ in range(2):
     tec = tec_from_quads(rays, m_tci.grid(), quads, check_bounds=False)
     _lib.call("iono_forwardprojector_quads_from_m_f64", fp.handle, _lib.ptr(m_tci.device_M()), w["K_ne"] / 1e13,
@@ -34,6 +37,9 @@ for _ in range(2):
     _lib.call("iono_backprojector_ne_rows_f64", bp.handle, _lib.ptr(m_tci.device_M()), w["K_ne"] / 1e13, _lib.ptr(ne),
               _lib.stream_ptr())
     acc = bp.apply_permuted(perm, scale=ne)
+    # the forward operator transposed (session default adjoint) + the chain-rule finish over its voxels
+    fp.adjoint(perm, acc_full)
+    fp.finish_gradient(acc_full, m_tci.device_M(), w["K_ne"] / 1e13, grad_p)
 if os.environ.get("SCATTER", "0") == "1":
     backproject(rays, m_tci.grid(), coef, tuple(ne.shape), check_bounds=False)
 torch.cuda.synchronize()
