@@ -222,15 +222,31 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const unsigne
             const double *tx_ = stage, *ty_ = stage + n4, *tz_ = stage + 2 * n4, *w_ = FACT ? pat + c0 : stage + 3 * n4;
             const int *cell_ = reinterpret_cast<const int *>(stage + (FACT ? 3 : 4) * n4);
             const int n_c = min(C, Ns - c0);
-#pragma unroll 2
-            for (int jb = 0; jb < n_c; jb += 32) {
-                const int j = jb + lane;
-                if (j < n_c) {
+            if (n_c == C) {
+                // full chunk (every chunk when Ns is a multiple of 64): no per-sample guard, so the gathers of both
+                // samples of a lane are issued before the first interpolation waits for its corners
+                double f[C / 32];
+#pragma unroll
+                for (int u = 0; u < C / 32; ++u) {
+                    const int j = 32 * u + lane;
                     if (LAYOUT == 1)
-                        acc = fma(w_[j], trilerp_quads(reinterpret_cast<const double4 *>(field) + cell_[j], sx, tx_[j],
-                                                       ty_[j], tz_[j]), acc);
+                        f[u] = trilerp_quads(reinterpret_cast<const double4 *>(field) + cell_[j], sx, tx_[j], ty_[j], tz_[j]);
                     else
-                        acc = fma(w_[j], trilerp(field + cell_[j], sy, sx, tx_[j], ty_[j], tz_[j]), acc);
+                        f[u] = trilerp(field + cell_[j], sy, sx, tx_[j], ty_[j], tz_[j]);
+                }
+#pragma unroll
+                for (int u = 0; u < C / 32; ++u) acc = fma(w_[32 * u + lane], f[u], acc);
+            } else {
+#pragma unroll 2
+                for (int jb = 0; jb < n_c; jb += 32) {
+                    const int j = jb + lane;
+                    if (j < n_c) {
+                        if (LAYOUT == 1)
+                            acc = fma(w_[j], trilerp_quads(reinterpret_cast<const double4 *>(field) + cell_[j], sx, tx_[j],
+                                                           ty_[j], tz_[j]), acc);
+                        else
+                            acc = fma(w_[j], trilerp(field + cell_[j], sy, sx, tx_[j], ty_[j], tz_[j]), acc);
+                    }
                 }
             }
             us = (us + 1 == stages) ? 0 : us + 1;

@@ -336,6 +336,28 @@ __global__ void __launch_bounds__(MAXT, 1) ray_sweep_kernel(const SweepParams p)
             const double *sx_ = stage, *sy_ = stage + C, *sz_ = stage + 2 * C;
             const double *ss_ = stage + StageLayout<C>::S_OFF + 2;   // ss_[j] = s[c0 + j]
             const int n_c = min(C, Ns - c0);
+#ifndef IONO_SIMPSON_SHFL
+            if (MODE == 0 && n_c == C && (C % 64) == 0) {
+                // full chunk of the forward: two samples per lane without per-sample guards, so both samples' corner
+                // gathers are in flight before the first interpolation needs its values (same summation order)
+                for (int jb = 0; jb < C; jb += 64) {
+                    double f[2], w[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int j = jb + 32 * u + lane;
+                        int ix, iy, iz;
+                        double tx, ty, tz;
+                        n_oob += locate3<AXK>(tabx, taby, tabz, ax, ay, az, sx_[j], sy_[j], sz_[j], ix, iy, iz, tx, ty, tz);
+                        w[u] = simpson_weight(c0 + j, Ns, n_odd, ss_[j - 2], ss_[j - 1], ss_[j], ss_[j + 1], ss_[j + 2]);
+                        const int v = (ix * ny + iy) * nz + iz;
+                        if (LAYOUT == 1) f[u] = trilerp_quads(p.quads + v, sx, tx, ty, tz);
+                        else f[u] = trilerp(p.field + v, sy, sx, tx, ty, tz);
+                    }
+                    acc = fma(w[0], f[0], acc);
+                    acc = fma(w[1], f[1], acc);
+                }
+            } else
+#endif
 #pragma unroll 2
             for (int jb = 0; jb < n_c; jb += 32) {
                 const int j = jb + lane;
