@@ -150,7 +150,10 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
         }
     };
 
-    for (long long task = (long long)blockIdx.x * nwarp + warp; task < n_tasks; task += (long long)gridDim.x * nwarp) {
+    // tasks are dealt to the CTAs round-robin (task -> CTA task % G, then warp), so that a shard with fewer tasks than
+    // warps (1/8 of the LOFAR case: 3 100 tasks, 3 552 warps) still loads every SM equally: the kernel is bound by the
+    // instruction issue of an SM, i.e. by the number of tasks it hosts
+    for (long long task = (long long)warp * gridDim.x + blockIdx.x; task < n_tasks; task += (long long)gridDim.x * nwarp) {
         const int seg = (int)(task % tsplit);
         const int c = (int)((task / tsplit) % chunks);
         const int ad = (int)(task / ((long long)tsplit * chunks));            // slot block: d * Na + a (time fastest inside)
@@ -320,9 +323,8 @@ extern "C" int iono_forwardprojector_adjoint_f64(iono_forwardprojector_t h, cons
         if (tsplit > h->Nt) tsplit = h->Nt;
     }
     n_tasks *= tsplit;
-    long long want = (n_tasks + warps - 1) / warps;
-    int ctas = sm_count();
-    if (ctas > want) ctas = (int)want;
+    int ctas = sm_count();            // (tasks are dealt round-robin: every SM gets its share even when tasks < warps)
+    if (ctas > n_tasks) ctas = (int)n_tasks;
 #define IONO_PADJ_DISPATCH(F, B)                                                                              \
     do {                                                                                                       \
         if (warps > 28) return launch_prepared_adjoint_t<F, B, 1024>(h, coef_perm, acc, warps, stages, smem, ctas, tsplit, st); \
