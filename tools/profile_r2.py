@@ -28,7 +28,7 @@ C = torch.full_like(dobs, 1e-4)
 from ionotomo_b200 import _lib
 acc_full = torch.zeros((256, 256, 128), dtype=torch.float64, device="cuda")
 grad_p = torch.zeros_like(acc_full)
-for _ in range(2):
+for _ in range(int(os.environ.get("PASSES", "2"))):
     tec = tec_from_quads(rays, m_tci.grid(), quads, check_bounds=False)
     _lib.call("iono_forwardprojector_quads_from_m_f64", fp.handle, _lib.ptr(m_tci.device_M()), w["K_ne"] / 1e13,
               _lib.ptr(quads), _lib.stream_ptr())

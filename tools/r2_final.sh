@@ -16,8 +16,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --
     python bench.py --steps 2 --warmup 3 --emulate-shard 8 --no-e2e --no-cpu-baseline > gpurun_out/ncu_l2.log 2>&1; echo "rc=$?"
 echo "== ncu full"
 NT=100 timeout 300 python tools/profile_r2.py; echo "plain rc=$?"
-SCATTER=1 NT=100 timeout 1200 ncu --set full --clock-control none --import-source on \
-    -k regex:"ray_sweep|prepared_forward|prepared_adjoint|finish_|backproject_w|backproject_combine|residual|quads|ne_rows|adjoint_runs" -c 24 -f -o gpurun_out/final_prof_step \
+# (one pass, 12 kernels: the report must stay well under gpurun's 64 MiB return limit)
+PASSES=1 SCATTER=1 NT=100 timeout 1200 ncu --set full --clock-control none --import-source on \
+    -k regex:"ray_sweep|prepared_forward|prepared_adjoint|finish_|backproject_w|backproject_combine|residual|quads|ne_rows|adjoint_runs" -c 12 -f -o gpurun_out/final_prof_step \
     python tools/profile_r2.py > gpurun_out/ncu_final_step.log 2>&1; echo "rc=$?"
 echo "== kernel bench"
 timeout 900 python tools/kernel_bench.py > gpurun_out/final_kernel_bench.json 2> gpurun_out/final_kernel_bench.err; echo "rc=$?"
