@@ -191,3 +191,89 @@ def test_run_compressed_indices_model():
     assert n_heads < len(idx) / 4                            # the point of the format
     # record size in 16-byte units as the build computes it
     assert all((256 + 4 * len(b) + 15) // 16 * 16 <= 256 + 256 * 4 for _, b in recs)
+
+
+# ---------------------------------------------------------------- face bookkeeping of the prepared adjoint
+def face_walk_model(cells, contribs, sx, sy, grid_size):
+    """One lane-sample of ``prepared_adjoint_kernel`` (csrc/iono_prepared_adjoint.cuh, lambda ``leave``): walk the
+    time axis with the 8 corner sums ``a[4x + 2y + z]`` of the current cell in registers; on a change of cell queue
+    only the FACE that is finished -- (base, stride; 4 values) reduced at base, base+1, base+stride, base+stride+1 --
+    and carry the shared face over.  Returns the accumulator and the number of faces flushed."""
+    acc = np.zeros(grid_size)
+    faces = 0
+
+    def flush(base, stride, f):
+        nonlocal faces
+        faces += 1
+        for off, val in zip((0, 1, stride, stride + 1), f):
+            acc[base + off] += val
+
+    a = [0.0] * 8
+    vc = -1
+    for v, l in zip(cells, contribs):
+        if vc >= 0 and v != vc:
+            delta = v - vc
+            dx = 1 if abs(delta - sx) <= sy else (-1 if abs(delta + sx) <= sy else 0)
+            ry = delta - dx * sx
+            dy = 1 if ry == sy else (-1 if ry == -sy else 0)
+            jump = ry != dy * sy
+            # round A
+            if jump:
+                flush(vc, sy, a[0:4]); a[0:4] = [0.0] * 4
+            elif dx > 0:
+                flush(vc, sy, a[0:4]); a[0:4] = a[4:8]; a[4:8] = [0.0] * 4
+            elif dx < 0:
+                flush(vc + sx, sy, a[4:8]); a[4:8] = a[0:4]; a[0:4] = [0.0] * 4
+            # round B
+            vm = vc + dx * sx
+            if jump:
+                flush(vc + sx, sy, a[4:8]); a[4:8] = [0.0] * 4
+            elif dy > 0:
+                flush(vm, sx, [a[0], a[1], a[4], a[5]])
+                a[0], a[1], a[4], a[5] = a[2], a[3], a[6], a[7]
+                a[2] = a[3] = a[6] = a[7] = 0.0
+            elif dy < 0:
+                flush(vm + sy, sx, [a[2], a[3], a[6], a[7]])
+                a[2], a[3], a[6], a[7] = a[0], a[1], a[4], a[5]
+                a[0] = a[1] = a[4] = a[5] = 0.0
+        vc = v
+        a = [ai + li for ai, li in zip(a, l)]
+    if vc >= 0:                                   # end of the task: the cell is left for good
+        flush(vc, sy, a[0:4])
+        flush(vc + sx, sy, a[4:8])
+    return acc, faces
+
+
+def test_face_walk_equals_direct_accumulation():
+    """Random walks with face moves, diagonal moves, z moves and jumps: the face bookkeeping deposits exactly what
+    adding every step's 8 corner contributions directly would (up to the order of the additions), with about one
+    face per move instead of two per cell."""
+    rng = np.random.RandomState(11)
+    nx, ny, nz = 9, 8, 7
+    sy, sx = nz, ny * nz
+    for trial in range(40):
+        ix, iy, iz = rng.randint(2, nx - 3), rng.randint(2, ny - 3), rng.randint(1, nz - 2)
+        cells, contribs = [], []
+        for t in range(60):
+            r = rng.rand()
+            if r < 0.25:
+                ix += rng.choice([-1, 1])
+            elif r < 0.5:
+                iy += rng.choice([-1, 1])
+            elif r < 0.6:
+                ix += rng.choice([-1, 1]); iy += rng.choice([-1, 1])
+            elif r < 0.65:
+                iz += rng.choice([-1, 1])
+            elif r < 0.7:
+                ix, iy = rng.randint(0, nx - 1), rng.randint(0, ny - 1)
+            ix, iy, iz = int(np.clip(ix, 0, nx - 2)), int(np.clip(iy, 0, ny - 2)), int(np.clip(iz, 0, nz - 2))
+            cells.append((ix * ny + iy) * nz + iz)
+            contribs.append(list(rng.normal(size=8)))
+        acc, faces = face_walk_model(cells, contribs, sx, sy, nx * ny * nz)
+        ref = np.zeros(nx * ny * nz)
+        for v, l in zip(cells, contribs):
+            for e in range(8):
+                ref[v + (e >> 2) * sx + ((e >> 1) & 1) * sy + (e & 1)] += l[e]
+        np.testing.assert_allclose(acc, ref, rtol=0, atol=1e-12)
+        n_cells = 1 + sum(1 for p, q in zip(cells[:-1], cells[1:]) if p != q)
+        assert faces <= 2 * n_cells
