@@ -31,7 +31,8 @@ m_true = ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_true"])
 rays = ib.cast_ray((w["origins"], w["directions"]), ib.Fermat(m_true), w["tmax"], w["Ns"])
 del w["origins"], w["directions"]
 dobs = ib.forward_equation(rays, w["K_ne"], m_true, 0)
-dobs = dobs + 0.01 * torch.randn_like(dobs)
+dobs = dobs + 0.01 * torch.randn(dobs.shape, dtype=dobs.dtype, device=dobs.device,
+                                generator=torch.Generator(device="cuda").manual_seed(1234))
 CdCt = torch.full_like(dobs, 1e-4)
 free, total = torch.cuda.mem_get_info()
 need = rays.shape[0] * rays.shape[1] * rays.shape[2] * w["Ns"] * 8 * 40

@@ -105,7 +105,8 @@ def main():
         out["unfactored_equals_sweep"] = bool(torch.equal(tec, tec_from_quads(rays, grid, quads, check_bounds=False)))
         del fp0
     dobs = ib.forward_equation(rays, K, ib.TriCubic(w["xvec"], w["yvec"], w["zvec"], w["m_true"]), 0)
-    dobs = dobs + 0.01 * torch.randn_like(dobs)
+    dobs = dobs + 0.01 * torch.randn(dobs.shape, dtype=dobs.dtype, device=dobs.device,
+                                generator=torch.Generator(device="cuda").manual_seed(1234))
     CdCt = torch.full_like(dobs, 1e-4)
     fp.tec_quads(quads, out=tec)
     bufs = {}
