@@ -630,6 +630,17 @@ def test_full_size_lofar_properties(ib):
     assert abs(lhs - float((b * binned).sum())) <= 1e-10 * abs(lhs)
     assert float((binned - scat).abs().max()) <= 1e-10 * float(scat.abs().max())
     assert torch.equal(binned, bp.apply(y))              # bit-reproducible
+    del bp
+    # ... and so is the prepared operator applied transposed (factored weights, face-level run aggregation)
+    fp = ib.ForwardProjector(rays, tci)
+    assert fp.factored and fp.n_voxels >= int((scat != 0).sum())
+    tp = fp.tec(b)
+    assert float((tp - tb).abs().max()) <= 1e-12 * float(tb.abs().max())
+    acc = torch.zeros_like(scat)
+    fp.adjoint(y.permute(0, 2, 1).contiguous().reshape(-1), acc)
+    assert abs(lhs - float((b * acc).sum())) <= 1e-10 * abs(lhs)
+    assert float((acc - scat).abs().max()) <= 1e-10 * float(scat.abs().max())
+    del fp, acc
     # 4. traversal order does not change the forward bits
     assert torch.equal(tec, tec_from_ne(rays, grid, ne, order="natural"))
     # 5. dTEC of the reference antenna is exactly zero
