@@ -545,9 +545,11 @@ def main():
                       "geometry, data and operators stay resident (the reference computes its rays once per solve)")
         e2e["multi_gpu"] = ("the host program is rank 0's: its model is broadcast to the other GPUs over NVLink, the "
                             "gradient returns on rank 0 only; byte counts are rank 0's")
-        e2e_active = time_host_session(True)
-        e2e_active["api"] = ("HostSession(..., active_only=True): model and gradient as vectors over the voxels some ray "
-                             "touches (the gradient is zero elsewhere)")
+        if args.forward == "prepared" or args.e2e_adjoint == "binned":
+            e2e_active = time_host_session(True)
+            e2e_active["api"] = ("HostSession(..., active_only=True): model and gradient as vectors over the voxels some "
+                                 "ray touches (the gradient is zero elsewhere)")
+        # (stateless kernels only: no operator knows the active voxels)
         if world == 1:
             # cold call: the materialised 5 GB ray array itself comes from the host, time block by time block
             rays_h = torch.empty(rays.shape, dtype=torch.float64, pin_memory=True)
