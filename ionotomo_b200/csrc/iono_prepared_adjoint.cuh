@@ -154,9 +154,11 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
     // warps (1/8 of the LOFAR case: 3 100 tasks, 3 552 warps) still loads every SM equally: the kernel is bound by the
     // instruction issue of an SM, i.e. by the number of tasks it hosts
     for (long long task = (long long)warp * gridDim.x + blockIdx.x; task < n_tasks; task += (long long)gridDim.x * nwarp) {
+        // chunk index slowest: the far chunks of a ray move through more cells than the near ones, and with the chunk
+        // fastest a CTA of an even-sized grid would only ever see one kind
         const int seg = (int)(task % tsplit);
-        const int c = (int)((task / tsplit) % chunks);
-        const int ad = (int)(task / ((long long)tsplit * chunks));            // slot block: d * Na + a (time fastest inside)
+        const int ad = (int)((task / tsplit) % ((long long)Na * Nd));         // slot block: d * Na + a (time fastest inside)
+        const int c = (int)(task / ((long long)tsplit * Na * Nd));
         const int a_ = ad % Na, d_ = ad / Na;
         const int t_lo = seg * tseg, n_t = min(Nt, t_lo + tseg) - t_lo;       // this task: time steps t_lo .. t_lo + n_t - 1
         const int c0 = c * C;
