@@ -55,8 +55,9 @@ def parse():
                     help="N > 1: peer = fused reduce/scale/expand kernel over NVLink peer memory (default); "
                          "nccl = torch.distributed.all_reduce of the compact accumulator")
     ap.add_argument("--forward", default="prepared", choices=["sweep", "prepared"],
-                    help="prepared: per-geometry forward projector (36 B/sample records assembled once per ray "
-                         "geometry, outside the timed steps, like the binned adjoint); sweep: stateless ray sweep")
+                    help="prepared: per-geometry forward projector (28-36 B/sample records assembled once per ray "
+                         "geometry, outside the timed steps; also applied transposed as the adjoint); sweep: stateless "
+                         "ray sweep")
     ap.add_argument("--adjoint", default=None, choices=["binned", "prepared", "scatter"],
                     help="prepared: the forward projector's records applied transposed, run-aggregated fp64 reductions "
                          "(default with --forward prepared); binned: pre-assembled voxel-binned gather, bitwise "

@@ -5,9 +5,9 @@ GPUs of a node (one process per GPU).
 This is how the reference's drivers use the path: rays are computed ONCE per solve
 (``inversion_pipeline.py:195-197``), then every iteration calls the forward and the gradient with a
 new model (``tests/test_inversion.py:30-39`` ``func_and_gradient(m)``; ``bfgs_dask.py:207-340``;
-``iterative_newton.py:954-1017``).  The session therefore assembles the two prepared operators once
-(``ForwardProjector``, ``BackProjector``), keeps every buffer of the step allocated, and replays
-the step as ONE CUDA graph:
+``iterative_newton.py:954-1017``).  The session therefore assembles the prepared operator once
+(``ForwardProjector``, applied in both directions; optionally the voxel-binned ``BackProjector``), keeps every
+buffer of the step allocated, and replays the step as ONE CUDA graph:
 
     quad records of ne = K exp(m)/1e13      iono_forwardprojector_quads_from_m_f64 (touched records only)
     TEC per ray                             iono_forwardprojector_apply_quads_f64  (or the stateless sweep)
