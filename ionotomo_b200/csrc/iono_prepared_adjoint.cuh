@@ -167,11 +167,14 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
         const unsigned char *src0 = rec + q0 * ray_bytes + (long long)c0 * RB;
         const double *cp = coef_perm + ((long long)a_ * Nd + d_) * Nt + t_lo;
         const uint32_t bytes = (uint32_t)(n4 * RB);
+        // ring positions advance by counters (stages is a run-time value: t % stages would be a division per step)
+        int ps = 0, us = 0;       // stage the next produce fills / the next step consumes
         auto produce = [&](int t) {
             if (t < n_t && elect_one()) {
-                mbar_expect_tx(&bars[t % stages], bytes);
-                bulk_g2s(ring + (t % stages) * SB, src0 + (long long)t * ray_bytes, bytes, &bars[t % stages], pol_stream);
+                mbar_expect_tx(&bars[ps], bytes);
+                bulk_g2s(ring + ps * SB, src0 + (long long)t * ray_bytes, bytes, &bars[ps], pol_stream);
             }
+            ps = (ps + 1 == stages) ? 0 : ps + 1;
         };
         if (BULK)
             for (int t = 0; t < stages - 1; ++t) produce(t);
@@ -198,7 +201,6 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
                 }
             }
             const double coef = __shfl_sync(full, cw, t & 31);
-            const int us = t % stages;
             double *stage = reinterpret_cast<double *>(ring + us * SB);
             if (BULK) {
                 produce(t + stages - 1);
@@ -232,6 +234,7 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
 #pragma unroll
                 for (int e = 0; e < 8; ++e) a[s][e] += l[e];
             }
+            us = (us + 1 == stages) ? 0 : us + 1;
             __syncwarp();     // the stage is free for the producer again
         }
 #pragma unroll
