@@ -178,15 +178,17 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
         };
         if (BULK)
             for (int t = 0; t < stages - 1; ++t) produce(t);
-        bool valid[PA_SPL];
+        // lanes beyond the end of a partial chunk shadow its last sample with weight 0 (no per-sample guards in the
+        // time loop; their faces carry zeros)
+        int jj[PA_SPL];
         double pw[PA_SPL];
         int v_cur[PA_SPL];
         double a[PA_SPL][8];
 #pragma unroll
         for (int s = 0; s < PA_SPL; ++s) {
             const int j = lane + 32 * s;
-            valid[s] = j < n_c;
-            pw[s] = (FACT && valid[s]) ? __ldg(pattern + c0 + j) : 1.0;
+            jj[s] = min(j, n_c - 1);
+            pw[s] = (j < n_c) ? (FACT ? __ldg(pattern + c0 + j) : 1.0) : 0.0;
             v_cur[s] = -1;
 #pragma unroll
             for (int e = 0; e < 8; ++e) a[s][e] = 0.0;
@@ -216,13 +218,12 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
             const int *cell_ = reinterpret_cast<const int *>(stage + (FACT ? 3 : 4) * n4);
 #pragma unroll
             for (int s = 0; s < PA_SPL; ++s) {
-                const int j = lane + 32 * s;
-                int v = -1;
-                double l[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                if (valid[s]) {
-                    v = cell_[j];
+                const int j = jj[s];
+                double l[8];
+                const int v = cell_[j];
+                {
                     const double tx = tx_[j], ty = ty_[j], tz = tz_[j];
-                    const double aw = coef * (FACT ? pw[s] : w_[j]);
+                    const double aw = FACT ? coef * pw[s] : (coef * pw[s]) * w_[j];
                     const double ax1 = aw * tx, ax0 = aw - ax1;
                     const double a01 = ax0 * ty, a00 = ax0 - a01;
                     const double a11 = ax1 * ty, a10 = ax1 - a11;
