@@ -190,6 +190,32 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
         : "memory");
 }
 
+// The same three operations on 32-bit shared-window addresses computed ONCE (smem_u32 of the ring / barrier array at
+// kernel start): inside a hot loop the generic->shared conversion of a pointer with a run-time offset is otherwise
+// re-derived at every use (S2UR CgaCtaId, ULEA, ... -- a dozen uniform instructions per copy).
+__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_s(uint32_t dst, const void *src_gmem, uint32_t bytes, uint32_t bar,
+                                           uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(dst), "l"(src_gmem), "r"(bytes), "r"(bar), "l"(policy)
+        : "memory");
+}
+
 // streaming read (ray data without the bulk path): do not allocate in L1, evict first from L2
 __device__ __forceinline__ double ld_stream(const double *p, uint64_t policy) {
     double v;

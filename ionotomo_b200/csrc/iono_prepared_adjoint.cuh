@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
         for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
     if (BULK) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);     // shared-window addresses, computed once
 
     const uint64_t pol_stream = policy_evict_first();
     const int chunks = (Ns + C - 1) / C;
@@ -169,11 +170,13 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
         const uint32_t bytes = (uint32_t)(n4 * RB);
         // ring positions advance by counters (stages is a run-time value: t % stages would be a division per step)
         int ps = 0, us = 0;       // stage the next produce fills / the next step consumes
+        const unsigned char *src_next = src0;        // block of the next time step to fetch
         auto produce = [&](int t) {
             if (t < n_t && elect_one()) {
-                mbar_expect_tx(&bars[ps], bytes);
-                bulk_g2s(ring + ps * SB, src0 + (long long)t * ray_bytes, bytes, &bars[ps], pol_stream);
+                mbar_expect_tx_s(bars_s + 8u * ps, bytes);
+                bulk_g2s_s(ring_s + (uint32_t)SB * ps, src_next, bytes, bars_s + 8u * ps, pol_stream);
             }
+            src_next += ray_bytes;
             ps = (ps + 1 == stages) ? 0 : ps + 1;
         };
         if (BULK)
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_adjoint_kernel(const unsigne
             double *stage = reinterpret_cast<double *>(ring + us * SB);
             if (BULK) {
                 produce(t + stages - 1);
-                mbar_wait(&bars[us], (phases >> us) & 1u);
+                mbar_wait_s(bars_s + 8u * us, (phases >> us) & 1u);
                 phases ^= 1u << us;
             } else {
                 const unsigned char *src = src0 + (long long)t * ray_bytes;
