@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const unsigne
         for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
     if (BULK) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);     // shared-window addresses, computed once
 
     const uint64_t pol_stream = policy_evict_first();
     const int chunks = (Ns + C - 1) / C;
@@ -187,8 +188,8 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const unsigne
         if (fk < my_rays) {
             if (elect_one()) {
                 const uint32_t bytes = (uint32_t)(min(C, Nsp - fc * C) * RB);
-                mbar_expect_tx(&bars[fs], bytes);
-                bulk_g2s(ring + fs * SB, fsrc + (long long)fc * (C * RB), bytes, &bars[fs], pol_stream);
+                mbar_expect_tx_s(bars_s + 8u * fs, bytes);
+                bulk_g2s_s(ring_s + (uint32_t)SB * fs, fsrc + (long long)fc * (C * RB), bytes, bars_s + 8u * fs, pol_stream);
             }
             fs = (fs + 1 == stages) ? 0 : fs + 1;
             if (++fc == chunks) { fc = 0; ++fk; fsrc += (long long)qstep * ray_bytes; }
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(MAXT, 1) prepared_forward_kernel(const unsigne
             double *stage = reinterpret_cast<double *>(ring + us * SB);
             if (BULK) {
                 produce();
-                mbar_wait(&bars[us], (phases >> us) & 1u);
+                mbar_wait_s(bars_s + 8u * us, (phases >> us) & 1u);
                 phases ^= 1u << us;
             } else {
                 const unsigned char *src = rec + (long long)q * ray_bytes + (long long)c0 * RB;
