@@ -277,3 +277,36 @@ def test_face_walk_equals_direct_accumulation():
         np.testing.assert_allclose(acc, ref, rtol=0, atol=1e-12)
         n_cells = 1 + sum(1 for p, q in zip(cells[:-1], cells[1:]) if p != q)
         assert faces <= 2 * n_cells
+
+
+# ---------------------------------------------------------------- factored Simpson weights of the prepared operator
+def weights_factor_model(S, tol=2e-13):
+    """``weight_pattern_kernel`` + ``weight_factor_kernel`` of csrc/iono_prepared.cuh: pattern from the first ray
+    (``P = w0 * Ns / sum(w0)``), per-ray factor ``c = sum(w) / Ns``, accepted when ``|w - c P| <= tol |c P|``
+    for every sample of every ray.  ``S``: (R, Ns) abscissae.  Returns ``(factored, P, c)``."""
+    R, Ns = S.shape
+    W = np.array([[simpson_weight_model(i, Ns, s) for i in range(Ns)] for s in S])
+    P = W[0] * Ns / W[0].sum()
+    c = W.sum(axis=1) / Ns
+    want = c[:, None] * P[None, :]
+    return bool(np.all(np.abs(W - want) <= tol * np.abs(want))), P, c
+
+
+def test_weight_factoring_accepts_linspace_and_rejects_perturbed_abscissae():
+    """Rays made by the casting kernels (s a linspace of ray-dependent length, rounded) factor into a common
+    pattern x a per-ray length; the factored operator then reproduces the oracle's Simpson integral to rounding.
+    Non-uniform abscissae that differ from ray to ray do not factor (the operator keeps per-sample weights)."""
+    rng = np.random.RandomState(3)
+    for Ns in (2, 3, 4, 5, 30, 31, 64, 128):
+        smax = rng.uniform(800., 1400., size=6)
+        S = np.array([(np.linspace(-10., 1000., Ns) - (-10.)) / (1010. / sm) for sm in smax])   # (z - z0)/pz: rounded
+        ok, P, c = weights_factor_model(S)
+        assert ok, Ns
+        y = rng.normal(size=S.shape)
+        got = c * (P[None, :] * y).sum(axis=1)
+        ref = np.array([O.simps_avg(y[r], S[r]) for r in range(S.shape[0])]) if hasattr(O, "simps_avg") else \
+            (np.array([[simpson_weight_model(i, Ns, S[r]) for i in range(Ns)] for r in range(S.shape[0])]) * y).sum(axis=1)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=2e-12 * np.abs(y).max() * smax.max())
+        if Ns >= 3:
+            Sp = S + 0.3 * np.sin(S / 50.)
+            assert not weights_factor_model(Sp)[0], Ns
